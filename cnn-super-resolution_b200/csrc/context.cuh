@@ -1,0 +1,159 @@
+// Context, handle table and launch bookkeeping of the C-ABI device layer.
+// Replaces the reference's opencl::Context / RawMemoryHandle
+// (src/opencl/Context.hpp:53-66,72-299, src/opencl/Context.cpp).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/srcnn_b200.h"
+
+namespace srcnn {
+
+// thread-local last-error text (srcnn_last_error)
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+#define SRCNN_CUDA(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::srcnn::fail(SRCNN_ECUDA, "CUDA error %s (%d) in `%s` at %s:%d",             \
+                           cudaGetErrorString(_e), (int)_e, #expr, __FILE__, __LINE__);    \
+  } while (0)
+
+#define SRCNN_REQUIRE(cond, ...)                                      \
+  do {                                                                \
+    if (!(cond)) return ::srcnn::fail(SRCNN_EINVAL, __VA_ARGS__);     \
+  } while (0)
+
+#define SRCNN_TRY(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != SRCNN_OK) return _rc; \
+  } while (0)
+
+struct Allocation {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool released = false;
+  bool owned = true;  // false: wrapped caller memory (srcnn_wrap)
+};
+
+struct KernelStat {
+  uint64_t total_ns = 0;
+  uint64_t launches = 0;
+};
+
+}  // namespace srcnn
+
+struct srcnn_ctx {
+  int device = 0;
+  bool profile = false;
+  bool own_stream = true;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  std::vector<srcnn::Allocation> allocs;
+  srcnn::KernelStat stats[SRCNN_K_COUNT];
+  uint64_t launch_count = 0;
+  // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
+  void* red_scratch = nullptr;      // fixed: kRedScratchBytes
+  void* splitk_scratch = nullptr;   // grown on demand
+  size_t splitk_bytes = 0;
+  void* band_in = nullptr;          // srcnn_infer_rows_host staging (device)
+  void* band_out = nullptr;
+  size_t band_in_bytes = 0, band_out_bytes = 0;
+  // last srcnn_net whose derived (repacked) parameters are cached; see fused kernels
+  void* packed_params = nullptr;
+  size_t packed_bytes = 0;
+
+  static constexpr size_t kRedScratchBytes = 64 * 1024;
+
+  srcnn::Allocation* get(srcnn_mem h) {
+    if (h >= allocs.size()) return nullptr;
+    srcnn::Allocation* a = &allocs[h];
+    if (a->released || a->ptr == nullptr) return nullptr;
+    return a;
+  }
+};
+
+namespace srcnn {
+
+// RAII bracket around one kernel launch: counts it and, in profile mode, times it with a
+// cudaEvent pair and blocks (reference: src/opencl/Kernel.cpp:108-116).
+struct LaunchScope {
+  srcnn_ctx* ctx;
+  int id;
+  int n_launches;
+  LaunchScope(srcnn_ctx* c, int kernel_id, int launches = 1)
+      : ctx(c), id(kernel_id), n_launches(launches) {
+    if (ctx->profile) cudaEventRecord(ctx->ev_start, ctx->stream);
+  }
+  ~LaunchScope() {
+    ctx->launch_count += (uint64_t)n_launches;
+    ctx->stats[id].launches += (uint64_t)n_launches;
+    if (ctx->profile) {
+      cudaEventRecord(ctx->ev_stop, ctx->stream);
+      cudaEventSynchronize(ctx->ev_stop);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+      ctx->stats[id].total_ns += (uint64_t)((double)ms * 1e6);
+    }
+  }
+};
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(SRCNN_ECUDA, "kernel launch `%s` failed: %s (%d)", what, cudaGetErrorString(e),
+                (int)e);
+  return SRCNN_OK;
+}
+
+// resolve a handle to a typed device pointer, checking it holds at least `need` bytes
+template <class T>
+inline int resolve(srcnn_ctx* ctx, srcnn_mem h, size_t need, T** out, const char* what) {
+  Allocation* a = ctx->get(h);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle for `%s` (%llu)", what,
+                      (unsigned long long)h);
+  if (a->bytes < need)
+    return fail(SRCNN_ERANGE, "buffer `%s` too small: %zu bytes allocated, %zu needed", what,
+                a->bytes, need);
+  *out = reinterpret_cast<T*>(a->ptr);
+  return SRCNN_OK;
+}
+
+inline int ensure_scratch(srcnn_ctx* ctx, void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return SRCNN_OK;
+  if (*ptr) {
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SRCNN_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = cudaMalloc(ptr, need);
+  if (e != cudaSuccess) return fail(SRCNN_ENOMEM, "scratch allocation of %zu bytes failed", need);
+  *have = need;
+  return SRCNN_OK;
+}
+
+}  // namespace srcnn

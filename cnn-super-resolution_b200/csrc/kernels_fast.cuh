@@ -1,0 +1,81 @@
+// Shape-specialised sm_100a kernels for the SRCNN configurations (9-1-5 / 9-5-5, n1/n2 =
+// 64/32, 128/64, 32/16) and the fused launches of the hot path.  Every entry returns
+// "not handled" for shapes it has no instantiation for; the caller then uses the any-shape
+// kernels of kernels_generic.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "context.cuh"
+
+namespace srcnn {
+namespace fast {
+
+// ------------------------------------------------------------------ fused update -----
+// ConfigBasedDataPipeline::update_parameters (src/ConfigBasedDataPipeline.cpp:325-361) in
+// one launch: update_params (src/kernel/update_parameters.cl:1-33) for the three layers
+// with their own learning rates, then the six gradient accumulators are zeroed
+// (ConfigBasedDataPipeline.cpp:353-358) by the same thread that consumed them.
+struct UpdateAllArgs {
+  float *w[3], *b[3], *gw[3], *gb[3], *pw[3], *pb[3];
+  unsigned ws[3], bs[3];
+  float lr[3];
+  float momentum, decay, batch;
+};
+
+__global__ void update_all_kernel(UpdateAllArgs a) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    if (i < a.ws[l]) {
+      const float wv = a.w[l][i];
+      const float dw = a.momentum * a.pw[l][i] + a.lr[l] * a.gw[l][i] + a.decay * wv;
+      a.w[l][i] = wv - dw / a.batch;
+      a.pw[l][i] = dw;
+      a.gw[l][i] = 0.f;
+      return;
+    }
+    i -= a.ws[l];
+    if (i < a.bs[l]) {
+      const float db = a.momentum * a.pb[l][i] + a.lr[l] * a.gb[l][i];
+      a.b[l][i] -= db / a.batch;
+      a.pb[l][i] = db;
+      a.gb[l][i] = 0.f;
+      return;
+    }
+    i -= a.bs[l];
+  }
+}
+
+// one-time per-context setup (opt-in shared memory sizes etc.)
+inline int configure(srcnn_ctx* ctx) {
+  (void)ctx;
+  return SRCNN_OK;
+}
+
+// returns true when it launched
+inline bool forward_layer(srcnn_ctx*, const float*, float*, const float*, const float*, int, int,
+                          int, bool, int, int, int) {
+  return false;
+}
+
+inline bool deltas(srcnn_ctx*, const float*, const float*, float*, const float*, int, int, int,
+                   int, int, int) {
+  return false;
+}
+
+// returns 1 when it launched, 0 when not handled, <0 on error
+inline int backpropagate(srcnn_ctx*, const float*, const float*, float*, float*, int, int, int,
+                         int, int, int) {
+  return 0;
+}
+
+inline bool fused_supported(int, int, int, int, int) { return false; }
+
+inline int forward_fused(srcnn_ctx*, int, int, int, int, int, const float*, float*, const float*,
+                         const float*, const float*, const float*, const float*, const float*,
+                         int, int, int) {
+  return fail(SRCNN_EINVAL, "no fused forward instantiation");
+}
+
+}  // namespace fast
+}  // namespace srcnn

@@ -1,0 +1,693 @@
+// C-ABI entry points of the B200 SRCNN device layer (include/srcnn_b200.h).
+// Built for sm_100a only.  There is no CPU fallback anywhere in this file: every entry
+// either launches CUDA kernels on the context's stream or fails with an error code.
+#include "../../include/srcnn_b200.h"
+
+#include <algorithm>
+#include <new>
+
+#include "context.cuh"
+#include "kernels_fast.cuh"
+#include "kernels_generic.cuh"
+
+using namespace srcnn;
+
+namespace {
+
+inline int grid_1d(size_t work, int threads, int cap) {
+  size_t b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if ((size_t)cap < b) b = cap;
+  return (int)b;
+}
+
+struct Dims {
+  int w1, h1, w2, h2, w3, h3;
+};
+inline Dims net_dims(const srcnn_net* net, int w, int h) {
+  Dims d;
+  d.w1 = w - net->f1 + 1;
+  d.h1 = h - net->f1 + 1;
+  d.w2 = d.w1 - net->f2 + 1;
+  d.h2 = d.h1 - net->f2 + 1;
+  d.w3 = d.w2 - net->f3 + 1;
+  d.h3 = d.h2 - net->f3 + 1;
+  return d;
+}
+
+inline int check_net(const srcnn_net* net) {
+  SRCNN_REQUIRE(net != nullptr, "net is null");
+  SRCNN_REQUIRE(net->n1 > 0 && net->n2 > 0, "n1/n2 must be > 0");
+  SRCNN_REQUIRE(net->f1 > 0 && net->f2 > 0 && net->f3 > 0, "f1/f2/f3 must be > 0");
+  return SRCNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ======================================================================= context =====
+
+const char* srcnn_last_error(void) { return last_error_ref().c_str(); }
+
+int srcnn_ctx_create_on_stream(int device, void* cuda_stream, int profile, srcnn_ctx** out) {
+  SRCNN_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(SRCNN_ECUDA,
+                "no CUDA device available (%s) -- this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  SRCNN_REQUIRE(device >= 0 && device < count, "device %d out of range (have %d)", device, count);
+  SRCNN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SRCNN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SRCNN_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  srcnn_ctx* ctx = new (std::nothrow) srcnn_ctx();
+  if (!ctx) return fail(SRCNN_ENOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->profile = profile != 0;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cuda_stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(SRCNN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+  }
+  cudaEventCreate(&ctx->ev_start);
+  cudaEventCreate(&ctx->ev_stop);
+  e = cudaMalloc(&ctx->red_scratch, srcnn_ctx::kRedScratchBytes);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(SRCNN_ENOMEM, "scratch allocation failed: %s", cudaGetErrorString(e));
+  }
+  ctx->allocs.reserve(256);
+  int rc = fast::configure(ctx);
+  if (rc != SRCNN_OK) {
+    srcnn_ctx_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return SRCNN_OK;
+}
+
+int srcnn_ctx_create(int device, int profile, srcnn_ctx** out) {
+  return srcnn_ctx_create_on_stream(device, nullptr, profile, out);
+}
+
+int srcnn_ctx_destroy(srcnn_ctx* ctx) {
+  if (!ctx) return SRCNN_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (Allocation& a : ctx->allocs)
+    if (a.owned && !a.released && a.ptr) cudaFree(a.ptr);
+  if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+  if (ctx->splitk_scratch) cudaFree(ctx->splitk_scratch);
+  if (ctx->band_in) cudaFree(ctx->band_in);
+  if (ctx->band_out) cudaFree(ctx->band_out);
+  if (ctx->packed_params) cudaFree(ctx->packed_params);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SRCNN_OK;
+}
+
+int srcnn_block(srcnn_ctx* ctx) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SRCNN_OK;
+}
+
+int srcnn_device_info(srcnn_ctx* ctx, char* name, size_t name_len, int* sm_count,
+                      size_t* global_mem_bytes) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  cudaDeviceProp prop;
+  SRCNN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  if (name && name_len) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (global_mem_bytes) *global_mem_bytes = prop.totalGlobalMem;
+  return SRCNN_OK;
+}
+
+int srcnn_profile_get(srcnn_ctx* ctx, int kernel_id, uint64_t* total_ns, uint64_t* launches) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(kernel_id >= 0 && kernel_id < SRCNN_K_COUNT, "bad kernel id %d", kernel_id);
+  if (total_ns) *total_ns = ctx->stats[kernel_id].total_ns;
+  if (launches) *launches = ctx->stats[kernel_id].launches;
+  return SRCNN_OK;
+}
+
+int srcnn_launch_count(srcnn_ctx* ctx, uint64_t* launches) {
+  SRCNN_REQUIRE(ctx && launches, "null argument");
+  *launches = ctx->launch_count;
+  return SRCNN_OK;
+}
+
+int srcnn_stream(srcnn_ctx* ctx, void** cuda_stream) {
+  SRCNN_REQUIRE(ctx && cuda_stream, "null argument");
+  *cuda_stream = reinterpret_cast<void*>(ctx->stream);
+  return SRCNN_OK;
+}
+
+// ======================================================================= memory ======
+
+int srcnn_alloc(srcnn_ctx* ctx, size_t bytes, srcnn_mem* out) {
+  SRCNN_REQUIRE(ctx && out, "null argument");
+  SRCNN_REQUIRE(bytes > 0, "cannot allocate 0 bytes");
+  SRCNN_REQUIRE(ctx->allocs.size() < (size_t)SRCNN_NULL_MEM, "handle table full");
+  Allocation a;
+  cudaError_t e = cudaMalloc(&a.ptr, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SRCNN_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  a.bytes = bytes;
+  ctx->allocs.push_back(a);
+  *out = (srcnn_mem)(ctx->allocs.size() - 1);
+  return SRCNN_OK;
+}
+
+int srcnn_wrap(srcnn_ctx* ctx, void* device_ptr, size_t bytes, srcnn_mem* out) {
+  SRCNN_REQUIRE(ctx && out && device_ptr, "null argument");
+  SRCNN_REQUIRE(bytes > 0, "cannot wrap 0 bytes");
+  Allocation a;
+  a.ptr = device_ptr;
+  a.bytes = bytes;
+  a.owned = false;
+  ctx->allocs.push_back(a);
+  *out = (srcnn_mem)(ctx->allocs.size() - 1);
+  return SRCNN_OK;
+}
+
+int srcnn_release(srcnn_ctx* ctx, srcnn_mem mem) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  if (mem >= ctx->allocs.size()) return fail(SRCNN_EHANDLE, "invalid memory handle");
+  Allocation& a = ctx->allocs[mem];
+  if (!a.released && a.ptr && a.owned) {
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SRCNN_CUDA(cudaFree(a.ptr));
+  }
+  a.released = true;
+  a.ptr = nullptr;
+  return SRCNN_OK;
+}
+
+int srcnn_mem_size(srcnn_ctx* ctx, srcnn_mem mem, size_t* bytes) {
+  SRCNN_REQUIRE(ctx && bytes, "null argument");
+  if (mem >= ctx->allocs.size())
+    return fail(SRCNN_EHANDLE, "Invalid memory handle.Could not get RawMemoryHandle object");
+  *bytes = ctx->allocs[mem].bytes;
+  return SRCNN_OK;
+}
+
+int srcnn_mem_ptr(srcnn_ctx* ctx, srcnn_mem mem, void** device_ptr) {
+  SRCNN_REQUIRE(ctx && device_ptr, "null argument");
+  Allocation* a = ctx->get(mem);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle");
+  *device_ptr = a->ptr;
+  return SRCNN_OK;
+}
+
+int srcnn_mem_usage(srcnn_ctx* ctx, size_t* buffer_bytes) {
+  SRCNN_REQUIRE(ctx && buffer_bytes, "null argument");
+  size_t t = 0;
+  for (const Allocation& a : ctx->allocs)
+    if (!a.released && a.owned) t += a.bytes;
+  *buffer_bytes = t;
+  return SRCNN_OK;
+}
+
+int srcnn_write(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, const void* src,
+                int block) {
+  SRCNN_REQUIRE(ctx && src, "null argument");
+  Allocation* a = ctx->get(mem);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in write");
+  if (offset + bytes > a->bytes)
+    return fail(SRCNN_ERANGE, "Tried to write more then is allocated (%zu+%zu > %zu)", offset,
+                bytes, a->bytes);
+  SRCNN_CUDA(cudaMemcpyAsync((char*)a->ptr + offset, src, bytes, cudaMemcpyHostToDevice,
+                             ctx->stream));
+  if (block) SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SRCNN_OK;
+}
+
+int srcnn_read(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, void* dst,
+               int block) {
+  SRCNN_REQUIRE(ctx && dst, "null argument");
+  Allocation* a = ctx->get(mem);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in read");
+  if (offset + bytes > a->bytes)
+    return fail(SRCNN_ERANGE, "Tried to read more then is allocated (%zu+%zu > %zu)", offset,
+                bytes, a->bytes);
+  SRCNN_CUDA(cudaMemcpyAsync(dst, (const char*)a->ptr + offset, bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  if (block) SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SRCNN_OK;
+}
+
+int srcnn_copy_region(srcnn_ctx* ctx, srcnn_mem src, size_t src_offset, srcnn_mem dst,
+                      size_t dst_offset, size_t bytes) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  Allocation* s = ctx->get(src);
+  Allocation* d = ctx->get(dst);
+  if (!s || !d) return fail(SRCNN_EHANDLE, "invalid memory handle in copy");
+  if (src_offset + bytes > s->bytes)
+    return fail(SRCNN_ERANGE, "buffer copy would read after src end");
+  if (dst_offset + bytes > d->bytes)
+    return fail(SRCNN_ERANGE, "When performing buffer copy, would write after dst end");
+  SRCNN_CUDA(cudaMemcpyAsync((char*)d->ptr + dst_offset, (const char*)s->ptr + src_offset, bytes,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  return SRCNN_OK;
+}
+
+int srcnn_copy(srcnn_ctx* ctx, srcnn_mem src, srcnn_mem dst, size_t dst_offset) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  Allocation* s = ctx->get(src);
+  if (!s) return fail(SRCNN_EHANDLE, "invalid memory handle in copy");
+  return srcnn_copy_region(ctx, src, 0, dst, dst_offset, s->bytes);
+}
+
+int srcnn_fill_float(srcnn_ctx* ctx, srcnn_mem mem, float value) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  Allocation* a = ctx->get(mem);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in fill");
+  const size_t len = a->bytes / sizeof(float);
+  if (len == 0) return SRCNN_OK;
+  if (value == 0.f) {
+    SRCNN_CUDA(cudaMemsetAsync(a->ptr, 0, len * sizeof(float), ctx->stream));
+    return SRCNN_OK;
+  }
+  generic::fill_kernel<<<grid_1d(len, 256, 4 * ctx->sm_count), 256, 0, ctx->stream>>>(
+      (float*)a->ptr, value, len);
+  ctx->launch_count++;
+  return check_launch("fill");
+}
+
+int srcnn_host_alloc(size_t bytes, void** host_ptr) {
+  SRCNN_REQUIRE(host_ptr && bytes > 0, "bad argument");
+  SRCNN_CUDA(cudaHostAlloc(host_ptr, bytes, cudaHostAllocDefault));
+  return SRCNN_OK;
+}
+
+int srcnn_host_free(void* host_ptr) {
+  if (host_ptr) SRCNN_CUDA(cudaFreeHost(host_ptr));
+  return SRCNN_OK;
+}
+
+// ======================================================================= kernels =====
+
+int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W, srcnn_mem B,
+                        int k, int n, int f, int skip_relu, int in_w, int in_h, int S) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(k > 0 && n > 0 && f > 0 && S > 0, "bad layer shape k=%d n=%d f=%d S=%d", k, n, f, S);
+  SRCNN_REQUIRE(in_w >= f && in_h >= f, "input %dx%d smaller than filter %d", in_w, in_h, f);
+  const int ow = in_w - f + 1, oh = in_h - f + 1;
+  const float *pin, *pW, *pB;
+  float* pout;
+  SRCNN_TRY(resolve(ctx, in, sizeof(float) * (size_t)S * in_w * in_h * k, &pin, "layer input"));
+  SRCNN_TRY(resolve(ctx, out, sizeof(float) * (size_t)S * ow * oh * n, &pout, "layer output"));
+  SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f * f * k * n, &pW, "weights"));
+  SRCNN_TRY(resolve(ctx, B, sizeof(float) * (size_t)n, &pB, "bias"));
+  LaunchScope scope(ctx, SRCNN_K_FORWARD);
+  if (fast::forward_layer(ctx, pin, pout, pW, pB, k, n, f, !skip_relu, in_w, in_h, S))
+    return check_launch("forward(fast)");
+  generic::FwdArgs a{pin, pout, pW, pB, k, n, f, skip_relu ? 0 : 1, in_w, in_h, ow, oh, S};
+  const long long M = (long long)S * ow * oh;
+  dim3 grid((unsigned)((M + generic::TM - 1) / generic::TM), (n + generic::TN - 1) / generic::TN);
+  generic::forward_gemm_kernel<<<grid, generic::NT, 0, ctx->stream>>>(a);
+  return check_launch("forward");
+}
+
+int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
+                        int gt_w, int gt_h, int algo_w, int algo_h, int S) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
+                "bad squared_error dimensions");
+  const float *pgt, *palgo;
+  float* pt;
+  SRCNN_TRY(resolve(ctx, gt, sizeof(float) * (size_t)S * gt_w * gt_h, &pgt, "ground truth"));
+  SRCNN_TRY(resolve(ctx, algo, sizeof(float) * (size_t)S * algo_w * algo_h, &palgo, "algo result"));
+  SRCNN_TRY(resolve(ctx, target, sizeof(float), &pt, "squared error target"));
+  const size_t total = (size_t)S * algo_w * algo_h;
+  const int blocks = grid_1d(total, generic::RED_THREADS, generic::RED_MAX_BLOCKS);
+  LaunchScope scope(ctx, SRCNN_K_SQUARED_ERR, 2);
+  generic::squared_error_stage1<<<blocks, generic::RED_THREADS, 0, ctx->stream>>>(
+      pgt, palgo, (double*)ctx->red_scratch, gt_w, gt_h, algo_w, algo_h, S);
+  generic::reduce_stage2<<<1, generic::RED_THREADS, 0, ctx->stream>>>(
+      (const double*)ctx->red_scratch, blocks, pt);
+  return check_launch("squared_err");
+}
+
+int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
+                           int gt_w, int gt_h, int algo_w, int algo_h, int S) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
+                "bad last_layer_delta dimensions");
+  const float *pgt, *palgo;
+  float* pt;
+  const size_t total = (size_t)S * algo_w * algo_h;
+  SRCNN_TRY(resolve(ctx, gt, sizeof(float) * (size_t)S * gt_w * gt_h, &pgt, "ground truth"));
+  SRCNN_TRY(resolve(ctx, algo, sizeof(float) * total, &palgo, "algo result"));
+  SRCNN_TRY(resolve(ctx, target, sizeof(float) * total, &pt, "last layer delta target"));
+  LaunchScope scope(ctx, SRCNN_K_LAST_LAYER_DELTA);
+  generic::last_layer_delta_kernel<<<grid_1d(total, 256, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
+      pgt, palgo, pt, gt_w, gt_h, algo_w, algo_h, S);
+  return check_launch("last_layer_delta");
+}
+
+int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
+                 srcnn_mem target, srcnn_mem W, int n_curr, int f_next, int n_next, int out_w,
+                 int out_h, int S) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(n_curr > 0 && f_next > 0 && n_next > 0 && S > 0, "bad deltas shape");
+  SRCNN_REQUIRE(out_w >= f_next && out_h >= f_next, "layer output smaller than next filter");
+  const int nw = out_w - f_next + 1, nh = out_h - f_next + 1;
+  const float *pdn, *plo, *pW;
+  float* pt;
+  const size_t cur = (size_t)S * out_w * out_h * n_curr;
+  SRCNN_TRY(resolve(ctx, deltas_next, sizeof(float) * (size_t)S * nw * nh * n_next, &pdn, "next layer deltas"));
+  SRCNN_TRY(resolve(ctx, layer_output, sizeof(float) * cur, &plo, "layer output"));
+  SRCNN_TRY(resolve(ctx, target, sizeof(float) * cur, &pt, "deltas target"));
+  SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f_next * f_next * n_curr * n_next, &pW, "next layer weights"));
+  LaunchScope scope(ctx, SRCNN_K_DELTAS);
+  if (fast::deltas(ctx, pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h, S))
+    return check_launch("deltas(fast)");
+  generic::DeltaArgs a{pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h, nw, nh, S};
+  const long long M = (long long)S * out_w * out_h;
+  dim3 grid((unsigned)((M + generic::TM - 1) / generic::TM), (n_curr + generic::TN - 1) / generic::TN);
+  generic::deltas_gemm_kernel<<<grid, generic::NT, 0, ctx->stream>>>(a);
+  return check_launch("deltas");
+}
+
+int srcnn_backpropagate(srcnn_ctx* ctx, srcnn_mem deltas, srcnn_mem layer_input,
+                        srcnn_mem grad_w, srcnn_mem grad_b, int n, int k, int f, int out_w,
+                        int out_h, int S) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(n > 0 && k > 0 && f > 0 && S > 0 && out_w > 0 && out_h > 0, "bad backpropagate shape");
+  const int iw = out_w + f - 1, ih = out_h + f - 1;
+  const float *pd, *pin;
+  float *pgw, *pgb;
+  SRCNN_TRY(resolve(ctx, deltas, sizeof(float) * (size_t)S * out_w * out_h * n, &pd, "layer deltas"));
+  SRCNN_TRY(resolve(ctx, layer_input, sizeof(float) * (size_t)S * iw * ih * k, &pin, "layer input"));
+  SRCNN_TRY(resolve(ctx, grad_w, sizeof(float) * (size_t)f * f * k * n, &pgw, "grad_w"));
+  SRCNN_TRY(resolve(ctx, grad_b, sizeof(float) * (size_t)n, &pgb, "grad_b"));
+  LaunchScope scope(ctx, SRCNN_K_BACKPROPAGATE, 2);
+  int rc_fast = fast::backpropagate(ctx, pd, pin, pgw, pgb, n, k, f, out_w, out_h, S);
+  if (rc_fast < 0) return rc_fast;
+  if (rc_fast > 0) return check_launch("backpropagate(fast)");
+  const int Mw = f * f * k, M = Mw + 1;
+  const long long P = (long long)S * out_w * out_h;
+  const int mt = (M + generic::TM - 1) / generic::TM, nt = (n + generic::TN - 1) / generic::TN;
+  // split the pixel (reduction) dimension so the grid fills the GPU ~2x, at least 256
+  // pixels per split
+  long long splits = std::max<long long>(1, (2LL * ctx->sm_count) / std::max(1, mt * nt));
+  splits = std::min<long long>(splits, std::max<long long>(1, P / 256));
+  long long pps = (P + splits - 1) / splits;
+  pps = (pps + generic::KC - 1) / generic::KC * generic::KC;
+  splits = (P + pps - 1) / pps;
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
+                           sizeof(float) * (size_t)splits * M * n));
+  generic::BpArgs a{pd, pin, (float*)ctx->splitk_scratch, n, k, f, out_w, out_h, iw, ih, S, pps};
+  dim3 grid(mt, nt, (unsigned)splits);
+  generic::backprop_gemm_kernel<<<grid, generic::NT, 0, ctx->stream>>>(a);
+  generic::backprop_reduce_kernel<<<(M * n + 255) / 256, 256, 0, ctx->stream>>>(
+      (const float*)ctx->splitk_scratch, pgw, pgb, Mw, n, (int)splits);
+  return check_launch("backpropagate");
+}
+
+int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad_w,
+                        srcnn_mem grad_b, srcnn_mem prev_dw, srcnn_mem prev_db, float momentum,
+                        float weight_decay, float learning_rate, unsigned batch_size,
+                        unsigned weights_size, unsigned bias_size) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
+  float *pw, *pb, *ppw, *ppb;
+  const float *pgw, *pgb;
+  const size_t wb = sizeof(float) * (size_t)weights_size, bb = sizeof(float) * (size_t)bias_size;
+  SRCNN_TRY(resolve(ctx, w, wb, &pw, "weights"));
+  SRCNN_TRY(resolve(ctx, b, bb, &pb, "bias"));
+  SRCNN_TRY(resolve(ctx, grad_w, wb, &pgw, "grad_w"));
+  SRCNN_TRY(resolve(ctx, grad_b, bb, &pgb, "grad_b"));
+  SRCNN_TRY(resolve(ctx, prev_dw, wb, &ppw, "previous delta w"));
+  SRCNN_TRY(resolve(ctx, prev_db, bb, &ppb, "previous delta b"));
+  const unsigned total = std::max(weights_size, bias_size);
+  LaunchScope scope(ctx, SRCNN_K_UPDATE_PARAMS);
+  generic::update_params_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(
+      pw, pb, pgw, pgb, ppw, ppb, momentum, weight_decay, learning_rate, batch_size,
+      weights_size, bias_size);
+  return check_launch("update_params");
+}
+
+int srcnn_sum(srcnn_ctx* ctx, srcnn_mem data, unsigned len, int squared, srcnn_mem target) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  const float* pd;
+  float* pt;
+  SRCNN_TRY(resolve(ctx, data, sizeof(float) * (size_t)len, &pd, "sum data"));
+  SRCNN_TRY(resolve(ctx, target, sizeof(float), &pt, "sum target"));
+  const int blocks = grid_1d(len, generic::RED_THREADS, generic::RED_MAX_BLOCKS);
+  LaunchScope scope(ctx, SRCNN_K_SUM, 2);
+  generic::sum_stage1<<<blocks, generic::RED_THREADS, 0, ctx->stream>>>(
+      pd, (double*)ctx->red_scratch, len, squared);
+  generic::reduce_stage2<<<1, generic::RED_THREADS, 0, ctx->stream>>>(
+      (const double*)ctx->red_scratch, blocks, pt);
+  return check_launch("sum");
+}
+
+int srcnn_sub_from_all(srcnn_ctx* ctx, srcnn_mem data, float value, unsigned len) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  float* pd;
+  SRCNN_TRY(resolve(ctx, data, sizeof(float) * (size_t)len, &pd, "sub_from_all data"));
+  if (len == 0) return SRCNN_OK;
+  LaunchScope scope(ctx, SRCNN_K_SUB_FROM_ALL);
+  generic::sub_from_all_kernel<<<grid_1d(len, 256, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
+      pd, value, len);
+  return check_launch("sub_from_all");
+}
+
+int srcnn_extract_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem target, int w, int h,
+                       int normalize) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(w > 0 && h > 0, "bad image size");
+  const uchar4* pi;
+  float* pt;
+  SRCNN_TRY(resolve(ctx, rgba, (size_t)w * h * 4, &pi, "rgba image"));
+  SRCNN_TRY(resolve(ctx, target, sizeof(float) * (size_t)w * h, &pt, "luma target"));
+  LaunchScope scope(ctx, SRCNN_K_EXTRACT_LUMA);
+  generic::extract_luma_kernel<<<(w * h + 255) / 256, 256, 0, ctx->stream>>>(pi, pt, w * h,
+                                                                            normalize);
+  return check_launch("extract_luma");
+}
+
+int srcnn_swap_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem new_luma, srcnn_mem target,
+                    int gt_w, int gt_h, int luma_w, int luma_h) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_REQUIRE(gt_w > 0 && gt_h > 0 && luma_w > 0 && luma_h > 0 && luma_w <= gt_w && luma_h <= gt_h,
+                "bad swap_luma dimensions");
+  const uchar4* pi;
+  const float* pl;
+  unsigned char* pt;
+  SRCNN_TRY(resolve(ctx, rgba, (size_t)gt_w * gt_h * 4, &pi, "rgba image"));
+  SRCNN_TRY(resolve(ctx, new_luma, sizeof(float) * (size_t)luma_w * luma_h, &pl, "new luma"));
+  SRCNN_TRY(resolve(ctx, target, (size_t)gt_w * gt_h * 3, &pt, "rgb target"));
+  LaunchScope scope(ctx, SRCNN_K_SWAP_LUMA);
+  dim3 block(32, 8), grid((gt_w + 31) / 32, (gt_h + 7) / 8);
+  generic::swap_luma_kernel<<<grid, block, 0, ctx->stream>>>(pi, pl, pt, gt_w, gt_h, luma_w, luma_h);
+  return check_launch("swap_luma");
+}
+
+// ======================================================================= fused hot path
+
+int srcnn_forward_fused_supported(const srcnn_net* net) {
+  if (!net) return 0;
+  return fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3) ? 1 : 0;
+}
+
+int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem out,
+                        int in_w, int in_h, int S, srcnn_mem scratch1, srcnn_mem scratch2) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, in_w, in_h);
+  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "image %dx%d too small for the network", in_w, in_h);
+  if (fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3)) {
+    const float *pin, *w1, *b1, *w2, *b2, *w3, *b3;
+    float* pout;
+    SRCNN_TRY(resolve(ctx, in, sizeof(float) * (size_t)S * in_w * in_h, &pin, "input luma"));
+    SRCNN_TRY(resolve(ctx, out, sizeof(float) * (size_t)S * d.w3 * d.h3, &pout, "output luma"));
+    SRCNN_TRY(resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1"));
+    SRCNN_TRY(resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1"));
+    SRCNN_TRY(resolve(ctx, net->w[1], sizeof(float) * (size_t)net->f2 * net->f2 * net->n1 * net->n2, &w2, "w2"));
+    SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
+    SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
+    SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
+    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+    SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin, pout, w1,
+                                  b1, w2, b2, w3, b3, in_w, in_h, S));
+    return check_launch("forward_fused");
+  }
+  SRCNN_REQUIRE(scratch1 != SRCNN_NULL_MEM && scratch2 != SRCNN_NULL_MEM,
+                "no fused kernel for %d-%d-%d n1=%d n2=%d and no scratch buffers for the "
+                "three-launch path", net->f1, net->f2, net->f3, net->n1, net->n2);
+  SRCNN_TRY(srcnn_forward_layer(ctx, in, scratch1, net->w[0], net->b[0], 1, net->n1, net->f1, 0,
+                                in_w, in_h, S));
+  SRCNN_TRY(srcnn_forward_layer(ctx, scratch1, scratch2, net->w[1], net->b[1], net->n1, net->n2,
+                                net->f2, 0, d.w1, d.h1, S));
+  return srcnn_forward_layer(ctx, scratch2, out, net->w[2], net->b[2], net->n2, 1, net->f3, 1,
+                             d.w2, d.h2, S);
+}
+
+int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int in_w,
+                          int in_h, int out_row0, int out_row1, float* host_out) {
+  SRCNN_REQUIRE(ctx && host_in && host_out, "null argument");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, in_w, in_h);
+  SRCNN_REQUIRE(d.w3 > 0 && d.h3 > 0, "image %dx%d too small for the network", in_w, in_h);
+  SRCNN_REQUIRE(out_row0 >= 0 && out_row0 < out_row1 && out_row1 <= d.h3,
+                "bad output row band [%d,%d) of %d", out_row0, out_row1, d.h3);
+  const int halo = net->f1 + net->f2 + net->f3 - 3;
+  const int band_out_h = out_row1 - out_row0, band_in_h = band_out_h + halo;
+  const size_t in_bytes = sizeof(float) * (size_t)band_in_h * in_w;
+  const size_t out_bytes = sizeof(float) * (size_t)band_out_h * d.w3;
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->band_in, &ctx->band_in_bytes, in_bytes));
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->band_out, &ctx->band_out_bytes, out_bytes));
+  SRCNN_CUDA(cudaMemcpyAsync(ctx->band_in, host_in + (size_t)out_row0 * in_w, in_bytes,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  SRCNN_TRY(resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1"));
+  SRCNN_TRY(resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1"));
+  SRCNN_TRY(resolve(ctx, net->w[1], sizeof(float) * (size_t)net->f2 * net->f2 * net->n1 * net->n2, &w2, "w2"));
+  SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
+  SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
+  SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
+  SRCNN_REQUIRE(fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3),
+                "srcnn_infer_rows_host needs a fused instantiation for %d-%d-%d n1=%d n2=%d",
+                net->f1, net->f2, net->f3, net->n1, net->n2);
+  {
+    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+    SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
+                                  (const float*)ctx->band_in, (float*)ctx->band_out, w1, b1, w2,
+                                  b2, w3, b3, in_w, band_in_h, 1));
+    SRCNN_TRY(check_launch("forward_fused"));
+  }
+  SRCNN_CUDA(cudaMemcpyAsync(host_out, ctx->band_out, out_bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SRCNN_OK;
+}
+
+size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S) {
+  if (!net || S <= 0) return 0;
+  const Dims d = net_dims(net, w, h);
+  if (d.w3 <= 0 || d.h3 <= 0) return 0;
+  const size_t e1 = (size_t)d.w1 * d.h1 * net->n1, e2 = (size_t)d.w2 * d.h2 * net->n2,
+               e3 = (size_t)d.w3 * d.h3;
+  return sizeof(float) * 2 * (e1 + e2 + e3) * (size_t)S;
+}
+
+namespace {
+struct Work {
+  srcnn_mem out1, out2, out3, d1, d2, d3;
+};
+// carve the chunk workspace into six wrapped sub-buffers (handles are cheap table entries)
+int carve(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem work, int w, int h, int S, Work* wk) {
+  const Dims d = net_dims(net, w, h);
+  const size_t e1 = sizeof(float) * (size_t)d.w1 * d.h1 * net->n1 * S,
+               e2 = sizeof(float) * (size_t)d.w2 * d.h2 * net->n2 * S,
+               e3 = sizeof(float) * (size_t)d.w3 * d.h3 * S;
+  char* base;
+  SRCNN_TRY(resolve(ctx, work, 2 * (e1 + e2 + e3), &base, "training workspace"));
+  SRCNN_TRY(srcnn_wrap(ctx, base, e1, &wk->out1));
+  SRCNN_TRY(srcnn_wrap(ctx, base + e1, e2, &wk->out2));
+  SRCNN_TRY(srcnn_wrap(ctx, base + e1 + e2, e3, &wk->out3));
+  SRCNN_TRY(srcnn_wrap(ctx, base + e1 + e2 + e3, e1, &wk->d1));
+  SRCNN_TRY(srcnn_wrap(ctx, base + 2 * e1 + e2 + e3, e2, &wk->d2));
+  SRCNN_TRY(srcnn_wrap(ctx, base + 2 * e1 + 2 * e2 + e3, e3, &wk->d3));
+  return SRCNN_OK;
+}
+// wrapped handles are always the last six table entries: drop them again so a long
+// training run does not grow the table
+void uncarve(srcnn_ctx* ctx) { ctx->allocs.resize(ctx->allocs.size() - 6); }
+}  // namespace
+
+int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
+                      int h, int S, srcnn_mem work) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  Work wk;
+  SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
+  int rc = SRCNN_OK;
+  // forward, keeping the activations (ConfigBasedDataPipeline.cpp:200-241)
+  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, in, wk.out1, net->w[0], net->b[0], 1, net->n1, net->f1, 0, w, h, S);
+  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out1, wk.out2, net->w[1], net->b[1], net->n1, net->n2, net->f2, 0, d.w1, d.h1, S);
+  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
+  // deltas (ConfigBasedDataPipeline.cpp:258-285)
+  if (rc == SRCNN_OK) rc = srcnn_last_layer_delta(ctx, gt, wk.out3, wk.d3, w, h, d.w3, d.h3, S);
+  if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d3, wk.out2, wk.d2, net->w[2], net->n2, net->f3, 1, d.w2, d.h2, S);
+  if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d2, wk.out1, wk.d1, net->w[1], net->n1, net->f2, net->n2, d.w1, d.h1, S);
+  // gradients (ConfigBasedDataPipeline.cpp:287-320)
+  if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
+  if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d2, wk.out1, net->grad_w[1], net->grad_b[1], net->n2, net->n1, net->f2, d.w2, d.h2, S);
+  if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
+  uncarve(ctx);
+  return rc;
+}
+
+int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,
+                     float weight_decay, const float lr[3]) {
+  SRCNN_REQUIRE(ctx && lr, "null argument");
+  SRCNN_TRY(check_net(net));
+  SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
+  fast::UpdateAllArgs a;
+  const int ks[3] = {1, net->n1, net->n2}, ns[3] = {net->n1, net->n2, 1},
+            fs[3] = {net->f1, net->f2, net->f3};
+  unsigned total = 0;
+  for (int l = 0; l < 3; l++) {
+    const unsigned ws = (unsigned)(fs[l] * fs[l] * ks[l] * ns[l]), bs = (unsigned)ns[l];
+    SRCNN_TRY(resolve(ctx, net->w[l], sizeof(float) * ws, &a.w[l], "weights"));
+    SRCNN_TRY(resolve(ctx, net->b[l], sizeof(float) * bs, &a.b[l], "bias"));
+    SRCNN_TRY(resolve(ctx, net->grad_w[l], sizeof(float) * ws, &a.gw[l], "grad_w"));
+    SRCNN_TRY(resolve(ctx, net->grad_b[l], sizeof(float) * bs, &a.gb[l], "grad_b"));
+    SRCNN_TRY(resolve(ctx, net->prev_dw[l], sizeof(float) * ws, &a.pw[l], "previous delta w"));
+    SRCNN_TRY(resolve(ctx, net->prev_db[l], sizeof(float) * bs, &a.pb[l], "previous delta b"));
+    a.ws[l] = ws;
+    a.bs[l] = bs;
+    a.lr[l] = lr[l];
+    total += ws + bs;
+  }
+  a.momentum = momentum;
+  a.decay = weight_decay;
+  a.batch = (float)batch_size;
+  LaunchScope scope(ctx, SRCNN_K_UPDATE_PARAMS);
+  fast::update_all_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(a);
+  return check_launch("update_all");
+}
+
+int srcnn_validate_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
+                         int w, int h, int S, srcnn_mem work, srcnn_mem target) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  Work wk;
+  SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
+  int rc = srcnn_forward_fused(ctx, net, in, wk.out3, w, h, S, wk.out1, wk.out2);
+  if (rc == SRCNN_OK) rc = srcnn_squared_error(ctx, gt, wk.out3, target, w, h, d.w3, d.h3, S);
+  uncarve(ctx);
+  return rc;
+}
+
+}  // extern "C"

@@ -249,7 +249,8 @@ void oracle_extract_luma(const unsigned char* rgba, float* target, int w, int h,
   for (int i = 0; i < w * h; i++) {
     const float r = (float)rgba[4 * i + 0], g = (float)rgba[4 * i + 1],
                 bl = (float)rgba[4 * i + 2], a = (float)rgba[4 * i + 3];
-    const float y = r * 0.299f + g * 0.587f + bl * 0.114f + a * 0.0f;
+    (void)a; /* alpha weight is 0 */
+    const float y = (r * 0.299f + g * 0.587f) + bl * 0.114f;
     target[i] = normalize ? y / 255.0f : y;
   }
 }
@@ -277,9 +278,10 @@ void oracle_swap_luma(const unsigned char* rgba, const float* new_luma, unsigned
         const float Y = new_luma[(size_t)ly * luma_w + lx] * 255.0f;
         const float Cb = r * -0.1687f + g * -0.3312f + b * 0.5f;
         const float Cr = r * 0.5f + g * -0.4186f + b * -0.0813f;
-        const float R = clampf(Y * 1.0f + Cb * 0.0f + Cr * 1.4f, 0.0f, 255.0f);
-        const float G = clampf(Y * 1.0f + Cb * -0.343f + Cr * -0.711f, 0.0f, 255.0f);
-        const float Bv = clampf(Y * 1.0f + Cb * 1.765f + Cr * 0.0f, 0.0f, 255.0f);
+        /* dot(YCbCr, row): Y*1 + Cb*c1 + Cr*c2; the zero terms add exactly nothing */
+        const float R = clampf(Y + Cr * 1.4f, 0.0f, 255.0f);
+        const float G = clampf((Y + Cb * -0.343f) + Cr * -0.711f, 0.0f, 255.0f);
+        const float Bv = clampf(Y + Cb * 1.765f, 0.0f, 255.0f);
         o0 = (unsigned char)(unsigned int)R;
         o1 = (unsigned char)(unsigned int)G;
         o2 = (unsigned char)(unsigned int)Bv;

@@ -1,0 +1,474 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the oracle
+on the same seeded inputs and against the committed golden fixtures.  Run on the B200 box:
+    python -m pytest tests -m gpu
+Tolerances (north_star): per-pixel max-abs <= 1e-4 on luma in [0,1]; PSNR within 0.01 dB;
+per-epoch weights <= 1e-4 relative.  Intermediate FP32 tensors: rtol 1e-4 + atol 1e-5 (the
+summation order differs from the oracle's).  8-bit luma output: bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _pkg
+from conftest import GOLDEN, load_npz
+from helpers import luma_image, make_params, patches, psnr
+from oracle.loader import NetState
+
+pytestmark = pytest.mark.gpu
+pkg = _pkg.load()
+
+RTOL, ATOL = 1e-4, 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def _json(name):
+    with open(os.path.join(GOLDEN, name)) as fh:
+        return json.load(fh)
+
+
+def gpu_forward(ctx, x, W, B, k, n, f, skip, w, h, S):
+    ow, oh = w - f + 1, h - f + 1
+    mi, mW, mB = ctx.upload(x), ctx.upload(W), ctx.upload(B)
+    mo = ctx.alloc(4 * S * ow * oh * n)
+    ctx.forward_layer(mi, mo, mW, mB, k, n, f, skip, w, h, S)
+    out = ctx.read(mo, (S, oh, ow, n))
+    for m in (mi, mW, mB, mo):
+        ctx.release(m)
+    return out
+
+
+def gpu_deltas(ctx, dn, lo, W, nc, fn, nn, ow, oh, S):
+    a, b, c = ctx.upload(dn), ctx.upload(lo), ctx.upload(W)
+    t = ctx.alloc(4 * S * ow * oh * nc)
+    ctx.deltas(a, b, t, c, nc, fn, nn, ow, oh, S)
+    out = ctx.read(t, (S, oh, ow, nc))
+    for m in (a, b, c, t):
+        ctx.release(m)
+    return out
+
+
+def gpu_backprop(ctx, d, li, gw0, gb0, n, k, f, ow, oh, S):
+    a, b = ctx.upload(d), ctx.upload(li)
+    gw, gb = ctx.upload(gw0), ctx.upload(gb0)
+    ctx.backpropagate(a, b, gw, gb, n, k, f, ow, oh, S)
+    r = ctx.read(gw, (gw0.size,)), ctx.read(gb, (gb0.size,))
+    for m in (a, b, gw, gb):
+        ctx.release(m)
+    return r
+
+
+# ------------------------------------------------------------------ reference goldens
+def test_forward_reference_layer_cases(ctx):
+    """reference: test/specs/LayerTest.cpp:97-130, test/data/test_cases.json"""
+    for name, c in _json("layer_cases.json")["cases"].items():
+        k, n, f = c["n_prev_filter_cnt"], c["current_filter_count"], c["f_spatial_size"]
+        out = gpu_forward(ctx, np.array(c["input"], np.float32), np.array(c["weights"], np.float32),
+                          np.array(c["bias"], np.float32), k, n, f, False, c["input_w"],
+                          c["input_h"], 1)
+        np.testing.assert_allclose(out.reshape(-1), np.array(c["output"], np.float32),
+                                   atol=5.1e-4, rtol=0, err_msg=name)
+
+
+def test_deltas_reference_case(ctx):
+    """reference: test/specs/LayerDeltasTest.cpp:33-126"""
+    c = _json("layer_deltas_case.json")
+    lo = np.maximum(np.array(c["input_x"], np.float32), 0)
+    out = gpu_deltas(ctx, np.array(c["deltas"], np.float32), lo, np.array(c["weights"], np.float32),
+                     c["n_curr"], c["f_next"], c["n_next"], c["out_w"], c["out_h"], 1)
+    np.testing.assert_allclose(out.reshape(-1), np.array(c["expected_output"], np.float32),
+                               atol=2e-6, rtol=0)
+
+
+def test_backpropagate_reference_case(ctx):
+    """reference: test/specs/BackpropagationTest.cpp:31-90 (accumulates onto 1.5)"""
+    c = _json("backprop_case.json")
+    gw0 = np.full(c["f"] ** 2 * c["k"] * c["n"], c["grad_w_init"], np.float32)
+    gw, gb = gpu_backprop(ctx, np.array(c["deltas"], np.float32), np.array(c["input"], np.float32),
+                          gw0, np.zeros(c["n"], np.float32), c["n"], c["k"], c["f"], c["out_w"],
+                          c["out_h"], 1)
+    np.testing.assert_allclose(gw, np.array(c["expected_weights"], np.float32), atol=6e-5, rtol=0)
+    np.testing.assert_allclose(gb, np.array(c["expected_bias"], np.float32), atol=1e-6, rtol=0)
+
+
+def test_backpropagate_big_data_does_not_crash(ctx):
+    """reference: BackpropagationTest.cpp data set 2 (k=32 n=16 f=3 on 1024x1024 deltas)"""
+    n, k, f, ow, oh = 16, 32, 3, 1024, 1024
+    d = ctx.zeros(ow * oh * n)
+    li = ctx.zeros((ow + f - 1) * (oh + f - 1) * k)
+    gw, gb = ctx.zeros(f * f * k * n), ctx.zeros(n)
+    ctx.backpropagate(d, li, gw, gb, n, k, f, ow, oh, 1)
+    ctx.block()
+    assert not ctx.read(gw, (f * f * k * n,)).any()
+    for m in (d, li, gw, gb):
+        ctx.release(m)
+
+
+def test_committed_reference_kernel_outputs(ctx):
+    """outputs of the reference's own kernels (tests/golden/ref_kernels_small.npz)"""
+    g = load_npz("ref_kernels_small.npz")
+    S, k, n, f, w, h = (int(v) for v in g["fw_shape"])
+    np.testing.assert_allclose(gpu_forward(ctx, g["fw_x"], g["fw_W"], g["fw_B"], k, n, f, False, w, h, S),
+                               g["fw_relu"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(gpu_forward(ctx, g["fw_x"], g["fw_W"], g["fw_B"], k, n, f, True, w, h, S),
+                               g["fw_lin"], rtol=RTOL, atol=ATOL)
+    S, nc, fn, nn, ow, oh = (int(v) for v in g["dl_shape"])
+    np.testing.assert_allclose(gpu_deltas(ctx, g["dl_next"], g["dl_out"], g["dl_W"], nc, fn, nn, ow, oh, S),
+                               g["dl_result"], rtol=RTOL, atol=ATOL)
+    S, k, n, f, ow, oh = (int(v) for v in g["bp_shape"])
+    gw, gb = gpu_backprop(ctx, g["bp_d"], g["bp_in"], g["bp_gw0"], g["bp_gb0"], n, k, f, ow, oh, S)
+    np.testing.assert_allclose(gw, g["bp_gw"], rtol=RTOL, atol=1e-4)
+    np.testing.assert_allclose(gb, g["bp_gb"], rtol=RTOL, atol=1e-4)
+    # last layer delta + squared error
+    S, ah, aw = g["ll_algo"].shape
+    gh, gwid = g["ll_gt"].shape[1:]
+    mg, ma = ctx.upload(g["ll_gt"]), ctx.upload(g["ll_algo"])
+    mt, ms = ctx.alloc(4 * S * ah * aw), ctx.alloc(4)
+    ctx.last_layer_delta(mg, ma, mt, gwid, gh, aw, ah, S)
+    np.testing.assert_array_equal(ctx.read(mt, (S, ah, aw)), g["ll_delta"])
+    ctx.squared_error(mg, ma, ms, gwid, gh, aw, ah, S)
+    assert float(ctx.read(ms, (1,))[0]) == pytest.approx(float(g["ll_sse"]), rel=1e-6)
+    # update with weight decay
+    m, dec, lr, batch = g["up_hyper"]
+    hs = [ctx.upload(g[k_]) for k_ in ("up_w0", "up_b0", "up_gw", "up_gb", "up_pw0", "up_pb0")]
+    ctx.update_params(*hs, float(m), float(dec), float(lr), int(batch), g["up_w0"].size, g["up_b0"].size)
+    for hnd, key in zip((hs[0], hs[1], hs[4], hs[5]), ("up_w", "up_b", "up_pw", "up_pb")):
+        np.testing.assert_allclose(ctx.read(hnd, g[key].shape), g[key], rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------ per-kernel vs oracle
+FWD_SHAPES = [
+    # k, n, f, w, h, S
+    (1, 64, 9, 33, 33, 3), (64, 32, 1, 25, 25, 3), (32, 1, 5, 25, 25, 3), (64, 32, 5, 25, 25, 2),
+    (1, 128, 9, 40, 21, 1), (128, 64, 1, 17, 30, 2), (64, 1, 5, 31, 18, 2),
+    (1, 32, 9, 20, 20, 1), (32, 16, 1, 12, 12, 2), (16, 1, 5, 12, 12, 2),
+    (5, 7, 3, 8, 6, 3), (3, 70, 1, 5, 5, 1), (2, 3, 5, 5, 5, 1), (1, 1, 1, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("shape", FWD_SHAPES)
+def test_forward_vs_oracle(ctx, port, shape):
+    k, n, f, w, h, S = shape
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    x = rng.normal(0, 1, (S, h, w, k)).astype(np.float32)
+    W = rng.normal(0, 1.0 / np.sqrt(f * f * k), f * f * k * n).astype(np.float32)
+    B = rng.normal(0, 0.1, n).astype(np.float32)
+    for skip in (False, True):
+        np.testing.assert_allclose(gpu_forward(ctx, x, W, B, k, n, f, skip, w, h, S),
+                                   port.forward(x, W, B, k, n, f, skip, w, h, S),
+                                   rtol=RTOL, atol=ATOL)
+
+
+DELTA_SHAPES = [
+    # n_curr, f_next, n_next, out_w, out_h, S
+    (32, 5, 1, 25, 25, 3), (64, 1, 32, 25, 25, 3), (64, 5, 32, 25, 25, 2), (64, 5, 1, 21, 30, 2),
+    (128, 1, 64, 9, 11, 2), (16, 5, 1, 12, 12, 2), (32, 1, 16, 12, 12, 2),
+    (4, 3, 5, 6, 5, 2), (3, 3, 2, 3, 3, 1), (70, 1, 3, 4, 4, 1),
+]
+
+
+@pytest.mark.parametrize("shape", DELTA_SHAPES)
+def test_deltas_vs_oracle(ctx, port, shape):
+    nc, fn, nn, ow, oh, S = shape
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    dn = rng.normal(0, 1, (S, oh - fn + 1, ow - fn + 1, nn)).astype(np.float32)
+    lo = np.maximum(rng.normal(0, 1, (S, oh, ow, nc)), 0).astype(np.float32)
+    W = rng.normal(0, 0.3, fn * fn * nc * nn).astype(np.float32)
+    np.testing.assert_allclose(gpu_deltas(ctx, dn, lo, W, nc, fn, nn, ow, oh, S),
+                               port.deltas(dn, lo, W, nc, fn, nn, ow, oh, S), rtol=RTOL, atol=ATOL)
+
+
+BP_SHAPES = [
+    # n, k, f, out_w, out_h, S
+    (64, 1, 9, 25, 25, 5), (32, 64, 1, 25, 25, 5), (1, 32, 5, 21, 21, 5), (32, 64, 5, 21, 21, 2),
+    (128, 1, 9, 12, 9, 2), (64, 128, 1, 10, 10, 2), (16, 32, 1, 8, 8, 3),
+    (4, 3, 3, 5, 4, 3), (3, 2, 3, 3, 3, 1), (1, 1, 1, 1, 1, 1), (70, 3, 1, 9, 2, 2),
+]
+
+
+@pytest.mark.parametrize("shape", BP_SHAPES)
+def test_backpropagate_vs_oracle(ctx, port, shape):
+    n, k, f, ow, oh, S = shape
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    d = rng.normal(0, 1, (S, oh, ow, n)).astype(np.float32)
+    li = rng.normal(0, 1, (S, oh + f - 1, ow + f - 1, k)).astype(np.float32)
+    gw0 = rng.normal(0, 1, f * f * k * n).astype(np.float32)
+    gb0 = rng.normal(0, 1, n).astype(np.float32)
+    egw, egb = gw0.copy(), gb0.copy()
+    port.backpropagate(d, li, egw, egb, n, k, f, ow, oh, S)
+    gw, gb = gpu_backprop(ctx, d, li, gw0, gb0, n, k, f, ow, oh, S)
+    scale = np.sqrt(S * ow * oh)   # |sum of P unit-variance products| ~ sqrt(P)
+    np.testing.assert_allclose(gw, egw, rtol=RTOL, atol=2e-5 * scale)
+    np.testing.assert_allclose(gb, egb, rtol=RTOL, atol=2e-5 * scale)
+
+
+def test_backpropagate_is_deterministic(ctx):
+    """The reference races on grad_w across samples (backpropagate.cl:110); ours must give the
+    same bits on every run."""
+    n, k, f, ow, oh, S = 64, 1, 9, 25, 25, 16
+    rng = np.random.default_rng(5)
+    d = rng.normal(0, 1, (S, oh, ow, n)).astype(np.float32)
+    li = rng.normal(0, 1, (S, oh + f - 1, ow + f - 1, k)).astype(np.float32)
+    z = np.zeros(f * f * k * n, np.float32), np.zeros(n, np.float32)
+    a = gpu_backprop(ctx, d, li, z[0], z[1], n, k, f, ow, oh, S)
+    b = gpu_backprop(ctx, d, li, z[0], z[1], n, k, f, ow, oh, S)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_elementwise_and_reductions_vs_oracle(ctx, port):
+    rng = np.random.default_rng(8)
+    # reference: LastLayerDeltaTest.cpp (6x6 in 14x14, poisoned border), S>1 added
+    S, aw, ah, pad = 3, 6, 6, 4
+    gt = np.full((S, ah + 2 * pad, aw + 2 * pad), 99999.0, np.float32)
+    gt[:, pad:pad + ah, pad:pad + aw] = rng.uniform(0, 2.56, (S, ah, aw))
+    algo = np.maximum(rng.uniform(-1, 1.56, (S, ah, aw)), 0).astype(np.float32)
+    mg, ma, mt, ms = ctx.upload(gt), ctx.upload(algo), ctx.alloc(4 * S * aw * ah), ctx.alloc(4)
+    ctx.last_layer_delta(mg, ma, mt, aw + 2 * pad, ah + 2 * pad, aw, ah, S)
+    np.testing.assert_array_equal(ctx.read(mt, (S, ah, aw)),
+                                  port.last_layer_delta(gt, algo, aw + 2 * pad, ah + 2 * pad, aw, ah, S))
+    ctx.squared_error(mg, ma, ms, aw + 2 * pad, ah + 2 * pad, aw, ah, S)
+    assert float(ctx.read(ms, (1,))[0]) == pytest.approx(
+        port.squared_error(gt, algo, aw + 2 * pad, ah + 2 * pad, aw, ah, S), rel=1e-6)
+    # reference: SquaredErrorTest.cpp at its full size 1000x2000 in 1008x2008
+    aw, ah, pad = 1000, 2000, 4
+    gt = np.full((ah + 2 * pad, aw + 2 * pad), 99999.0, np.float32)
+    gt[pad:pad + ah, pad:pad + aw] = rng.integers(0, 256, (ah, aw))
+    algo = (rng.integers(0, 2560, (ah, aw)) / 10.0).astype(np.float32)
+    mg2, ma2 = ctx.upload(gt), ctx.upload(algo)
+    ctx.squared_error(mg2, ma2, ms, aw + 2 * pad, ah + 2 * pad, aw, ah, 1)
+    assert float(ctx.read(ms, (1,))[0]) == pytest.approx(
+        port.squared_error(gt, algo, aw + 2 * pad, ah + 2 * pad, aw, ah, 1), rel=1e-6)
+    # reference: SumTest.cpp / SubtractFromAllTest.cpp (0..899)
+    data = np.arange(900, dtype=np.float32)
+    md = ctx.upload(data)
+    ctx.sum(md, 900, False, ms)
+    assert float(ctx.read(ms, (1,))[0]) == 404550.0
+    ctx.sum(md, 900, True, ms)
+    assert float(ctx.read(ms, (1,))[0]) == pytest.approx(port.sum(data, True), rel=1e-7)
+    ctx.sub_from_all(md, 450.0, 900)
+    np.testing.assert_array_equal(ctx.read(md, (900,)), data - 450.0)
+    # a length that is not a multiple of anything, > one reduction pass
+    big = rng.normal(0, 1, 1_234_567).astype(np.float32)
+    mb = ctx.upload(big)
+    ctx.sum(mb, big.size, False, ms)
+    assert float(ctx.read(ms, (1,))[0]) == pytest.approx(port.sum(big), rel=1e-5, abs=1e-2)
+
+
+def test_update_parameters_vs_oracle(ctx, port):
+    """reference: UpdateParametersTest.cpp (2*400*5^2 weights, 400 biases, momentum .8,
+    lr .001, batch 2) plus non-zero weight decay."""
+    rng = np.random.default_rng(13)
+    ws, bs = 2 * 400 * 25, 400
+    for decay in (0.0, 0.05):
+        arrs = dict(w=rng.integers(0, 2560, ws) / 10.0, b=rng.integers(0, 2560, bs) / 10.0,
+                    gw=rng.integers(0, 2560, ws) / 100.0, gb=rng.integers(0, 2560, bs) / 100.0,
+                    pw=rng.integers(0, 2560, ws) / 10.0, pb=rng.integers(0, 2560, bs) / 10.0)
+        arrs = {k: v.astype(np.float32) for k, v in arrs.items()}
+        hs = {k: ctx.upload(v) for k, v in arrs.items()}
+        ctx.update_params(hs["w"], hs["b"], hs["gw"], hs["gb"], hs["pw"], hs["pb"], 0.8, decay,
+                          0.001, 2, ws, bs)
+        e = {k: v.copy() for k, v in arrs.items()}
+        port.update_params(e["w"], e["b"], e["gw"], e["gb"], e["pw"], e["pb"], 0.8, decay, 0.001, 2)
+        for k in ("w", "b", "pw", "pb"):
+            np.testing.assert_allclose(ctx.read(hs[k], arrs[k].shape), e[k], rtol=1e-6, atol=1e-5)
+
+
+def test_luma_kernels_bit_exact(ctx, port):
+    """extract_luma / swap_luma (reference: ExtractLumaTest.cpp, SwapLumaTest.cpp): float luma
+    to 1 ulp-ish, 8-bit output bit-exact against the oracle."""
+    rng = np.random.default_rng(17)
+    h, w, pad = 37, 53, 6
+    rgba = rng.integers(0, 256, (h, w, 4)).astype(np.uint8)
+    mi = ctx.upload(rgba, np.uint8)
+    ml = ctx.alloc(4 * w * h)
+    for norm in (True, False):
+        ctx.extract_luma(mi, ml, w, h, norm)
+        np.testing.assert_array_equal(ctx.read(ml, (h, w)), port.extract_luma(rgba, norm))
+    new_luma = rng.uniform(-0.1, 1.1, (h - 2 * pad, w - 2 * pad)).astype(np.float32)
+    mn = ctx.upload(new_luma)
+    mt = ctx.alloc(w * h * 3)
+    ctx.swap_luma(mi, mn, mt, w, h, w - 2 * pad, h - 2 * pad)
+    np.testing.assert_array_equal(ctx.read(mt, (h, w, 3), np.uint8),
+                                  port.swap_luma(rgba, new_luma, w - 2 * pad, h - 2 * pad))
+
+
+# ------------------------------------------------------------------ errors
+def test_error_behaviour(ctx):
+    """Validation mirrors the reference's (src/DataPipeline.cpp:339-356, Context.cpp:235-341):
+    failures are reported, never silently computed."""
+    small = ctx.alloc(16)
+    with pytest.raises(pkg.SrcnnError, match="too small"):
+        ctx.forward_layer(small, small, small, small, 1, 64, 9, False, 33, 33, 1)
+    with pytest.raises(pkg.SrcnnError, match="smaller than filter"):
+        ctx.forward_layer(small, small, small, small, 1, 1, 9, False, 5, 5, 1)
+    with pytest.raises(pkg.SrcnnError, match="more then is allocated"):
+        ctx.read(small, (100,))
+    with pytest.raises(pkg.SrcnnError, match="invalid memory handle"):
+        ctx.fill_float(pkg.NULL_MEM, 0.0)
+    ctx.release(small)
+    with pytest.raises(pkg.SrcnnError, match="invalid memory handle"):
+        ctx.read(small, (1,))
+    a, b = ctx.alloc(64), ctx.alloc(32)
+    with pytest.raises(pkg.SrcnnError, match="after dst end"):
+        ctx.copy(a, b)
+
+
+# ------------------------------------------------------------------ whole net
+NETS = [
+    # n1, n2, f1, f2, f3, w, h, S
+    (64, 32, 9, 1, 5, 33, 33, 4), (64, 32, 9, 5, 5, 33, 33, 2), (128, 64, 9, 1, 5, 40, 29, 2),
+    (32, 16, 9, 1, 5, 33, 33, 3), (8, 4, 9, 1, 5, 33, 33, 3), (4, 3, 3, 1, 3, 9, 8, 3),
+]
+
+
+@pytest.mark.parametrize("cfg", NETS)
+def test_train_chunk_vs_oracle(ctx, port, cfg):
+    """forward + deltas + gradients of one chunk: every intermediate buffer and the six
+    gradient tensors against the oracle."""
+    n1, n2, f1, f2, f3, w, h, S = cfg
+    rng = np.random.default_rng(sum(cfg))
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x, gt = patches(rng, S, w, h)
+    on = NetState(n1, n2, f1, f2, f3, params)
+    o1, o2, o3 = port.net_forward(on, x, w, h, S)
+    d1, d2, d3 = port.net_backward(on, x, gt, w, h, S, o1, o2, o3)
+
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    mi, mg = ctx.upload(x), ctx.upload(gt)
+    work = ctx.alloc(net.train_workspace_bytes(w, h, S))
+    net.train_chunk(mi, mg, w, h, S, work)
+    flat = ctx.read(work, (net.train_workspace_bytes(w, h, S) // 4,))
+    off = 0
+    for name, exp in (("out1", o1), ("out2", o2), ("out3", o3), ("d1", d1), ("d2", d2), ("d3", d3)):
+        got = flat[off:off + exp.size].reshape(exp.shape)
+        off += exp.size
+        np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL, err_msg=name)
+    g = net.grads()
+    for l in range(3):
+        np.testing.assert_allclose(g["w%d" % (l + 1)], on.gw[l], rtol=RTOL, atol=1e-4, err_msg="gw%d" % l)
+        np.testing.assert_allclose(g["b%d" % (l + 1)], on.gb[l], rtol=RTOL, atol=1e-4, err_msg="gb%d" % l)
+
+
+@pytest.mark.parametrize("name", ["ref_train_chain.npz", "ref_train_915.npz"])
+def test_training_epochs_vs_committed_reference(ctx, name):
+    """2 epochs x 2 chunks, momentum + weight decay: per-epoch parameters within 1e-4 relative
+    of what the reference's own kernels produce (fixture generated by make_golden.py)."""
+    g = load_npz(name)
+    n1, n2, f1, f2, f3 = (int(v) for v in g["cfg"])
+    ns, w, h, chunk, epochs = (int(v) for v in g["dims"])
+    params = {k[3:]: g[k] for k in g if k.startswith("p0_")}
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    x, gt = g["x"], g["gt"]
+    work = ctx.alloc(net.train_workspace_bytes(w, h, chunk))
+    for e in range(epochs):
+        for i in range(0, ns, chunk):
+            S = min(chunk, ns - i)
+            mi, mg = ctx.upload(x[i:i + S]), ctx.upload(gt[i:i + S])
+            net.train_chunk(mi, mg, w, h, S, work)
+        net.update_all(ns, float(g["momentum"]), float(g["decay"]), g["lr"])
+        p = net.params()
+        for l in range(3):
+            np.testing.assert_allclose(p["w%d" % (l + 1)], g["e%d_w%d" % (e + 1, l + 1)],
+                                       rtol=1e-4, atol=1e-7)
+            np.testing.assert_allclose(p["b%d" % (l + 1)], g["e%d_b%d" % (e + 1, l + 1)],
+                                       rtol=1e-4, atol=1e-7)
+        assert not any(v.any() for v in net.grads().values()), "accumulators must be zeroed"
+    # validation SSE after training
+    mi, mg, tgt = ctx.upload(x), ctx.upload(gt), ctx.alloc(4)
+    work2 = ctx.alloc(net.train_workspace_bytes(w, h, ns))
+    net.validate_chunk(mi, mg, w, h, ns, work2, tgt)
+    assert float(ctx.read(tgt, (1,))[0]) == pytest.approx(float(g["final_sse"]), rel=1e-4)
+
+
+INFER = [
+    # n1, n2, f1, f2, f3, w, h, S
+    (64, 32, 9, 1, 5, 256, 256, 1),     # BASELINE config C1
+    (64, 32, 9, 1, 5, 13, 13, 1),       # 1x1 output
+    (64, 32, 9, 1, 5, 141, 77, 2),      # ragged, S>1
+    (64, 32, 9, 5, 5, 96, 80, 1),       # 9-5-5
+    (128, 64, 9, 1, 5, 120, 67, 1),     # C5's network
+    (32, 16, 9, 1, 5, 64, 64, 1),       # example_config.json
+    (4, 3, 3, 1, 3, 20, 11, 2),         # no fused instantiation -> three-launch path
+]
+
+
+@pytest.mark.parametrize("cfg", INFER)
+def test_inference_vs_oracle(ctx, port, cfg):
+    """Whole forward pass (the fused launch where instantiated): max-abs <= 1e-4 on luma,
+    PSNR (from the squared-error sum) within 0.01 dB."""
+    n1, n2, f1, f2, f3, w, h, S = cfg
+    rng = np.random.default_rng(sum(cfg) + 1)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x = np.stack([luma_image(rng, h, w) for _ in range(S)])
+    gt = np.stack([luma_image(rng, h, w) for _ in range(S)])
+    on = NetState(n1, n2, f1, f2, f3, params)
+    _, _, e3 = port.net_forward(on, x, w, h, S)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (w1, h1), (w2, h2), (w3, h3) = net.out_dims(w, h)
+    mi, mo = ctx.upload(x), ctx.alloc(4 * S * w3 * h3)
+    s1, s2 = ctx.alloc(4 * S * w1 * h1 * n1), ctx.alloc(4 * S * w2 * h2 * n2)
+    net.forward_fused(mi, mo, w, h, S, s1, s2)
+    got = ctx.read(mo, (S, h3, w3))
+    assert np.abs(e3).max() > 0.05, "degenerate test input"
+    assert np.abs(got - e3).max() <= 1e-4
+    mg, tgt = ctx.upload(gt), ctx.alloc(4)
+    ctx.squared_error(mg, mo, tgt, w, h, w3, h3, S)
+    sse_gpu = float(ctx.read(tgt, (1,))[0])
+    sse_ref = port.squared_error(gt, e3, w, h, w3, h3, S)
+    assert abs(psnr(sse_gpu, e3.size) - psnr(sse_ref, e3.size)) <= 0.01
+    for m in (mi, mo, s1, s2, mg, tgt):
+        ctx.release(m)
+
+
+def test_full_size_4096_properties(ctx, port):
+    """BASELINE config C3 (4096x4096, 9-1-5 64/32) at full size, through size-independent
+    properties: (1) random 48x48 output windows equal the oracle run on just their receptive
+    field; (2) row-band results (the multi-GPU partition, through the HOST entry point) are
+    bit-identical to the single-launch result; (3) translation: cropping the input by (dy,dx)
+    shifts the output by the same amount, bit for bit."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    w = h = 4096
+    rng = np.random.default_rng(4096)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x = luma_image(rng, h, w)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    if not net.fused_supported():
+        pytest.skip("no fused instantiation yet")
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    pad = net.padding
+    mi, mo = ctx.upload(x), ctx.alloc(4 * w3 * h3)
+    net.forward_fused(mi, mo, w, h, 1)
+    full = ctx.read(mo, (h3, w3))
+    on = NetState(n1, n2, f1, f2, f3, params)
+    for _ in range(12):
+        y0, x0 = int(rng.integers(0, h3 - 48)), int(rng.integers(0, w3 - 48))
+        crop = np.ascontiguousarray(x[y0:y0 + 48 + pad, x0:x0 + 48 + pad])
+        _, _, e3 = port.net_forward(on, crop, 48 + pad, 48 + pad, 1)
+        assert np.abs(full[y0:y0 + 48, x0:x0 + 48] - e3[0]).max() <= 1e-4
+    # corners and edges too
+    for (y0, x0) in ((0, 0), (h3 - 48, w3 - 48), (0, w3 - 48), (h3 - 48, 0)):
+        crop = np.ascontiguousarray(x[y0:y0 + 48 + pad, x0:x0 + 48 + pad])
+        _, _, e3 = port.net_forward(on, crop, 48 + pad, 48 + pad, 1)
+        assert np.abs(full[y0:y0 + 48, x0:x0 + 48] - e3[0]).max() <= 1e-4
+    # (2) row bands through the host entry point, N = 8 and an uneven N = 3
+    for world in (8, 3):
+        out = np.zeros((h3, w3), np.float32)
+        for (r0, r1) in pkg.row_bands(h3, world):
+            if r1 > r0:
+                net.infer_rows_host(x, w, h, r0, r1, out[r0:r1])
+        np.testing.assert_array_equal(out, full)
+    # (3) translation
+    dy, dx = 37, 101
+    xs = np.ascontiguousarray(x[dy:, dx:])
+    hs, ws_ = xs.shape
+    m2, o2 = ctx.upload(xs), ctx.alloc(4 * (ws_ - pad) * (hs - pad))
+    net.forward_fused(m2, o2, ws_, hs, 1)
+    np.testing.assert_array_equal(ctx.read(o2, (hs - pad, ws_ - pad)), full[dy:, dx:])

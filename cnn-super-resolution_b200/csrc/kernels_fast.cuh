@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "context.cuh"
+#include "fused_forward.cuh"
 
 namespace srcnn {
 namespace fast {
@@ -49,6 +50,7 @@ __global__ void update_all_kernel(UpdateAllArgs a) {
 // one-time per-context setup (opt-in shared memory sizes etc.)
 inline int configure(srcnn_ctx* ctx) {
   (void)ctx;
+  SRCNN_TRY(fused::configure());
   return SRCNN_OK;
 }
 
@@ -69,12 +71,19 @@ inline int backpropagate(srcnn_ctx*, const float*, const float*, float*, float*,
   return 0;
 }
 
-inline bool fused_supported(int, int, int, int, int) { return false; }
+inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {
+  return fused::supported(n1, n2, f1, f2, f3);
+}
 
-inline int forward_fused(srcnn_ctx*, int, int, int, int, int, const float*, float*, const float*,
-                         const float*, const float*, const float*, const float*, const float*,
-                         int, int, int) {
-  return fail(SRCNN_EINVAL, "no fused forward instantiation");
+inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* in,
+                         float* out, const float* w1, const float* b1, const float* w2,
+                         const float* b2, const float* w3, const float* b3, int in_w, int in_h,
+                         int S) {
+  if (!fused::supported(n1, n2, f1, f2, f3))
+    return fail(SRCNN_EINVAL, "no fused forward instantiation");
+  fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
+                in_h - (f1 + f2 + f3 - 3)};
+  return fused::launch(ctx, n1, n2, a, S);
 }
 
 }  // namespace fast

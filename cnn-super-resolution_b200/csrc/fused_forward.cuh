@@ -13,8 +13,9 @@
 //           9 input taps of a row slide through registers; result -> smem, channel-major
 //       L2  out2[RB x OW2 px][N2] = relu(b2 + W2 * out1)        thread tile 8 px x 4 ch2;
 //           result -> smem ring of RB+4 rows, channel-major
-//       L3  out3[RB x OW3 px]     = b3 + W3 * out2-window       thread tile 4 px x N2/4 ch2,
-//           the four channel quarters are folded with two warp shuffles; -> global
+//       L3  out3[RB x OW3 px]     = b3 + W3 * out2-window       thread tile 4 px x RB rows x
+//           N2/16 ch2 (taps in registers, each out2 row reused by every output row that
+//           sees it); the 16 channel slices are folded with four warp shuffles; -> global
 //   * the input rows and the out2 rows live in circular row buffers, so vertical halo
 //     recomputation is (RPC+4)/RPC and horizontal OW2/OW3 (1.03 x 1.07 for 64/32).
 //   * two __syncthreads per block; weights (W1 20.7 KB, W2 8 KB, W3) stay in smem.
@@ -43,7 +44,7 @@ struct Cfg {
   static constexpr int L1_TASKS = (OW2 / 8) * RB * (N1 / 8);
   static constexpr int L2_TASKS = (PX / 8) * (N2 / 4);
   static constexpr int NPG3 = OW3 / 4;
-  static constexpr int L3_TASKS = NPG3 * RB * 4;
+  static_assert(NPG3 * 16 <= NT, "L3 thread tiling");
   static_assert(L1_TASKS == NT, "L1 thread tiling must cover the block exactly");
   static_assert(L2_TASKS == NT, "L2 thread tiling must cover the block exactly");
   static_assert(OW2 % 8 == 0 && OW3 % 4 == 0 && N2 % 16 == 0, "tile shape");
@@ -52,7 +53,7 @@ struct Cfg {
   static constexpr int oB1 = oW1 + F1 * F1 * N1;
   static constexpr int oW2 = oB1 + N1;
   static constexpr int oB2 = oW2 + N1 * N2;
-  static constexpr int oW3 = oB2 + N2;           // repacked [dy][c2][8]
+  static constexpr int oW3 = oB2 + N2;           // repacked, 8 floats per (dy, c2)
   static constexpr int oIn = oW3 + F3 * N2 * 8;
   static constexpr int oO1 = oIn + IR * IWP;
   static constexpr int oO2 = oO1 + N1 * PXP;
@@ -90,9 +91,15 @@ __global__ void __launch_bounds__(256, 1) forward_fused_kernel(Args a) {
   for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i);
   for (int i = tid; i < C::N1 * C::N2; i += C::NT) sW2[i] = __ldg(a.pw2 + i);
   for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i);
-  for (int i = tid; i < C::F3 * C::N2 * 8; i += C::NT) {
-    const int dx = i % 8, c2 = (i / 8) % C::N2, dy = i / (8 * C::N2);
-    sW3[i] = dx < C::F3 ? __ldg(a.pw3 + (dy * C::F3 + dx) * C::N2 + c2) : 0.f;
+  // W3 repacked: taps dx 0..3 as [dy][c2][4], tap dx 4 as [dy][c2] behind them, so that the
+  // 16 lanes of a pixel group read consecutive 16-byte / 4-byte words (no bank conflicts)
+  for (int i = tid; i < C::F3 * C::N2 * 5; i += C::NT) {
+    const int dx = i % 5, c2 = (i / 5) % C::N2, dy = i / (5 * C::N2);
+    const float v = __ldg(a.pw3 + (dy * C::F3 + dx) * C::N2 + c2);
+    if (dx < 4)
+      sW3[(dy * C::N2 + c2) * 4 + dx] = v;
+    else
+      sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2] = v;
   }
   const float b3 = __ldg(a.pb3);
 
@@ -219,47 +226,80 @@ __global__ void __launch_bounds__(256, 1) forward_fused_kernel(Args a) {
     }
     __syncthreads();   // S2: out2 rows of this block complete; next input rows landed
 
-    // ================= L3: 4 px x N2/4 ch2 per thread, quarters folded by shuffle ======
-    for (int t0 = 0; t0 < C::L3_TASKS; t0 += C::NT) {
-      const int t = t0 + tid;
-      const bool live = t < C::L3_TASKS;
-      const int tt = live ? t : 0;
-      const int q = tt % 4;
-      const int pxg = (tt / 4) % C::NPG3;
-      const int r = tt / (4 * C::NPG3);
-      const int j = y0 - (C::F3 - 1) + r;   // output row relative to R0
-      const int jj = j < 0 ? 0 : j;         // (clamped for addressing; masked at the store)
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // ================= L3: 4 px x RB rows x N2/16 ch2 per thread ======================
+    // 16 lanes share a pixel group and split the channels (c2 = lane16 + 16*i); each lane
+    // keeps the 5x5 taps of its channel in registers and reuses every out2 row it loads for
+    // all output rows that see it.  The 16 partial sums are folded with four shuffles.
+    {
+      const int cgi = tid % 16;
+      const int pxg = tid / 16;
+      const bool live = pxg < C::NPG3;
+      const int pxa = live ? pxg : 0;
+      const int j0 = y0 - (C::F3 - 1);        // first output row of this block, rel. to R0
+      // ring slot of out2 row j0 (negative in the first block: those slots hold stale data
+      // that only ever reaches output rows < 0, which are masked at the store)
+      const int slot0 = ((j0 % C::RING) + C::RING) % C::RING;
+      float acc[C::RB][4];
+#pragma unroll
+      for (int r = 0; r < C::RB; r++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) acc[r][p] = 0.f;
 #pragma unroll 1
-      for (int dy = 0; dy < C::F3; dy++) {
-        const int slot = (jj + dy) % C::RING;
-        const float* vp = sO2 + (slot * C::N2 + q * (C::N2 / 4)) * C::OW2P + pxg * 4;
-        const float* wp = sW3 + (dy * C::N2 + q * (C::N2 / 4)) * 8;
+      for (int i = 0; i < C::N2 / 16; i++) {
+        const int c2 = cgi + 16 * i;
+        float wv[C::F3][C::F3];
 #pragma unroll
-        for (int c = 0; c < C::N2 / 4; c++) {
-          const float4 v0 = *reinterpret_cast<const float4*>(vp + c * C::OW2P);
-          const float4 v1 = *reinterpret_cast<const float4*>(vp + c * C::OW2P + 4);
-          const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8);
-          const float w4 = wp[c * 8 + 4];
+        for (int dy = 0; dy < C::F3; dy++) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sW3 + (dy * C::N2 + c2) * 4);
+          wv[dy][0] = w0.x;
+          wv[dy][1] = w0.y;
+          wv[dy][2] = w0.z;
+          wv[dy][3] = w0.w;
+          wv[dy][4] = sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2];
+        }
+        int slot = slot0;
+#pragma unroll
+        for (int jj = 0; jj < C::RB + C::F3 - 1; jj++) {
+          const float* vp = sO2 + (slot * C::N2 + c2) * C::OW2P + pxa * 4;
+          const float4 v0 = *reinterpret_cast<const float4*>(vp);
+          const float4 v1 = *reinterpret_cast<const float4*>(vp + 4);
           const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          const float wv[5] = {w0.x, w0.y, w0.z, w0.w, w4};
 #pragma unroll
-          for (int dx = 0; dx < 5; dx++)
+          for (int r = 0; r < C::RB; r++) {
+            const int dy = jj - r;
+            if (dy >= 0 && dy < C::F3) {
 #pragma unroll
-            for (int p = 0; p < 4; p++) acc[p] = fmaf(vv[p + dx], wv[dx], acc[p]);
+              for (int dx = 0; dx < C::F3; dx++)
+#pragma unroll
+                for (int p = 0; p < 4; p++) acc[r][p] = fmaf(vv[p + dx], wv[dy][dx], acc[r][p]);
+            }
+          }
+          slot = slot + 1 == C::RING ? 0 : slot + 1;
         }
       }
 #pragma unroll
-      for (int p = 0; p < 4; p++) {
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
-      }
-      if (live && q == 0 && j >= 0 && j < rows_here) {
-        const int gy = R0 + j;
+      for (int r = 0; r < C::RB; r++)
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-          const int gx = X0 + pxg * 4 + p;
-          if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[p] + b3;
+          float v = acc[r][p];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          acc[r][p] = v;
+        }
+      if (live && cgi == 0) {
+#pragma unroll
+        for (int r = 0; r < C::RB; r++) {
+          const int j = j0 + r;
+          if (j >= 0 && j < rows_here) {
+            const int gy = R0 + j;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+              const int gx = X0 + pxg * 4 + p;
+              if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[r][p] + b3;
+            }
+          }
         }
       }
     }

@@ -82,6 +82,16 @@ def transcribe_reference_specs():
         json.dump(b, fh, indent=1)
 
 
+def copy_config_fixtures():
+    """test/data/config*.json -> tests/golden/ref_config/ (reference: test/specs/ConfigTest.cpp)"""
+    import shutil
+    dst = os.path.join(HERE, "ref_config")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("config.json", "config_invalid_val.json", "config_non_parseable.json"):
+        shutil.copy(os.path.join(REF, "test/data", f), os.path.join(dst, f))
+    shutil.copy(os.path.join(REF, "example_config.json"), os.path.join(dst, "example_config.json"))
+
+
 def make_params(rng, n1, n2, f1, f2, f3, sd=0.05, bias_sd=0.01):
     return {
         "w1": rng.normal(0, sd, f1 * f1 * 1 * n1).astype(np.float32),
@@ -186,6 +196,7 @@ def reference_train_chain(ref, name, cfg, n_samples, w, h, chunk, epochs, full):
 
 def main():
     transcribe_reference_specs()
+    copy_config_fixtures()
     ref = Oracle("reference")
     reference_kernel_outputs(ref)
     reference_train_chain(ref, "ref_train_chain.npz", (4, 3, 3, 1, 3), 5, 9, 8, 2, 2, True)

@@ -75,6 +75,9 @@ struct srcnn_ctx {
   std::vector<srcnn::Allocation> allocs;
   srcnn::KernelStat stats[SRCNN_K_COUNT];
   uint64_t launch_count = 0;
+  // fused inference implementation: tensor cores (tcgen05, 3xTF32) where instantiated, unless
+  // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
+  bool fused_use_tc = true;
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand

@@ -1,0 +1,371 @@
+// Fused SRCNN inference, tensor-core version (9-1-5, n1=64, n2=32): layers 1 and 2 -- the two
+// dense contractions, 90 % of the FLOPs -- run on the 5th-generation tensor cores (tcgen05,
+// accumulators in TMEM); layer 3 (N = 1) stays FP32 SIMT with a warp-shuffle fold.
+//
+//   L1  D1[128 px][64] = A1[128 px][88] * W1[64][88]^T      A1 = im2col of the 9x9 window (81 taps
+//                                                            + 7 zero columns), built in smem
+//   L2  D2[128 px][32] = A2[128 px][64] * W2[32][64]^T      A2 = relu(D1 + b1), TMEM -> regs -> smem
+//   L3  out3 = b3 + W3 * relu(D2 + b2)-window               as in fused_forward.cuh
+//
+// Precision: operands are FP32 values split into TF32 hi + lo; every product is evaluated as
+// hi*hi + hi*lo + lo*hi with FP32 accumulation ("3xTF32"), measured at 8e-7 max error against
+// fp64 on a K=88 contraction (csrc/probe/tc_probe.cu) -- the same as FP32 FMA.  Plain TF32
+// (3e-4) cannot meet the path's 1e-4 tolerance.
+//
+// Tiling: as in the SIMT kernel a CTA owns 60 output columns x RPC output rows and marches down
+// the strip, here 2 rows (= one 128-pixel MMA tile) per step; input rows and out2 rows live in
+// circular row buffers.  Operands use the no-swizzle K-major canonical layout (tc_common.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "context.cuh"
+#include "fused_forward.cuh"
+#include "tc_common.cuh"
+
+namespace srcnn {
+namespace fused_tc {
+
+struct Cfg {
+  static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
+  static constexpr int NT = 256;
+  static constexpr int OW2 = 64, RB = 2;
+  static constexpr int OW3 = OW2 - (F3 - 1);
+  static constexpr int IW = OW2 + F1 - 1, IWP = IW + 4;
+  static constexpr int IR = RB + F1 - 1;
+  static constexpr int RING = RB + F3 - 1;
+  static constexpr int OW2P = OW2 + 4;
+  static constexpr int RPC = 128;
+  static constexpr int M = OW2 * RB;           // 128 pixels per MMA tile
+  static constexpr int K1 = 88;                // 81 taps padded to a multiple of 8
+  static constexpr int K2 = N1;
+  static constexpr int NPG3 = OW3 / 4;
+  // shared memory carve-up (floats).  A2 aliases A1: A1 is dead once MMA-1 has completed.
+  static constexpr int oA1h = 0;
+  static constexpr int oA1l = oA1h + M * K1;
+  static constexpr int oA2h = oA1h;
+  static constexpr int oA2l = oA2h + M * K2;
+  static constexpr int oW1h = oA1l + M * K1;
+  static constexpr int oW1l = oW1h + N1 * K1;
+  static constexpr int oW2h = oW1l + N1 * K1;
+  static constexpr int oW2l = oW2h + N2 * K2;
+  static constexpr int oB1 = oW2l + N2 * K2;
+  static constexpr int oB2 = oB1 + N1;
+  static constexpr int oW3 = oB2 + N2;         // [dy][c2][4] + [dy][c2]
+  static constexpr int oIn = oW3 + F3 * N2 * 5 + 4;
+  static constexpr int oO2 = oIn + IR * IWP;
+  static constexpr int TOTAL = oO2 + RING * N2 * OW2P;
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)TOTAL + 128;
+  static_assert(2 * M * K2 <= M * K1 + M * K1, "A2 must fit in the A1 area");
+  static constexpr uint32_t TMEM_COLS = 128;   // D1: columns 0..63, D2: columns 64..95
+};
+
+__global__ void __launch_bounds__(256, 1) forward_fused_tc_kernel(fused::Args a) {
+  using C = Cfg;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte aligned base (descriptor addresses are in 16-byte units; core matrices 128 B)
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                         ~(uintptr_t)127);
+  float* sA1h = smem + C::oA1h;
+  float* sA1l = smem + C::oA1l;
+  float* sA2h = smem + C::oA2h;
+  float* sA2l = smem + C::oA2l;
+  float* sW1h = smem + C::oW1h;
+  float* sW1l = smem + C::oW1l;
+  float* sW2h = smem + C::oW2h;
+  float* sW2l = smem + C::oW2l;
+  float* sB1 = smem + C::oB1;
+  float* sB2 = smem + C::oB2;
+  float* sW3 = smem + C::oW3;
+  float* sIn = smem + C::oIn;
+  float* sO2 = smem + C::oO2;
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int X0 = blockIdx.x * C::OW3;
+  const int R0 = blockIdx.y * C::RPC;
+  const float* img = a.in + (size_t)blockIdx.z * a.w * a.h;
+  float* dst = a.out + (size_t)blockIdx.z * a.w3 * a.h3;
+
+  // ---- stage parameters: B operands split into TF32 hi/lo, canonical [n][k] layout -------
+  for (int i = tid; i < C::N1 * C::K1; i += C::NT) {
+    const int n = i / C::K1, k = i % C::K1;
+    const float w = k < C::F1 * C::F1 ? __ldg(a.pw1 + k * C::N1 + n) : 0.f;
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    sW1h[kmajor_offset(n, k, C::K1)] = hi;
+    sW1l[kmajor_offset(n, k, C::K1)] = lo;
+  }
+  for (int i = tid; i < C::N2 * C::K2; i += C::NT) {
+    const int n = i / C::K2, k = i % C::K2;
+    float hi, lo;
+    split_tf32(__ldg(a.pw2 + k * C::N2 + n), hi, lo);
+    sW2h[kmajor_offset(n, k, C::K2)] = hi;
+    sW2l[kmajor_offset(n, k, C::K2)] = lo;
+  }
+  for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i);
+  for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i);
+  for (int i = tid; i < C::F3 * C::N2 * 5; i += C::NT) {
+    const int dx = i % 5, c2 = (i / 5) % C::N2, dy = i / (5 * C::N2);
+    const float v = __ldg(a.pw3 + (dy * C::F3 + dx) * C::N2 + c2);
+    if (dx < 4)
+      sW3[(dy * C::N2 + c2) * 4 + dx] = v;
+    else
+      sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2] = v;
+  }
+  const float b3 = __ldg(a.pb3);
+
+  auto load_rows = [&](int first_rel_row, int count) {
+    for (int i = tid; i < count * C::IW; i += C::NT) {
+      const int rr = first_rel_row + i / C::IW, xx = i % C::IW;
+      const int gy = R0 + rr, gx = X0 + xx;
+      const float v = (gy < a.h && gx < a.w) ? __ldg(img + (size_t)gy * a.w + gx) : 0.f;
+      sIn[(rr % C::IR) * C::IWP + xx] = v;
+    }
+  };
+  load_rows(0, C::F1 - 1 + C::RB);
+
+  if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar1, 1);
+    mbar_init(&bar2, 1);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc1 = make_idesc_tf32(C::M, C::N1);
+  const uint32_t idesc2 = make_idesc_tf32(C::M, C::N2);
+
+  const int rows_here = min(C::RPC, a.h3 - R0);
+  const int n_blocks = (rows_here + (C::F3 - 1) + C::RB - 1) / C::RB;
+
+  // im2col role: row m of the tile and half of the K chunks
+  const int im_m = tid & (C::M - 1);
+  const int im_half = tid >> 7;              // 0: chunks 0..10, 1: chunks 11..21
+  const int im_r = im_m / C::OW2, im_x = im_m % C::OW2;
+  // epilogue role: TMEM lane quarter + column half
+  const int ep_q = warp & 3, ep_h = warp >> 2;
+  const int ep_m = ep_q * 32 + lane;
+  // L3 role
+  const int cgi = tid % 16, pxg = tid / 16;
+  const bool l3_live = pxg < C::NPG3;
+  const int pxa = l3_live ? pxg : 0;
+  float w3r[2][C::F3][C::F3];   // the 5x5 taps of this lane's two channels stay in registers
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int dy = 0; dy < C::F3; dy++) {
+      const int c2 = cgi + 16 * i;
+      const float4 w0 = *reinterpret_cast<const float4*>(sW3 + (dy * C::N2 + c2) * 4);
+      w3r[i][dy][0] = w0.x;
+      w3r[i][dy][1] = w0.y;
+      w3r[i][dy][2] = w0.z;
+      w3r[i][dy][3] = w0.w;
+      w3r[i][dy][4] = sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2];
+    }
+
+  uint32_t parity = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    const int y0 = b * C::RB;
+
+    // ================= im2col: A1[m][k] = in[r+dy][x+dx], k = dy*9+dx, split hi/lo ==========
+    {
+      const int base_slot = (y0 + im_r) % C::IR;
+#pragma unroll
+      for (int cc = 0; cc < 11; cc++) {
+        const int c = im_half * 11 + cc;      // 16-byte K chunk
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int k = c * 4 + j;
+          float v = 0.f;
+          if (k < C::F1 * C::F1) {
+            const int dy = k / C::F1, dx = k - dy * C::F1;
+            int slot = base_slot + dy;
+            slot = slot >= C::IR ? slot - C::IR : slot;
+            v = sIn[slot * C::IWP + im_x + dx];
+          }
+          split_tf32(v, hi[j], lo[j]);
+        }
+        const int off = kmajor_offset(im_m, c * 4, C::K1);
+        *reinterpret_cast<float4*>(sA1h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();   // A1 complete; input ring rows of this block are dead
+
+    // ================= MMA-1: D1 = A1 * W1^T  (33 x M128 N64 K8) =============================
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t sbo = 128 * (C::K1 / 4);
+#pragma unroll 1
+      for (int ks = 0; ks < C::K1 / 8; ks++) {
+        const uint64_t ah = make_desc_kmajor(sA1h, ks * 256, 128, sbo);
+        const uint64_t al = make_desc_kmajor(sA1l, ks * 256, 128, sbo);
+        const uint64_t bh = make_desc_kmajor(sW1h, ks * 256, 128, sbo);
+        const uint64_t bl = make_desc_kmajor(sW1l, ks * 256, 128, sbo);
+        mma_tf32(tmem, al, bh, idesc1, ks > 0);
+        mma_tf32(tmem, ah, bl, idesc1, 1);
+        mma_tf32(tmem, ah, bh, idesc1, 1);
+      }
+      mma_commit(&bar1);
+    }
+    // meanwhile: next block's input rows (overwrites the RB oldest ring rows)
+    if (b + 1 < n_blocks) load_rows((b + 1) * C::RB + C::F1 - 1, C::RB);
+    mbar_wait(&bar1, parity);
+    tcgen05_fence_after();
+
+    // ================= epilogue 1: A2 = split(relu(D1 + b1)) ================================
+    {
+      const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + ep_h * 32;
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        float v[16];
+        tmem_ld16(taddr + g * 16, v);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int ch = ep_h * 32 + g * 16 + c4 * 4 + j;
+            split_tf32(fmaxf(v[c4 * 4 + j] + sB1[ch], 0.f), hi[j], lo[j]);
+          }
+          const int off = kmajor_offset(ep_m, ep_h * 32 + g * 16 + c4 * 4, C::K2);
+          *reinterpret_cast<float4*>(sA2h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(sA2l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();   // A2 complete, D1 fully read
+
+    // ================= MMA-2: D2 = A2 * W2^T  (24 x M128 N32 K8) =============================
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t sbo = 128 * (C::K2 / 4);
+#pragma unroll 1
+      for (int ks = 0; ks < C::K2 / 8; ks++) {
+        const uint64_t ah = make_desc_kmajor(sA2h, ks * 256, 128, sbo);
+        const uint64_t al = make_desc_kmajor(sA2l, ks * 256, 128, sbo);
+        const uint64_t bh = make_desc_kmajor(sW2h, ks * 256, 128, sbo);
+        const uint64_t bl = make_desc_kmajor(sW2l, ks * 256, 128, sbo);
+        mma_tf32(tmem + 64, al, bh, idesc2, ks > 0);
+        mma_tf32(tmem + 64, ah, bl, idesc2, 1);
+        mma_tf32(tmem + 64, ah, bh, idesc2, 1);
+      }
+      mma_commit(&bar2);
+    }
+    mbar_wait(&bar2, parity);
+    tcgen05_fence_after();
+    parity ^= 1;
+
+    // ================= epilogue 2: out2 = relu(D2 + b2) -> ring, channel-major ==============
+    {
+      const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + 64 + ep_h * 16;
+      float v[16];
+      tmem_ld16(taddr, v);
+      const int r = ep_m / C::OW2, x = ep_m % C::OW2;
+      const int slot = (y0 + r) % C::RING;
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int c2 = ep_h * 16 + j;
+        sO2[(slot * C::N2 + c2) * C::OW2P + x] = fmaxf(v[j] + sB2[c2], 0.f);
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();   // out2 rows of this block complete; D2 fully read; next input rows landed
+
+    // ================= L3 (FP32 SIMT): 4 px x RB rows x 2 ch per thread =====================
+    {
+      const int j0 = y0 - (C::F3 - 1);
+      const int slot0 = ((j0 % C::RING) + C::RING) % C::RING;
+      float acc[C::RB][4];
+#pragma unroll
+      for (int r = 0; r < C::RB; r++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) acc[r][p] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int c2 = cgi + 16 * i;
+        int slot = slot0;
+#pragma unroll
+        for (int jj = 0; jj < C::RB + C::F3 - 1; jj++) {
+          const float* vp = sO2 + (slot * C::N2 + c2) * C::OW2P + pxa * 4;
+          const float4 v0 = *reinterpret_cast<const float4*>(vp);
+          const float4 v1 = *reinterpret_cast<const float4*>(vp + 4);
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int r = 0; r < C::RB; r++) {
+            const int dy = jj - r;
+            if (dy >= 0 && dy < C::F3) {
+#pragma unroll
+              for (int dx = 0; dx < C::F3; dx++)
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+                  acc[r][p] = fmaf(vv[p + dx], w3r[i][dy][dx], acc[r][p]);
+            }
+          }
+          slot = slot + 1 == C::RING ? 0 : slot + 1;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < C::RB; r++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          float v = acc[r][p];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          acc[r][p] = v;
+        }
+      if (l3_live && cgi == 0) {
+#pragma unroll
+        for (int r = 0; r < C::RB; r++) {
+          const int j = j0 + r;
+          if (j >= 0 && j < rows_here) {
+            const int gy = R0 + j;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+              const int gx = X0 + pxg * 4 + p;
+              if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[r][p] + b3;
+            }
+          }
+        }
+      }
+    }
+    // the next im2col writes A1 (= A2 area, last read by MMA-2, complete since bar2) and reads
+    // the input ring (complete at the last barrier); the next epilogue 2 writes ring rows that
+    // this L3 reads only if RING were smaller than RB + 4 -- guarded by the barrier after
+    // im2col, which every thread passes only after finishing this L3.
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+inline int configure() {
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_tc_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
+  return SRCNN_OK;
+}
+
+inline bool supported(int n1, int n2, int f1, int f2, int f3) {
+  return n1 == 64 && n2 == 32 && f1 == 9 && f2 == 1 && f3 == 5;
+}
+
+inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S) {
+  dim3 grid((a.w3 + Cfg::OW3 - 1) / Cfg::OW3, (a.h3 + Cfg::RPC - 1) / Cfg::RPC, S);
+  forward_fused_tc_kernel<<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a);
+  return SRCNN_OK;
+}
+
+}  // namespace fused_tc
+}  // namespace srcnn

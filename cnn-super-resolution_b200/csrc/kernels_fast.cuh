@@ -7,6 +7,10 @@
 
 #include "context.cuh"
 #include "fused_forward.cuh"
+#include "fused_forward_tc.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace srcnn {
 namespace fast {
@@ -49,8 +53,10 @@ __global__ void update_all_kernel(UpdateAllArgs a) {
 
 // one-time per-context setup (opt-in shared memory sizes etc.)
 inline int configure(srcnn_ctx* ctx) {
-  (void)ctx;
   SRCNN_TRY(fused::configure());
+  SRCNN_TRY(fused_tc::configure());
+  const char* impl = std::getenv("SRCNN_FUSED_IMPL");
+  ctx->fused_use_tc = !(impl && std::strcmp(impl, "simt") == 0);
   return SRCNN_OK;
 }
 
@@ -83,6 +89,7 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
+  if (ctx->fused_use_tc && fused_tc::supported(n1, n2, f1, f2, f3)) return fused_tc::launch(ctx, a, S);
   return fused::launch(ctx, n1, n2, a, S);
 }
 

@@ -4,7 +4,7 @@
 //
 //   L1  D1[128 px][64] = A1[128 px][88] * W1[64][88]^T      A1 = im2col of the 9x9 window (81 taps
 //                                                            + 7 zero columns), built in smem
-//   L2  D2[128 px][32] = A2[128 px][64] * W2[32][64]^T      A2 = relu(D1 + b1), TMEM -> regs -> smem
+//   L2  D2[128 px][32] = A2[128 px][64] * W2[32][64]^T      A2 = relu(D1 + b1), TMEM -> regs -> TMEM
 //   L3  out3 = b3 + W3 * relu(D2 + b2)-window               as in fused_forward.cuh
 //
 // Precision: operands are FP32 values split into TF32 hi + lo; every product is evaluated as
@@ -27,11 +27,12 @@ namespace fused_tc {
 
 struct Cfg {
   static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
-  static constexpr int NT = 256;
+  static constexpr int NW = 256;               // worker threads (im2col, epilogues, L3)
+  static constexpr int NT = NW + 32;           // + one warp that only issues the MMAs
   static constexpr int OW2 = 64, RB = 2;
   static constexpr int OW3 = OW2 - (F3 - 1);
   static constexpr int IW = OW2 + F1 - 1, IWP = IW + 4;
-  static constexpr int IR = RB + F1 - 1;
+  static constexpr int IR = RB + F1 - 1 + RB;  // one block of slack: rows of tile b+2 land while tile b+1 is read
   static constexpr int RING = RB + F3 - 1;
   static constexpr int OW2P = OW2 + 4;
   static constexpr int RPC = 128;
@@ -39,11 +40,9 @@ struct Cfg {
   static constexpr int K1 = 88;                // 81 taps padded to a multiple of 8
   static constexpr int K2 = N1;
   static constexpr int NPG3 = OW3 / 4;
-  // shared memory carve-up (floats).  A2 aliases A1: A1 is dead once MMA-1 has completed.
+  // shared memory carve-up (floats)
   static constexpr int oA1h = 0;
   static constexpr int oA1l = oA1h + M * K1;
-  static constexpr int oA2h = oA1h;
-  static constexpr int oA2l = oA2h + M * K2;
   static constexpr int oW1h = oA1l + M * K1;
   static constexpr int oW1l = oW1h + N1 * K1;
   static constexpr int oW2h = oW1l + N1 * K1;
@@ -54,22 +53,20 @@ struct Cfg {
   static constexpr int oIn = oW3 + F3 * N2 * 5 + 4;
   static constexpr int oO2 = oIn + IR * IWP;
   static constexpr int TOTAL = oO2 + RING * N2 * OW2P;
-  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)TOTAL + 128;
-  static_assert(2 * M * K2 <= M * K1 + M * K1, "A2 must fit in the A1 area");
-  static constexpr uint32_t TMEM_COLS = 128;   // D1: columns 0..63, D2: columns 64..95
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)TOTAL;
+  // tensor memory columns: D1 accumulator, D2 accumulator, A2 = relu(D1+b1) split hi / lo
+  static constexpr uint32_t cD1 = 0, cD2 = 64, cA2h = 128, cA2l = 192;
+  static constexpr uint32_t TMEM_COLS = 256;
 };
 
-__global__ void __launch_bounds__(256, 1) forward_fused_tc_kernel(fused::Args a) {
+__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Args a) {
   using C = Cfg;
   using namespace tc;
-  extern __shared__ uint8_t smem_raw[];
-  // 128-byte aligned base (descriptor addresses are in 16-byte units; core matrices 128 B)
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                         ~(uintptr_t)127);
+  // 128-byte aligned dynamic shared memory (descriptor addresses are in 16-byte units, core
+  // matrices are 128 B); indexing the extern array directly keeps the accesses LDS/STS
+  extern __shared__ __align__(128) float smem[];
   float* sA1h = smem + C::oA1h;
   float* sA1l = smem + C::oA1l;
-  float* sA2h = smem + C::oA2h;
-  float* sA2l = smem + C::oA2l;
   float* sW1h = smem + C::oW1h;
   float* sW1l = smem + C::oW1l;
   float* sW2h = smem + C::oW2h;
@@ -117,17 +114,18 @@ __global__ void __launch_bounds__(256, 1) forward_fused_tc_kernel(fused::Args a)
   const float b3 = __ldg(a.pb3);
 
   auto load_rows = [&](int first_rel_row, int count) {
-    for (int i = tid; i < count * C::IW; i += C::NT) {
+    for (int i = tid; i < count * C::IW; i += C::NW) {
       const int rr = first_rel_row + i / C::IW, xx = i % C::IW;
       const int gy = R0 + rr, gx = X0 + xx;
       const float v = (gy < a.h && gx < a.w) ? __ldg(img + (size_t)gy * a.w + gx) : 0.f;
       sIn[(rr % C::IR) * C::IWP + xx] = v;
     }
   };
-  load_rows(0, C::F1 - 1 + C::RB);
+  load_rows(0, C::F1 - 1 + C::RB);   // input rows of tile 0
 
   if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
   if (tid == 0) {
+    if (smem_u32(smem) & 127u) __trap();   // operand layout needs a 128-byte aligned base
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
   }
@@ -166,183 +164,228 @@ __global__ void __launch_bounds__(256, 1) forward_fused_tc_kernel(fused::Args a)
       w3r[i][dy][4] = sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2];
     }
 
-  uint32_t parity = 0;
-  for (int b = 0; b < n_blocks; b++) {
-    const int y0 = b * C::RB;
-
-    // ================= im2col: A1[m][k] = in[r+dy][x+dx], k = dy*9+dx, split hi/lo ==========
-    {
-      const int base_slot = (y0 + im_r) % C::IR;
+  // ---- pipeline stages ------------------------------------------------------------------
+  // im2col of tile b: A1[m][k] = in[r+dy][x+dx], k = dy*9+dx, split hi/lo
+  auto im2col = [&](int b) {
+    const int base_slot = (b * C::RB + im_r) % C::IR;
 #pragma unroll
-      for (int cc = 0; cc < 11; cc++) {
-        const int c = im_half * 11 + cc;      // 16-byte K chunk
-        float hi[4], lo[4];
+    for (int cc = 0; cc < 11; cc++) {
+      const int c = im_half * 11 + cc;      // 16-byte K chunk
+      float hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int k = c * 4 + j;
-          float v = 0.f;
-          if (k < C::F1 * C::F1) {
-            const int dy = k / C::F1, dx = k - dy * C::F1;
-            int slot = base_slot + dy;
-            slot = slot >= C::IR ? slot - C::IR : slot;
-            v = sIn[slot * C::IWP + im_x + dx];
-          }
-          split_tf32(v, hi[j], lo[j]);
+      for (int j = 0; j < 4; j++) {
+        const int k = c * 4 + j;
+        float v = 0.f;
+        if (k < C::F1 * C::F1) {
+          const int dy = k / C::F1, dx = k - dy * C::F1;
+          int slot = base_slot + dy;
+          slot = slot >= C::IR ? slot - C::IR : slot;
+          v = sIn[slot * C::IWP + im_x + dx];
         }
-        const int off = kmajor_offset(im_m, c * 4, C::K1);
-        *reinterpret_cast<float4*>(sA1h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        split_tf32(v, hi[j], lo[j]);
       }
+      const int off = kmajor_offset(im_m, c * 4, C::K1);
+      *reinterpret_cast<float4*>(sA1h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
-    fence_proxy_async();
-    tcgen05_fence_before();
-    __syncthreads();   // A1 complete; input ring rows of this block are dead
-
-    // ================= MMA-1: D1 = A1 * W1^T  (33 x M128 N64 K8) =============================
-    if (tid == 0) {
-      tcgen05_fence_after();
-      const uint32_t sbo = 128 * (C::K1 / 4);
-#pragma unroll 1
-      for (int ks = 0; ks < C::K1 / 8; ks++) {
-        const uint64_t ah = make_desc_kmajor(sA1h, ks * 256, 128, sbo);
-        const uint64_t al = make_desc_kmajor(sA1l, ks * 256, 128, sbo);
-        const uint64_t bh = make_desc_kmajor(sW1h, ks * 256, 128, sbo);
-        const uint64_t bl = make_desc_kmajor(sW1l, ks * 256, 128, sbo);
-        mma_tf32(tmem, al, bh, idesc1, ks > 0);
-        mma_tf32(tmem, ah, bl, idesc1, 1);
-        mma_tf32(tmem, ah, bh, idesc1, 1);
-      }
-      mma_commit(&bar1);
-    }
-    // meanwhile: next block's input rows (overwrites the RB oldest ring rows)
-    if (b + 1 < n_blocks) load_rows((b + 1) * C::RB + C::F1 - 1, C::RB);
-    mbar_wait(&bar1, parity);
+  };
+  // MMA-1: D1 = A1 * W1^T  (33 x M128 N64 K8), one thread.  A k-step advances every operand by
+  // two 128-byte core matrices = 16 in the descriptor's 16-byte address units.
+  auto issue_mma1 = [&]() {
     tcgen05_fence_after();
-
-    // ================= epilogue 1: A2 = split(relu(D1 + b1)) ================================
-    {
-      const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + ep_h * 32;
+    const uint32_t sbo = 128 * (C::K1 / 4);
+    uint64_t ah = make_desc_kmajor(sA1h, 0, 128, sbo), al = make_desc_kmajor(sA1l, 0, 128, sbo);
+    uint64_t bh = make_desc_kmajor(sW1h, 0, 128, sbo), bl = make_desc_kmajor(sW1l, 0, 128, sbo);
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        float v[16];
-        tmem_ld16(taddr + g * 16, v);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          float hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int ch = ep_h * 32 + g * 16 + c4 * 4 + j;
-            split_tf32(fmaxf(v[c4 * 4 + j] + sB1[ch], 0.f), hi[j], lo[j]);
-          }
-          const int off = kmajor_offset(ep_m, ep_h * 32 + g * 16 + c4 * 4, C::K2);
-          *reinterpret_cast<float4*>(sA2h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(sA2l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
+    for (int ks = 0; ks < C::K1 / 8; ks++) {
+      mma_tf32(tmem + C::cD1, al, bh, idesc1, ks > 0);
+      mma_tf32(tmem + C::cD1, ah, bl, idesc1, 1);
+      mma_tf32(tmem + C::cD1, ah, bh, idesc1, 1);
+      ah += 16; al += 16; bh += 16; bl += 16;
     }
-    fence_proxy_async();
-    tcgen05_fence_before();
-    __syncthreads();   // A2 complete, D1 fully read
-
-    // ================= MMA-2: D2 = A2 * W2^T  (24 x M128 N32 K8) =============================
-    if (tid == 0) {
-      tcgen05_fence_after();
-      const uint32_t sbo = 128 * (C::K2 / 4);
-#pragma unroll 1
-      for (int ks = 0; ks < C::K2 / 8; ks++) {
-        const uint64_t ah = make_desc_kmajor(sA2h, ks * 256, 128, sbo);
-        const uint64_t al = make_desc_kmajor(sA2l, ks * 256, 128, sbo);
-        const uint64_t bh = make_desc_kmajor(sW2h, ks * 256, 128, sbo);
-        const uint64_t bl = make_desc_kmajor(sW2l, ks * 256, 128, sbo);
-        mma_tf32(tmem + 64, al, bh, idesc2, ks > 0);
-        mma_tf32(tmem + 64, ah, bl, idesc2, 1);
-        mma_tf32(tmem + 64, ah, bh, idesc2, 1);
-      }
-      mma_commit(&bar2);
-    }
-    mbar_wait(&bar2, parity);
+    mma_commit(&bar1);
+  };
+  // MMA-2: D2 = A2 * W2^T  (24 x M128 N32 K8), A2 hi/lo in tensor memory
+  auto issue_mma2 = [&]() {
     tcgen05_fence_after();
-    parity ^= 1;
-
-    // ================= epilogue 2: out2 = relu(D2 + b2) -> ring, channel-major ==============
-    {
-      const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + 64 + ep_h * 16;
+    const uint32_t sbo = 128 * (C::K2 / 4);
+    uint64_t bh = make_desc_kmajor(sW2h, 0, 128, sbo), bl = make_desc_kmajor(sW2l, 0, 128, sbo);
+#pragma unroll
+    for (int ks = 0; ks < C::K2 / 8; ks++) {
+      mma_tf32_ts(tmem + C::cD2, tmem + C::cA2l + ks * 8, bh, idesc2, ks > 0);
+      mma_tf32_ts(tmem + C::cD2, tmem + C::cA2h + ks * 8, bl, idesc2, 1);
+      mma_tf32_ts(tmem + C::cD2, tmem + C::cA2h + ks * 8, bh, idesc2, 1);
+      bh += 16; bl += 16;
+    }
+    mma_commit(&bar2);
+  };
+  // epilogue 1: A2 = split(relu(D1 + b1)) -> tensor memory
+  auto epilogue1 = [&]() {
+    const uint32_t lane_base = (uint32_t)(ep_q * 32) << 16;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
       float v[16];
-      tmem_ld16(taddr, v);
-      const int r = ep_m / C::OW2, x = ep_m % C::OW2;
-      const int slot = (y0 + r) % C::RING;
+      const int c0 = ep_h * 32 + g * 16;
+      tmem_ld16(tmem + lane_base + C::cD1 + c0, v);
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int c2 = ep_h * 16 + j;
-        sO2[(slot * C::N2 + c2) * C::OW2P + x] = fmaxf(v[j] + sB2[c2], 0.f);
+      for (int h8 = 0; h8 < 2; h8++) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          split_tf32(fmaxf(v[h8 * 8 + j] + sB1[c0 + h8 * 8 + j], 0.f), hi[j], lo[j]);
+        tmem_st8(tmem + lane_base + C::cA2h + c0 + h8 * 8, hi);
+        tmem_st8(tmem + lane_base + C::cA2l + c0 + h8 * 8, lo);
       }
     }
-    tcgen05_fence_before();
-    __syncthreads();   // out2 rows of this block complete; D2 fully read; next input rows landed
-
-    // ================= L3 (FP32 SIMT): 4 px x RB rows x 2 ch per thread =====================
-    {
-      const int j0 = y0 - (C::F3 - 1);
-      const int slot0 = ((j0 % C::RING) + C::RING) % C::RING;
-      float acc[C::RB][4];
+    tmem_st_wait();
+  };
+  // epilogue 2 of tile b: out2 = relu(D2 + b2) -> ring, channel-major
+  auto epilogue2 = [&](int b) {
+    const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + C::cD2 + ep_h * 16;
+    float v[16];
+    tmem_ld16(taddr, v);
+    const int r = ep_m / C::OW2, x = ep_m % C::OW2;
+    const int slot = (b * C::RB + r) % C::RING;
 #pragma unroll
-      for (int r = 0; r < C::RB; r++)
+    for (int j = 0; j < 16; j++) {
+      const int c2 = ep_h * 16 + j;
+      sO2[(slot * C::N2 + c2) * C::OW2P + x] = fmaxf(v[j] + sB2[c2], 0.f);
+    }
+  };
+  // L3 (FP32 SIMT) for the output rows completed by tile b: 4 px x RB rows x 2 ch per thread
+  auto layer3 = [&](int b) {
+    const int j0 = b * C::RB - (C::F3 - 1);
+    const int slot0 = ((j0 % C::RING) + C::RING) % C::RING;
+    float acc[C::RB][4];
 #pragma unroll
-        for (int p = 0; p < 4; p++) acc[r][p] = 0.f;
+    for (int r = 0; r < C::RB; r++)
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        const int c2 = cgi + 16 * i;
-        int slot = slot0;
+      for (int p = 0; p < 4; p++) acc[r][p] = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < C::RB + C::F3 - 1; jj++) {
-          const float* vp = sO2 + (slot * C::N2 + c2) * C::OW2P + pxa * 4;
-          const float4 v0 = *reinterpret_cast<const float4*>(vp);
-          const float4 v1 = *reinterpret_cast<const float4*>(vp + 4);
-          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    for (int i = 0; i < 2; i++) {
+      const int c2 = cgi + 16 * i;
+      int slot = slot0;
 #pragma unroll
-          for (int r = 0; r < C::RB; r++) {
-            const int dy = jj - r;
-            if (dy >= 0 && dy < C::F3) {
-#pragma unroll
-              for (int dx = 0; dx < C::F3; dx++)
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-                  acc[r][p] = fmaf(vv[p + dx], w3r[i][dy][dx], acc[r][p]);
-            }
-          }
-          slot = slot + 1 == C::RING ? 0 : slot + 1;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < C::RB; r++)
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-          float v = acc[r][p];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          acc[r][p] = v;
-        }
-      if (l3_live && cgi == 0) {
+      for (int jj = 0; jj < C::RB + C::F3 - 1; jj++) {
+        const float* vp = sO2 + (slot * C::N2 + c2) * C::OW2P + pxa * 4;
+        const float4 v0 = *reinterpret_cast<const float4*>(vp);
+        const float4 v1 = *reinterpret_cast<const float4*>(vp + 4);
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
         for (int r = 0; r < C::RB; r++) {
-          const int j = j0 + r;
-          if (j >= 0 && j < rows_here) {
-            const int gy = R0 + j;
+          const int dy = jj - r;
+          if (dy >= 0 && dy < C::F3) {
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-              const int gx = X0 + pxg * 4 + p;
-              if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[r][p] + b3;
-            }
+            for (int dx = 0; dx < C::F3; dx++)
+#pragma unroll
+              for (int p = 0; p < 4; p++)
+                acc[r][p] = fmaf(vv[p + dx], w3r[i][dy][dx], acc[r][p]);
+          }
+        }
+        slot = slot + 1 == C::RING ? 0 : slot + 1;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < C::RB; r++)
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        float v = acc[r][p];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        acc[r][p] = v;
+      }
+    if (l3_live && cgi == 0) {
+#pragma unroll
+      for (int r = 0; r < C::RB; r++) {
+        const int j = j0 + r;
+        if (j >= 0 && j < rows_here) {
+          const int gy = R0 + j;
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            const int gx = X0 + pxg * 4 + p;
+            if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[r][p] + b3;
           }
         }
       }
     }
-    // the next im2col writes A1 (= A2 area, last read by MMA-2, complete since bar2) and reads
-    // the input ring (complete at the last barrier); the next epilogue 2 writes ring rows that
-    // this L3 reads only if RING were smaller than RB + 4 -- guarded by the barrier after
-    // im2col, which every thread passes only after finishing this L3.
+  };
+
+  // ---- software pipeline: MMA-1(b) runs under epilogue-2 + L3 of tile b-1, MMA-2(b) under the
+  // im2col of tile b+1.  Warp 8 only issues the MMAs (one lane), so descriptor set-up and the
+  // 33 + 24 issue slots are off the workers' critical path; it takes part in the same
+  // __syncthreads sequence as the workers.
+  const bool is_worker = tid < C::NW;
+  // input rows of tile b+2 are fetched into a register before the im2col of tile b+1 and
+  // stored after it (one element per thread covers RB rows), hiding the global-load latency
+  auto prefetch_row_elem = [&](int first_rel_row, float& v, int& dst_index) {
+    dst_index = -1;
+    if (tid < C::RB * C::IW) {
+      const int rr = first_rel_row + tid / C::IW, xx = tid % C::IW;
+      const int gy = R0 + rr, gx = X0 + xx;
+      v = (gy < a.h && gx < a.w) ? __ldg(img + (size_t)gy * a.w + gx) : 0.f;
+      dst_index = (rr % C::IR) * C::IWP + xx;
+    }
+  };
+  static_assert(C::RB * C::IW <= C::NW, "one prefetched element per worker thread");
+
+  if (is_worker) {
+    im2col(0);
+    if (n_blocks > 1) load_rows(C::RB + C::F1 - 1, C::RB);   // input rows of tile 1
+    fence_proxy_async();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (is_worker) {
+    for (int b = 0; b < n_blocks; b++) {
+      if (b > 0) {
+        mbar_wait(&bar2, (uint32_t)((b - 1) & 1));      // MMA-2(b-1) done
+        tcgen05_fence_after();
+        epilogue2(b - 1);
+        tcgen05_fence_before();
+        __syncthreads();                                // (B1) out2 rows of tile b-1 visible
+        layer3(b - 1);
+      }
+      mbar_wait(&bar1, (uint32_t)(b & 1));              // MMA-1(b) done: D1 ready, A1 free
+      tcgen05_fence_after();
+      epilogue1();
+      tcgen05_fence_before();
+      __syncthreads();                                  // (B2) A2 complete, D1 fully read
+      if (b + 1 < n_blocks) {
+        float pre = 0.f;
+        int pre_idx = -1;
+        if (b + 2 < n_blocks) prefetch_row_elem((b + 2) * C::RB + C::F1 - 1, pre, pre_idx);
+        im2col(b + 1);
+        if (pre_idx >= 0) sIn[pre_idx] = pre;
+        fence_proxy_async();
+      }
+      tcgen05_fence_before();
+      __syncthreads();                                  // (B3) A1(b+1) complete
+    }
+    mbar_wait(&bar2, (uint32_t)((n_blocks - 1) & 1));
+    tcgen05_fence_after();
+    epilogue2(n_blocks - 1);
+    tcgen05_fence_before();
+    __syncthreads();                                    // (B4)
+    layer3(n_blocks - 1);
+  } else {
+    const bool issuer = lane == 0;
+    for (int b = 0; b < n_blocks; b++) {
+      if (issuer) issue_mma1();                         // A1(b) ready; D1 free since epilogue1(b-1)
+      __syncwarp();
+      if (b > 0) {
+        tcgen05_fence_before();
+        __syncthreads();                                // (B1)
+      }
+      tcgen05_fence_before();
+      __syncthreads();                                  // (B2)
+      if (issuer) issue_mma2();                         // A2(b) ready; D2 free since epilogue2(b-1)
+      __syncwarp();
+      tcgen05_fence_before();
+      __syncthreads();                                  // (B3)
+    }
+    __syncthreads();                                    // (B4)
   }
 
   tcgen05_fence_before();

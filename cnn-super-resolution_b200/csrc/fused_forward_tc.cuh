@@ -18,6 +18,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "context.cuh"
 #include "fused_forward.cuh"
 #include "tc_common.cuh"
@@ -168,26 +170,41 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   // im2col of tile b: A1[m][k] = in[r+dy][x+dx], k = dy*9+dx, split hi/lo
   auto im2col = [&](int b) {
     const int base_slot = (b * C::RB + im_r) % C::IR;
+    // ring-row pointers of the nine input rows this pixel reads, computed once
+    const float* rowp[C::F1];
 #pragma unroll
-    for (int cc = 0; cc < 11; cc++) {
-      const int c = im_half * 11 + cc;      // 16-byte K chunk
-      float hi[4], lo[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int k = c * 4 + j;
-        float v = 0.f;
-        if (k < C::F1 * C::F1) {
-          const int dy = k / C::F1, dx = k - dy * C::F1;
-          int slot = base_slot + dy;
-          slot = slot >= C::IR ? slot - C::IR : slot;
-          v = sIn[slot * C::IWP + im_x + dx];
-        }
-        split_tf32(v, hi[j], lo[j]);
-      }
-      const int off = kmajor_offset(im_m, c * 4, C::K1);
-      *reinterpret_cast<float4*>(sA1h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    for (int dy = 0; dy < C::F1; dy++) {
+      int slot = base_slot + dy;
+      slot = slot >= C::IR ? slot - C::IR : slot;
+      rowp[dy] = sIn + slot * C::IWP + im_x;
     }
+    // the K half is a compile-time constant inside `half`, so every (dy, dx) below is too and
+    // rowp[] stays in registers
+    auto half = [&](auto half_tag) {
+      constexpr int H = decltype(half_tag)::value;
+#pragma unroll
+      for (int cc = 0; cc < 11; cc++) {
+        const int c = H * 11 + cc;      // 16-byte K chunk
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int k = c * 4 + j;
+          float v = 0.f;
+          if (k < C::F1 * C::F1) {
+            const int dy = k / C::F1, dx = k - dy * C::F1;
+            v = rowp[dy][dx];
+          }
+          split_tf32(v, hi[j], lo[j]);
+        }
+        const int off = kmajor_offset(im_m, c * 4, C::K1);
+        *reinterpret_cast<float4*>(sA1h + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    };
+    if (im_half == 0)
+      half(std::integral_constant<int, 0>{});
+    else
+      half(std::integral_constant<int, 1>{});
   };
   // MMA-1: D1 = A1 * W1^T  (33 x M128 N64 K8), one thread.  A k-step advances every operand by
   // two 128-byte core matrices = 16 in the descriptor's 16-byte address units.

@@ -8,6 +8,7 @@
 #include "context.cuh"
 #include "fused_forward.cuh"
 #include "fused_forward_tc.cuh"
+#include "train_kernels.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -61,20 +62,25 @@ inline int configure(srcnn_ctx* ctx) {
 }
 
 // returns true when it launched
-inline bool forward_layer(srcnn_ctx*, const float*, float*, const float*, const float*, int, int,
-                          int, bool, int, int, int) {
-  return false;
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// returns true when it launched
+inline bool forward_layer(srcnn_ctx* ctx, const float* in, float* out, const float* W,
+                          const float* B, int k, int n, int f, bool relu, int in_w, int in_h,
+                          int S) {
+  return train::n1_forward(ctx, in, out, W, B, k, n, f, relu, in_w, in_h, S);
 }
 
-inline bool deltas(srcnn_ctx*, const float*, const float*, float*, const float*, int, int, int,
-                   int, int, int) {
-  return false;
+inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
+                   const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
+  return train::n1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S);
 }
 
 // returns 1 when it launched, 0 when not handled, <0 on error
-inline int backpropagate(srcnn_ctx*, const float*, const float*, float*, float*, int, int, int,
-                         int, int, int) {
-  return 0;
+inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float* gw, float* gb,
+                         int n, int k, int f, int ow, int oh, int S) {
+  if (!aligned16(d) || !aligned16(in)) return 0;   // the register-tiled kernels use LDG.128
+  return train::gradw(ctx, d, in, gw, gb, n, k, f, ow, oh, S);
 }
 
 inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {

@@ -35,6 +35,8 @@ inline Dims net_dims(const srcnn_net* net, int w, int h) {
   return d;
 }
 
+inline size_t align256(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
 inline int check_net(const srcnn_net* net) {
   SRCNN_REQUIRE(net != nullptr, "net is null");
   SRCNN_REQUIRE(net->n1 > 0 && net->n2 > 0, "n1/n2 must be > 0");
@@ -591,9 +593,10 @@ size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S) {
   if (!net || S <= 0) return 0;
   const Dims d = net_dims(net, w, h);
   if (d.w3 <= 0 || d.h3 <= 0) return 0;
-  const size_t e1 = (size_t)d.w1 * d.h1 * net->n1, e2 = (size_t)d.w2 * d.h2 * net->n2,
-               e3 = (size_t)d.w3 * d.h3;
-  return sizeof(float) * 2 * (e1 + e2 + e3) * (size_t)S;
+  const size_t e1 = align256(sizeof(float) * (size_t)d.w1 * d.h1 * net->n1 * S),
+               e2 = align256(sizeof(float) * (size_t)d.w2 * d.h2 * net->n2 * S),
+               e3 = align256(sizeof(float) * (size_t)d.w3 * d.h3 * S);
+  return 2 * (e1 + e2 + e3);
 }
 
 namespace {
@@ -603,9 +606,10 @@ struct Work {
 // carve the chunk workspace into six wrapped sub-buffers (handles are cheap table entries)
 int carve(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem work, int w, int h, int S, Work* wk) {
   const Dims d = net_dims(net, w, h);
-  const size_t e1 = sizeof(float) * (size_t)d.w1 * d.h1 * net->n1 * S,
-               e2 = sizeof(float) * (size_t)d.w2 * d.h2 * net->n2 * S,
-               e3 = sizeof(float) * (size_t)d.w3 * d.h3 * S;
+  // every sub-buffer starts 256-byte aligned (vectorised loads in the training kernels)
+  const size_t e1 = align256(sizeof(float) * (size_t)d.w1 * d.h1 * net->n1 * S),
+               e2 = align256(sizeof(float) * (size_t)d.w2 * d.h2 * net->n2 * S),
+               e3 = align256(sizeof(float) * (size_t)d.w3 * d.h3 * S);
   char* base;
   SRCNN_TRY(resolve(ctx, work, 2 * (e1 + e2 + e3), &base, "training workspace"));
   SRCNN_TRY(srcnn_wrap(ctx, base, e1, &wk->out1));

@@ -346,10 +346,10 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
     work = ctx.alloc(net.train_workspace_bytes(w, h, S))
     net.train_chunk(mi, mg, w, h, S, work)
     flat = ctx.read(work, (net.train_workspace_bytes(w, h, S) // 4,))
-    off = 0
+    off = 0   # sub-buffers are 256-byte aligned inside the workspace (srcnn_train_chunk)
     for name, exp in (("out1", o1), ("out2", o2), ("out3", o3), ("d1", d1), ("d2", d2), ("d3", d3)):
         got = flat[off:off + exp.size].reshape(exp.shape)
-        off += exp.size
+        off += ((exp.size * 4 + 255) // 256 * 256) // 4
         np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL, err_msg=name)
     g = net.grads()
     for l in range(3):

@@ -144,6 +144,62 @@ __global__ void __launch_bounds__(NT) n1_deltas_kernel(const float* __restrict__
   }
 }
 
+// Same, for samples whose zero-padded next-layer delta map fits in shared memory (training
+// patches): one CTA per sample stages the padded map once, so the inner loop has no bounds
+// tests and no global-memory latency.
+template <int F, int CPL>
+__global__ void __launch_bounds__(NT) n1_deltas_smem_kernel(const float* __restrict__ dn,
+                                                            const float* __restrict__ lo,
+                                                            float* __restrict__ target,
+                                                            const float* __restrict__ W, int k,
+                                                            int ow, int oh, int S) {
+  extern __shared__ float dpad[];   // [(oh + F - 1)][(ow + F - 1)], zero border of F-1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = ow - F + 1, nh = oh - F + 1;
+  const int pw = ow + F - 1, ph = oh + F - 1;
+  float w[CPL][F][F];
+#pragma unroll
+  for (int j = 0; j < CPL; j++) {
+    const int c = lane + 32 * j;
+#pragma unroll
+    for (int dy = 0; dy < F; dy++)
+#pragma unroll
+      for (int dx = 0; dx < F; dx++) w[j][dy][dx] = c < k ? __ldg(W + (dy * F + dx) * k + c) : 0.f;
+  }
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < pw * ph; i += NT) {
+      const int y = i / pw - (F - 1), x = i % pw - (F - 1);
+      dpad[i] = (y >= 0 && y < nh && x >= 0 && x < nw)
+                    ? __ldg(dn + ((long long)s * nh + y) * nw + x)
+                    : 0.f;
+    }
+    __syncthreads();
+    for (int p = warp; p < ow * oh; p += NT / 32) {
+      const int j = p / ow, i = p - j * ow;
+      // target pixel (j,i) sees dn[j-dy][i-dx] = dpad[j-dy+F-1][i-dx+F-1]
+      const float* base = dpad + (j + F - 1) * pw + i + F - 1;
+      float d[F][F];
+#pragma unroll
+      for (int dy = 0; dy < F; dy++)
+#pragma unroll
+        for (int dx = 0; dx < F; dx++) d[dy][dx] = base[-dy * pw - dx];
+#pragma unroll
+      for (int jc = 0; jc < CPL; jc++) {
+        const int c = lane + 32 * jc;
+        if (c >= k) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < F; dy++)
+#pragma unroll
+          for (int dx = 0; dx < F; dx++) acc = fmaf(d[dy][dx], w[jc][dy][dx], acc);
+        const long long idx = ((long long)s * oh * ow + p) * k + c;
+        target[idx] = __ldg(lo + idx) > 0.f ? acc : 0.f;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ gW of an n=1 layer --------
 // gW[dy][dx][c] += sum_{s,row,col} d[s][row][col] * in[s][row+dy][col+dx][c];  gB += sum d
 // reference: src/kernel/backpropagate.cl:56-114 with n_current_filter_cnt = 1.
@@ -172,6 +228,7 @@ __global__ void __launch_bounds__(NT) n1_gradw_kernel(const float* __restrict__ 
     const float* ds = d + (long long)s * ow * oh;
     const float* ins = in + (long long)s * iw * ih * k;
     for (int row = 0; row < oh; row++)
+#pragma unroll 4
       for (int col = 0; col < ow; col++) {
         const float dv = __ldg(ds + row * ow + col);
         gb += dv;
@@ -200,95 +257,109 @@ __global__ void __launch_bounds__(NT) n1_gradw_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) dst[F * F * k] = gb;
 }
 
-// ------------------------------------------------------------------ gW of an f=1 layer --------
-// gW[c][n] += sum_p in[p][c] * d[p][n];  gB[n] += sum_p d[p][n]     (p over all pixels)
-// reference: src/kernel/backpropagate.cl:56-114 with f_spatial_size = 1.
-// A "slice" is WPS warps covering the (K/8) x (N/8) grid of 8x8 register tiles; slices own
-// disjoint, contiguous pixel ranges.  partial[slice][K+1][N].
-template <int K, int N>
-__global__ void __launch_bounds__(NT) dense_gradw_kernel(const float* __restrict__ d,
-                                                         const float* __restrict__ in,
-                                                         float* __restrict__ partial,
-                                                         long long P, long long pix_per_slice) {
-  constexpr int NG = N / 8, TILES = (K / 8) * NG, WPS = TILES / 32;
-  static_assert(TILES % 32 == 0 && (NT / 32) % WPS == 0, "tile grid must fill whole warps");
-  constexpr int SLICES_PER_CTA = (NT / 32) / WPS;
-  const int slice_in_cta = (threadIdx.x >> 5) / WPS;
-  const int t = threadIdx.x - slice_in_cta * WPS * 32;   // tile index inside the slice
-  const int mi = t / NG, ni = t % NG;
-  const long long slice = (long long)blockIdx.x * SLICES_PER_CTA + slice_in_cta;
-  const long long p0 = slice * pix_per_slice;
-  const long long p1 = min(P, p0 + pix_per_slice);
-  float acc[8][8];
-  float gb[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    gb[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
-  }
-  for (long long p = p0; p < p1; p++) {
-    const float4* ap = reinterpret_cast<const float4*>(in + p * K + mi * 8);
-    const float4* bp = reinterpret_cast<const float4*>(d + p * N + ni * 8);
-    const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    if (mi == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) gb[j] += bv[j];
-    }
-  }
-  float* dst = partial + slice * (long long)((K + 1) * N);
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    float4* o = reinterpret_cast<float4*>(dst + (mi * 8 + i) * N + ni * 8);
-    o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-  }
-  if (mi == 0) {
-    float4* o = reinterpret_cast<float4*>(dst + K * N + ni * 8);
-    o[0] = make_float4(gb[0], gb[1], gb[2], gb[3]);
-    o[1] = make_float4(gb[4], gb[5], gb[6], gb[7]);
-  }
+// ------------------------------------------------------------------ gW of f=1 / k=1 layers ---
+// gW[m][n] += sum_p A[p][m] * d[p][n];  gB[n] += sum_p d[p][n]       (p over all pixels)
+//   MODE 0 (f = 1, layer 2): A[p][m] = in[p][m]                       m < K
+//   MODE 1 (k = 1, layer 1): A[p][m] = in[s][row+dy][col+dx], m = dy*F+dx   (gathered)
+// reference: src/kernel/backpropagate.cl:56-114.
+// A CTA streams blocks of PB pixels through a 2-stage cp.async pipeline (all threads copy,
+// coalesced 16-byte requests; the k=1 gather uses 4-byte requests), so the memory-level
+// parallelism does not depend on occupancy.  Each lane owns an 8x8 register tile of the
+// gradient; WPS warps cover the whole (M/8) x (N/8) tile grid and the CTA's SPLITS warp groups
+// take disjoint pixels of every block.  One partial [M+1][N] per (CTA, split); the fixed-order
+// second stage makes the result deterministic.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N_));
 }
 
-// ------------------------------------------------------------------ gW of a k=1 layer ---------
-// gW[dy][dx][n] += sum_{s,row,col} in[s][row+dy][col+dx] * d[s][row][col][n];  gB[n] += sum d
-// reference: src/kernel/backpropagate.cl:56-114 with n_prev_filter_cnt = 1.
-// Register tiles: 8 taps x 8 channels; MG = ceil(f*f/8) tap groups (taps >= f*f read as 0).
-template <int F, int N>
-__global__ void __launch_bounds__(NT) k1_gradw_kernel(const float* __restrict__ d,
-                                                      const float* __restrict__ in,
-                                                      float* __restrict__ partial, int ow, int oh,
-                                                      int S, long long pix_per_slice) {
-  constexpr int FF = F * F, MG = (FF + 7) / 8, NG = N / 8, TILES = MG * NG;
-  constexpr int WPS = (TILES + 31) / 32;
-  constexpr int SLICES_PER_CTA = (NT / 32) / WPS;
-  static_assert(SLICES_PER_CTA >= 1, "tile grid larger than a CTA");
-  const int iw = ow + F - 1, ih = oh + F - 1;
-  const int slice_in_cta = (threadIdx.x >> 5) / WPS;
-  if (slice_in_cta >= SLICES_PER_CTA) return;
-  const int t = threadIdx.x - slice_in_cta * WPS * 32;
-  const bool live = t < TILES;
+template <int MODE, int F, int K, int N>
+struct GradCfg {
+  static constexpr int M = MODE == 0 ? K : F * F;       // gradient rows
+  static constexpr int MP = (M + 7) / 8 * 8;            // padded to whole 8-row tiles
+  static constexpr int MG = MP / 8, NG = N / 8, TILES = MG * NG;
+  static constexpr int WPS = (TILES + 31) / 32;          // warps per split
+  static constexpr int SPLITS = (NT / 32) / WPS;         // pixel splits per CTA
+  static constexpr int PB = 64;                          // pixels per pipeline stage
+  static constexpr int AP = MP + 4;                      // smem pitch of an A row (bank spread)
+  static constexpr int STAGE_FLOATS = PB * AP + PB * N;
+  static constexpr size_t SMEM_BYTES = sizeof(float) * 2 * (size_t)STAGE_FLOATS;
+  static_assert(SPLITS >= 1 && PB % SPLITS == 0, "tile grid / split shape");
+};
+
+template <int MODE, int F, int K, int N>
+__global__ void __launch_bounds__(NT) grad_stream_kernel(const float* __restrict__ d,
+                                                         const float* __restrict__ in,
+                                                         float* __restrict__ partial, int ow,
+                                                         int oh, long long P,
+                                                         long long blocks_per_cta) {
+  using G = GradCfg<MODE, F, K, N>;
+  extern __shared__ __align__(16) float gsm[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int split = warp / G::WPS;
+  const int t = tid - split * G::WPS * 32;               // tile index inside the split
+  const bool live = split < G::SPLITS && t < G::TILES;
   const int tt = live ? t : 0;
-  const int mi = tt / NG, ni = tt % NG;
-  int toff[8];
-  float tmask[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int tap = mi * 8 + i;
-    const int tc = tap < FF ? tap : 0;
-    toff[i] = (tc / F) * iw + (tc % F);
-    tmask[i] = tap < FF ? 1.f : 0.f;
+  const int mi = tt / G::NG, ni = tt % G::NG;
+  const int iw = ow + F - 1, ih = oh + F - 1;
+
+  const long long nblocks = (P + G::PB - 1) / G::PB;
+  const long long b0 = (long long)blockIdx.x * blocks_per_cta;
+  const long long b1 = min(nblocks, b0 + blocks_per_cta);
+
+  auto stage_A = [&](int st) { return gsm + st * G::STAGE_FLOATS; };
+  auto stage_B = [&](int st) { return gsm + st * G::STAGE_FLOATS + G::PB * G::AP; };
+
+  // zero the A padding columns once (taps >= F*F); cp.async never touches them
+  if (G::MP > G::M) {
+    for (int i = tid; i < 2 * G::PB * (G::AP - G::M); i += NT) {
+      const int st = i / (G::PB * (G::AP - G::M)), r = i % (G::PB * (G::AP - G::M));
+      stage_A(st)[(r / (G::AP - G::M)) * G::AP + G::M + r % (G::AP - G::M)] = 0.f;
+    }
   }
-  const long long P = (long long)S * ow * oh;
-  const long long slice = (long long)blockIdx.x * SLICES_PER_CTA + slice_in_cta;
-  const long long p0 = slice * pix_per_slice;
-  const long long p1 = min(P, p0 + pix_per_slice);
+
+  auto load_block = [&](long long blk, int st) {
+    const long long p0 = blk * G::PB;
+    const int npx = (int)min((long long)G::PB, P - p0);
+    float* sA = stage_A(st);
+    float* sB = stage_B(st);
+    // B: npx * N contiguous floats
+    for (int i = tid; i < npx * (N / 4); i += NT)
+      cp_async16(sB + i * 4, d + p0 * N + (long long)i * 4);
+    if (MODE == 0) {
+      for (int i = tid; i < npx * (K / 4); i += NT) {
+        const int px = i / (K / 4), c4 = i % (K / 4);
+        cp_async16(sA + px * G::AP + c4 * 4, in + (p0 + px) * K + c4 * 4);
+      }
+    } else {
+      for (int i = tid; i < npx * F; i += NT) {
+        const int px = i / F, dy = i % F;
+        const long long p = p0 + px;
+        const long long s = p / ((long long)ow * oh);
+        const int rem = (int)(p - s * ow * oh);
+        const int row = rem / ow, col = rem - row * ow;
+        const float* src = in + (s * ih + row + dy) * (long long)iw + col;
+        float* dst = sA + px * G::AP + dy * F;
+#pragma unroll
+        for (int dx = 0; dx < F; dx++) cp_async4(dst + dx, src + dx);
+      }
+    }
+    // pixels past the end of the data (last block only): zero both operands so they add nothing
+    for (int i = tid; i < (G::PB - npx) * N; i += NT) sB[npx * N + i] = 0.f;
+    for (int i = tid; i < (G::PB - npx) * G::AP; i += NT) sA[npx * G::AP + i] = 0.f;
+  };
+
   float acc[8][8];
   float gb[8];
 #pragma unroll
@@ -297,73 +368,117 @@ __global__ void __launch_bounds__(NT) k1_gradw_kernel(const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
   }
-  // walk (s,row,col) incrementally instead of dividing per pixel
-  long long s = p0 / ((long long)ow * oh);
-  int rem = (int)(p0 - s * ow * oh);
-  int row = rem / ow, col = rem - row * ow;
-  for (long long p = p0; p < p1; p++) {
-    const float* px = in + (s * ih + row) * (long long)iw + col;
-    const float4* bp = reinterpret_cast<const float4*>(d + p * N + ni * 8);
-    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float av[8];
+
+  if (b0 < b1) load_block(b0, 0);
+  cp_async_commit();
+  for (long long blk = b0; blk < b1; blk++) {
+    const int st = (int)((blk - b0) & 1);
+    if (blk + 1 < b1) load_block(blk + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();          // this block's copies have landed (the next may be in flight)
+    __syncthreads();
+    if (live) {
+      const float* sA = stage_A(st) + mi * 8;
+      const float* sB = stage_B(st) + ni * 8;
+      constexpr int PPS = G::PB / G::SPLITS;             // pixels of the block per split
+#pragma unroll 4
+      for (int q = 0; q < PPS; q++) {
+        const int px = split * PPS + q;
+        const float4 a0 = *reinterpret_cast<const float4*>(sA + px * G::AP);
+        const float4 a1 = *reinterpret_cast<const float4*>(sA + px * G::AP + 4);
+        const float4 c0 = *reinterpret_cast<const float4*>(sB + px * N);
+        const float4 c1 = *reinterpret_cast<const float4*>(sB + px * N + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-    for (int i = 0; i < 8; i++) av[i] = __ldg(px + toff[i]) * tmask[i];
+        for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+          for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        if (mi == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    if (mi == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) gb[j] += bv[j];
-    }
-    if (++col == ow) {
-      col = 0;
-      if (++row == oh) {
-        row = 0;
-        ++s;
+          for (int j = 0; j < 8; j++) gb[j] += bv[j];
+        }
       }
     }
+    __syncthreads();             // everyone is done with stage st before it is refilled
   }
+  cp_async_wait<0>();
   if (!live) return;
-  float* dst = partial + slice * (long long)((FF + 1) * N);
+  float* dst = partial + ((long long)blockIdx.x * G::SPLITS + split) * (long long)((G::M + 1) * N);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const int tap = mi * 8 + i;
-    if (tap < FF) {
-      float4* o = reinterpret_cast<float4*>(dst + tap * N + ni * 8);
+    const int m = mi * 8 + i;
+    if (m < G::M) {
+      float4* o = reinterpret_cast<float4*>(dst + m * N + ni * 8);
       o[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       o[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
   }
   if (mi == 0) {
-    float4* o = reinterpret_cast<float4*>(dst + FF * N + ni * 8);
+    float4* o = reinterpret_cast<float4*>(dst + G::M * N + ni * 8);
     o[0] = make_float4(gb[0], gb[1], gb[2], gb[3]);
     o[1] = make_float4(gb[4], gb[5], gb[6], gb[7]);
   }
 }
 
+template <int MODE, int F, int K, int N>
+inline int launch_grad_stream(srcnn_ctx* ctx, const float* d, const float* in, int ow, int oh,
+                              long long P, int* count) {
+  using G = GradCfg<MODE, F, K, N>;
+  static bool configured = false;
+  if (!configured) {
+    SRCNN_CUDA(cudaFuncSetAttribute(grad_stream_kernel<MODE, F, K, N>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)G::SMEM_BYTES));
+    configured = true;
+  }
+  const long long nblocks = (P + G::PB - 1) / G::PB;
+  long long ctas = std::min<long long>(2LL * ctx->sm_count, nblocks);
+  const long long bpc = (nblocks + ctas - 1) / ctas;
+  ctas = (nblocks + bpc - 1) / bpc;
+  *count = (int)(ctas * G::SPLITS);
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
+                           sizeof(float) * (size_t)(*count) * (G::M + 1) * N));
+  grad_stream_kernel<MODE, F, K, N><<<(int)ctas, NT, G::SMEM_BYTES, ctx->stream>>>(
+      d, in, (float*)ctx->splitk_scratch, ow, oh, P, bpc);
+  return SRCNN_OK;
+}
+
 // fixed-order sum of the partial vectors, then `+=` into the accumulators
 // (layout of one partial: [Mw rows][n] weights followed by [n] bias sums)
-__global__ void partial_reduce_kernel(const float* __restrict__ partial, float* grad_w,
-                                      float* grad_b, int Mw, int n, int count) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+// A block owns 32 consecutive outputs; its 8 warps take the partial vectors z = w, w+8, ... (each
+// with 4 independent chains), then the 8 per-warp sums are folded in warp order -- the
+// association is fixed, so the result does not depend on scheduling.
+constexpr int RED_OUT = 32, RED_WARPS = 8;
+__global__ void __launch_bounds__(RED_OUT * RED_WARPS)
+partial_reduce_kernel(const float* __restrict__ partial, float* grad_w, float* grad_b, int Mw,
+                      int n, int count) {
+  __shared__ float sh[RED_WARPS][RED_OUT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int id = blockIdx.x * RED_OUT + lane;
   const int total = (Mw + 1) * n;
-  if (id >= total) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // 4 independent chains, fixed association
-  int z = 0;
-  for (; z + 3 < count; z += 4) {
-    s0 += partial[(long long)z * total + id];
-    s1 += partial[(long long)(z + 1) * total + id];
-    s2 += partial[(long long)(z + 2) * total + id];
-    s3 += partial[(long long)(z + 3) * total + id];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (id < total) {
+    int z = warp;
+    for (; z + 3 * RED_WARPS < count; z += 4 * RED_WARPS) {
+      s0 += __ldg(partial + (long long)z * total + id);
+      s1 += __ldg(partial + (long long)(z + RED_WARPS) * total + id);
+      s2 += __ldg(partial + (long long)(z + 2 * RED_WARPS) * total + id);
+      s3 += __ldg(partial + (long long)(z + 3 * RED_WARPS) * total + id);
+    }
+    for (; z < count; z += RED_WARPS) s0 += __ldg(partial + (long long)z * total + id);
   }
-  for (; z < count; z++) s0 += partial[(long long)z * total + id];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (id < Mw * n)
-    grad_w[id] += s;
-  else
-    grad_b[id - Mw * n] += s;
+  sh[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (warp == 0 && id < total) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < RED_WARPS; w++) s += sh[w][lane];
+    if (id < Mw * n)
+      grad_w[id] += s;
+    else
+      grad_b[id - Mw * n] += s;
+  }
 }
 
 // ================================================================== dispatch ================
@@ -394,6 +509,15 @@ inline bool n1_forward(srcnn_ctx* ctx, const float* in, float* out, const float*
 inline bool n1_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
                       const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
   if (n_next != 1 || f_next != 5 || (n_curr != 16 && n_curr != 32 && n_curr != 64)) return false;
+  const size_t pad_bytes = sizeof(float) * (size_t)(ow + f_next - 1) * (oh + f_next - 1);
+  if (pad_bytes <= 40 * 1024) {   // patch-sized samples: padded delta map staged in smem
+    const int g = (int)std::min<long long>(S, 4LL * ctx->sm_count);
+    if (n_curr <= 32)
+      n1_deltas_smem_kernel<5, 1><<<g, NT, pad_bytes, ctx->stream>>>(dn, lo, target, W, n_curr, ow, oh, S);
+    else
+      n1_deltas_smem_kernel<5, 2><<<g, NT, pad_bytes, ctx->stream>>>(dn, lo, target, W, n_curr, ow, oh, S);
+    return true;
+  }
   const int grid = grid_for(ctx, (long long)S * ow * oh);
   if (n_curr <= 32)
     n1_deltas_kernel<5, 1><<<grid, NT, 0, ctx->stream>>>(dn, lo, target, W, n_curr, ow, oh, S);
@@ -416,40 +540,23 @@ inline int gradw(srcnn_ctx* ctx, const float* d, const float* in, float* grad_w,
       n1_gradw_kernel<5, 1><<<count, NT, 0, ctx->stream>>>(d, in, part, k, ow, oh, S);
     else
       n1_gradw_kernel<5, 2><<<count, NT, 0, ctx->stream>>>(d, in, part, k, ow, oh, S);
-  } else if (f == 1 && ((k == 64 && n == 32) || (k == 128 && n == 64))) {
-    const int wps = (k / 8) * (n / 8) / 32, spc = (NT / 32) / wps;
-    long long slices = std::min<long long>((long long)2 * ctx->sm_count * spc, (P + 63) / 64);
-    slices = (slices + spc - 1) / spc * spc;
-    const long long pps = (P + slices - 1) / slices;
-    count = (int)slices;
-    SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
-                             sizeof(float) * (size_t)count * (Mw + 1) * n));
-    float* part = (float*)ctx->splitk_scratch;
-    if (k == 64)
-      dense_gradw_kernel<64, 32><<<(int)(slices / spc), NT, 0, ctx->stream>>>(d, in, part, P, pps);
-    else
-      dense_gradw_kernel<128, 64><<<(int)(slices / spc), NT, 0, ctx->stream>>>(d, in, part, P, pps);
-  } else if (k == 1 && f == 9 && (n == 64 || n == 128 || n == 32)) {
-    const int tiles = 11 * (n / 8), wps = (tiles + 31) / 32, spc = (NT / 32) / wps;
-    long long slices = std::min<long long>((long long)2 * ctx->sm_count * spc, (P + 63) / 64);
-    slices = (slices + spc - 1) / spc * spc;
-    const long long pps = (P + slices - 1) / slices;
-    count = (int)slices;
-    SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
-                             sizeof(float) * (size_t)count * (Mw + 1) * n));
-    float* part = (float*)ctx->splitk_scratch;
-    const int grid = (int)(slices / spc);
-    if (n == 64)
-      k1_gradw_kernel<9, 64><<<grid, NT, 0, ctx->stream>>>(d, in, part, ow, oh, S, pps);
-    else if (n == 128)
-      k1_gradw_kernel<9, 128><<<grid, NT, 0, ctx->stream>>>(d, in, part, ow, oh, S, pps);
-    else
-      k1_gradw_kernel<9, 32><<<grid, NT, 0, ctx->stream>>>(d, in, part, ow, oh, S, pps);
+  } else if (f == 1 && k == 64 && n == 32) {
+    SRCNN_TRY((launch_grad_stream<0, 1, 64, 32>(ctx, d, in, ow, oh, P, &count)));
+  } else if (f == 1 && k == 128 && n == 64) {
+    SRCNN_TRY((launch_grad_stream<0, 1, 128, 64>(ctx, d, in, ow, oh, P, &count)));
+  } else if (f == 1 && k == 32 && n == 16) {
+    SRCNN_TRY((launch_grad_stream<0, 1, 32, 16>(ctx, d, in, ow, oh, P, &count)));
+  } else if (k == 1 && f == 9 && n == 64) {
+    SRCNN_TRY((launch_grad_stream<1, 9, 1, 64>(ctx, d, in, ow, oh, P, &count)));
+  } else if (k == 1 && f == 9 && n == 128) {
+    SRCNN_TRY((launch_grad_stream<1, 9, 1, 128>(ctx, d, in, ow, oh, P, &count)));
+  } else if (k == 1 && f == 9 && n == 32) {
+    SRCNN_TRY((launch_grad_stream<1, 9, 1, 32>(ctx, d, in, ow, oh, P, &count)));
   } else {
     return 0;
   }
   const int total = (Mw + 1) * n;
-  partial_reduce_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
+  partial_reduce_kernel<<<(total + RED_OUT - 1) / RED_OUT, RED_OUT * RED_WARPS, 0, ctx->stream>>>(
       (const float*)ctx->splitk_scratch, grad_w, grad_b, Mw, n, count);
   return 1;
 }

@@ -117,6 +117,14 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->band_in) cudaFree(ctx->band_in);
   if (ctx->band_out) cudaFree(ctx->band_out);
   if (ctx->packed_params) cudaFree(ctx->packed_params);
+  if (ctx->copy_in) {
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < 8; i++) {
+      cudaEventDestroy(ctx->ev_in[i]);
+      cudaEventDestroy(ctx->ev_k[i]);
+    }
+  }
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -564,8 +572,6 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   const size_t out_bytes = sizeof(float) * (size_t)band_out_h * d.w3;
   SRCNN_TRY(ensure_scratch(ctx, &ctx->band_in, &ctx->band_in_bytes, in_bytes));
   SRCNN_TRY(ensure_scratch(ctx, &ctx->band_out, &ctx->band_out_bytes, out_bytes));
-  SRCNN_CUDA(cudaMemcpyAsync(ctx->band_in, host_in + (size_t)out_row0 * in_w, in_bytes,
-                             cudaMemcpyHostToDevice, ctx->stream));
   const float *w1, *b1, *w2, *b2, *w3, *b3;
   SRCNN_TRY(resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1"));
   SRCNN_TRY(resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1"));
@@ -576,15 +582,67 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   SRCNN_REQUIRE(fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3),
                 "srcnn_infer_rows_host needs a fused instantiation for %d-%d-%d n1=%d n2=%d",
                 net->f1, net->f2, net->f3, net->n1, net->n2);
-  {
-    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
-    SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
-                                  (const float*)ctx->band_in, (float*)ctx->band_out, w1, b1, w2,
-                                  b2, w3, b3, in_w, band_in_h, 1));
-    SRCNN_TRY(check_launch("forward_fused"));
+  // The band is cut into sub-bands of whole 128-row CTA strips; upload (copy-in stream),
+  // fused forward (context stream) and download (copy-out stream) of consecutive sub-bands
+  // overlap, so a large image costs ~max(H2D, compute, D2H) instead of their sum.  Every
+  // sub-band is the same valid-convolution problem with a halo, so the result is bit-identical
+  // to a single launch.
+  constexpr int kMaxSub = 8;
+  int n_sub = band_out_h >= 1024 ? 6 : 1;
+  int rows_per = ((band_out_h + n_sub - 1) / n_sub + 127) / 128 * 128;
+  n_sub = (band_out_h + rows_per - 1) / rows_per;
+  if (n_sub > kMaxSub) n_sub = kMaxSub;
+  if (n_sub > 1 && !ctx->copy_in) {
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxSub; i++) {
+      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
   }
-  SRCNN_CUDA(cudaMemcpyAsync(host_out, ctx->band_out, out_bytes, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+  float* din = (float*)ctx->band_in;
+  float* dout = (float*)ctx->band_out;
+  if (n_sub == 1) {
+    SRCNN_CUDA(cudaMemcpyAsync(din, host_in + (size_t)out_row0 * in_w, in_bytes,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    {
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+      SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, din, dout,
+                                    w1, b1, w2, b2, w3, b3, in_w, band_in_h, 1));
+      SRCNN_TRY(check_launch("forward_fused"));
+    }
+    SRCNN_CUDA(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SRCNN_OK;
+  }
+  // order the side streams after whatever the context stream was doing with the buffers
+  SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[0], 0));
+  for (int i = 0; i < n_sub; i++) {
+    const int r0 = i * rows_per, r1 = std::min(band_out_h, r0 + rows_per);   // band-relative
+    // input rows [r0 + (i ? halo : 0), r1 + halo): disjoint pieces that tile the band
+    const int in0 = r0 + (i ? halo : 0), in1 = r1 + halo;
+    SRCNN_CUDA(cudaMemcpyAsync(din + (size_t)in0 * in_w,
+                               host_in + ((size_t)out_row0 + in0) * in_w,
+                               sizeof(float) * (size_t)(in1 - in0) * in_w, cudaMemcpyHostToDevice,
+                               ctx->copy_in));
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+    SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+    {
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+      SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
+                                    din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2,
+                                    b2, w3, b3, in_w, r1 - r0 + halo, 1));
+      SRCNN_TRY(check_launch("forward_fused"));
+    }
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_k[i], ctx->stream));
+    SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
+    SRCNN_CUDA(cudaMemcpyAsync(host_out + (size_t)r0 * d.w3, dout + (size_t)r0 * d.w3,
+                               sizeof(float) * (size_t)(r1 - r0) * d.w3, cudaMemcpyDeviceToHost,
+                               ctx->copy_out));
+  }
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_out));
   SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
   return SRCNN_OK;
 }

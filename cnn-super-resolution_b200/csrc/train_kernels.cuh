@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(NT) grad_stream_kernel(const float* __restrict
     // B: npx * N contiguous floats
     for (int i = tid; i < npx * (N / 4); i += NT)
       cp_async16(sB + i * 4, d + p0 * N + (long long)i * 4);
-    if (MODE == 0) {
+    if constexpr (MODE == 0) {
       for (int i = tid; i < npx * (K / 4); i += NT) {
         const int px = i / (K / 4), c4 = i % (K / 4);
         cp_async16(sA + px * G::AP + c4 * 4, in + (p0 + px) * K + c4 * 4);

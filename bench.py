@@ -121,6 +121,8 @@ def run_reference(args, rank, world):
     from oracle.loader import NetState, Oracle, have
     kind = "reference" if have("reference") else "port"
     orc = Oracle(kind)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    orc.set_num_threads(len(os.sched_getaffinity(0)))
     cores = orc.num_threads()
     rng, params, luma_image, patches = synthetic_inputs()
     net = NetState(N1, N2, F1, F2, F3, params)
@@ -391,6 +393,7 @@ def cpu_baseline(args):
     from oracle.loader import NetState, Oracle, have
     kind = "reference" if have("reference") else "port"
     orc = Oracle(kind)
+    orc.set_num_threads(len(os.sched_getaffinity(0)))
     rng, params, luma_image, patches = synthetic_inputs()
     net = NetState(N1, N2, F1, F2, F3, params)
     rows = args.ref_rows

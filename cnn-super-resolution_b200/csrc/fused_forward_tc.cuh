@@ -1,11 +1,14 @@
-// Fused SRCNN inference, tensor-core version (9-1-5, n1=64, n2=32): layers 1 and 2 -- the two
-// dense contractions, 90 % of the FLOPs -- run on the 5th-generation tensor cores (tcgen05,
-// accumulators in TMEM); layer 3 (N = 1) stays FP32 SIMT with a warp-shuffle fold.
+// Fused SRCNN inference, tensor-core version (9-1-5, n1=64, n2=32): all three layers run on
+// the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
 //
 //   L1  D1[128 px][64] = A1[128 px][88] * W1[64][88]^T      A1 = im2col of the 9x9 window (81 taps
 //                                                            + 7 zero columns), built in smem
 //   L2  D2[128 px][32] = A2[128 px][64] * W2[32][64]^T      A2 = relu(D1 + b1), TMEM -> regs -> TMEM
-//   L3  out3 = b3 + W3 * relu(D2 + b2)-window               as in fused_forward.cuh
+//   L3  Q [128 px][32] = A3[128 px][32] * W3[32 taps][32]^T A3 = relu(D2 + b2), TMEM -> regs -> TMEM
+//       out3[y][x] = b3 + sum_{dy,dx} Q[(y+dy, x+dx)][dy*5+dx]   (25-term FP32 gather from a ring
+//       of Q rows in shared memory).  Layer 3 has one output channel, so instead of an N = 1
+//       contraction the 25 taps become the N dimension of a shift-free GEMM: every out2 pixel is
+//       multiplied with all 25 tap vectors once, and the spatial shifts move to the gather.
 //
 // Precision: operands are FP32 values split into TF32 hi + lo; every product is evaluated as
 // hi*hi + hi*lo + lo*hi with FP32 accumulation ("3xTF32"), measured at 8e-7 max error against
@@ -35,8 +38,9 @@ struct Cfg {
   static constexpr int OW3 = OW2 - (F3 - 1);
   static constexpr int IW = OW2 + F1 - 1, IWP = IW + 4;
   static constexpr int IR = RB + F1 - 1 + RB;  // one block of slack: rows of tile b+2 land while tile b+1 is read
-  static constexpr int RING = RB + F3 - 1;
-  static constexpr int OW2P = OW2 + 4;
+  static constexpr int RING = RB + F3 - 1;      // ring of Q rows
+  static constexpr int NT3 = 32;                // 25 taps padded to an MMA N of 32
+  static constexpr int QP = F3 * F3;            // floats per pixel in the Q ring (odd: no conflicts)
   static constexpr int RPC = 128;
   static constexpr int M = OW2 * RB;           // 128 pixels per MMA tile
   static constexpr int K1 = 88;                // 81 taps padded to a multiple of 8
@@ -49,16 +53,19 @@ struct Cfg {
   static constexpr int oW1l = oW1h + N1 * K1;
   static constexpr int oW2h = oW1l + N1 * K1;
   static constexpr int oW2l = oW2h + N2 * K2;
-  static constexpr int oB1 = oW2l + N2 * K2;
+  static constexpr int oW3h = oW2l + N2 * K2;   // B operand of layer 3: [32 taps][32 ch]
+  static constexpr int oW3l = oW3h + NT3 * N2;
+  static constexpr int oB1 = oW3l + NT3 * N2;
   static constexpr int oB2 = oB1 + N1;
-  static constexpr int oW3 = oB2 + N2;         // [dy][c2][4] + [dy][c2]
-  static constexpr int oIn = oW3 + F3 * N2 * 5 + 4;
-  static constexpr int oO2 = oIn + IR * IWP;
-  static constexpr int TOTAL = oO2 + RING * N2 * OW2P;
+  static constexpr int oIn = oB2 + N2;
+  static constexpr int oQ = oIn + IR * IWP;
+  static constexpr int TOTAL = oQ + RING * OW2 * QP;
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)TOTAL;
-  // tensor memory columns: D1 accumulator, D2 accumulator, A2 = relu(D1+b1) split hi / lo
-  static constexpr uint32_t cD1 = 0, cD2 = 64, cA2h = 128, cA2l = 192;
-  static constexpr uint32_t TMEM_COLS = 256;
+  // tensor memory columns: the three accumulators, A2 = relu(D1+b1) and A3 = relu(D2+b2) split
+  // into TF32 hi / lo
+  static constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 96, cA2h = 128, cA2l = 192, cA3h = 256,
+                            cA3l = 288;
+  static constexpr uint32_t TMEM_COLS = 512;
 };
 
 __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Args a) {
@@ -73,12 +80,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   float* sW1l = smem + C::oW1l;
   float* sW2h = smem + C::oW2h;
   float* sW2l = smem + C::oW2l;
+  float* sW3h = smem + C::oW3h;
+  float* sW3l = smem + C::oW3l;
   float* sB1 = smem + C::oB1;
   float* sB2 = smem + C::oB2;
-  float* sW3 = smem + C::oW3;
   float* sIn = smem + C::oIn;
-  float* sO2 = smem + C::oO2;
-  __shared__ __align__(8) uint64_t bar1, bar2;
+  float* sQ = smem + C::oQ;
+  __shared__ __align__(8) uint64_t bar1, bar2, bar3;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,13 +113,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   }
   for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i);
   for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i);
-  for (int i = tid; i < C::F3 * C::N2 * 5; i += C::NT) {
-    const int dx = i % 5, c2 = (i / 5) % C::N2, dy = i / (5 * C::N2);
-    const float v = __ldg(a.pw3 + (dy * C::F3 + dx) * C::N2 + c2);
-    if (dx < 4)
-      sW3[(dy * C::N2 + c2) * 4 + dx] = v;
-    else
-      sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2] = v;
+  for (int i = tid; i < C::NT3 * C::N2; i += C::NT) {
+    const int n = i / C::N2, k = i % C::N2;   // n = tap dy*5+dx, k = channel: W3 is [tap][c2]
+    float hi, lo;
+    split_tf32(n < C::F3 * C::F3 ? __ldg(a.pw3 + n * C::N2 + k) : 0.f, hi, lo);
+    sW3h[kmajor_offset(n, k, C::N2)] = hi;
+    sW3l[kmajor_offset(n, k, C::N2)] = lo;
   }
   const float b3 = __ldg(a.pb3);
 
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
     if (smem_u32(smem) & 127u) __trap();   // operand layout needs a 128-byte aligned base
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
+    mbar_init(&bar3, 1);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -137,6 +145,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc1 = make_idesc_tf32(C::M, C::N1);
   const uint32_t idesc2 = make_idesc_tf32(C::M, C::N2);
+  const uint32_t idesc3 = make_idesc_tf32(C::M, C::NT3);
 
   const int rows_here = min(C::RPC, a.h3 - R0);
   const int n_blocks = (rows_here + (C::F3 - 1) + C::RB - 1) / C::RB;
@@ -148,23 +157,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   // epilogue role: TMEM lane quarter + column half
   const int ep_q = warp & 3, ep_h = warp >> 2;
   const int ep_m = ep_q * 32 + lane;
-  // L3 role
-  const int cgi = tid % 16, pxg = tid / 16;
-  const bool l3_live = pxg < C::NPG3;
-  const int pxa = l3_live ? pxg : 0;
-  float w3r[2][C::F3][C::F3];   // the 5x5 taps of this lane's two channels stay in registers
-#pragma unroll
-  for (int i = 0; i < 2; i++)
-#pragma unroll
-    for (int dy = 0; dy < C::F3; dy++) {
-      const int c2 = cgi + 16 * i;
-      const float4 w0 = *reinterpret_cast<const float4*>(sW3 + (dy * C::N2 + c2) * 4);
-      w3r[i][dy][0] = w0.x;
-      w3r[i][dy][1] = w0.y;
-      w3r[i][dy][2] = w0.z;
-      w3r[i][dy][3] = w0.w;
-      w3r[i][dy][4] = sW3[C::F3 * C::N2 * 4 + dy * C::N2 + c2];
-    }
+  // gather role: two threads per output pixel of the tile's RB x OW3 outputs
+  const int g_px = tid >> 1, g_half = tid & 1;
+  const bool g_live = g_px < C::RB * C::OW3;
+  const int g_r = g_live ? g_px / C::OW3 : 0, g_x = g_live ? g_px % C::OW3 : 0;
 
   // ---- pipeline stages ------------------------------------------------------------------
   // im2col of tile b: A1[m][k] = in[r+dy][x+dx], k = dy*9+dx, split hi/lo
@@ -256,76 +252,70 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
     }
     tmem_st_wait();
   };
-  // epilogue 2 of tile b: out2 = relu(D2 + b2) -> ring, channel-major
-  auto epilogue2 = [&](int b) {
-    const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + C::cD2 + ep_h * 16;
+  // MMA-3: Q = A3 * W3^T  (12 x M128 N32 K8), A3 hi/lo in tensor memory
+  auto issue_mma3 = [&]() {
+    tcgen05_fence_after();
+    const uint32_t sbo = 128 * (C::N2 / 4);
+    uint64_t bh = make_desc_kmajor(sW3h, 0, 128, sbo), bl = make_desc_kmajor(sW3l, 0, 128, sbo);
+#pragma unroll
+    for (int ks = 0; ks < C::N2 / 8; ks++) {
+      mma_tf32_ts(tmem + C::cD3, tmem + C::cA3l + ks * 8, bh, idesc3, ks > 0);
+      mma_tf32_ts(tmem + C::cD3, tmem + C::cA3h + ks * 8, bl, idesc3, 1);
+      mma_tf32_ts(tmem + C::cD3, tmem + C::cA3h + ks * 8, bh, idesc3, 1);
+      bh += 16; bl += 16;
+    }
+    mma_commit(&bar3);
+  };
+  // epilogue 2: A3 = split(relu(D2 + b2)) -> tensor memory
+  auto epilogue2 = [&]() {
+    const uint32_t lane_base = (uint32_t)(ep_q * 32) << 16;
+    const int c0 = ep_h * 16;
+    float v[16];
+    tmem_ld16(tmem + lane_base + C::cD2 + c0, v);
+#pragma unroll
+    for (int h8 = 0; h8 < 2; h8++) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        split_tf32(fmaxf(v[h8 * 8 + j] + sB2[c0 + h8 * 8 + j], 0.f), hi[j], lo[j]);
+      tmem_st8(tmem + lane_base + C::cA3h + c0 + h8 * 8, hi);
+      tmem_st8(tmem + lane_base + C::cA3l + c0 + h8 * 8, lo);
+    }
+    tmem_st_wait();
+  };
+  // epilogue 3 of tile b: Q rows (25 tap products per out2 pixel) -> ring in shared memory
+  auto epilogue3 = [&](int b) {
+    const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + C::cD3 + ep_h * 16;
     float v[16];
     tmem_ld16(taddr, v);
     const int r = ep_m / C::OW2, x = ep_m % C::OW2;
     const int slot = (b * C::RB + r) % C::RING;
+    float* q = sQ + (slot * C::OW2 + x) * C::QP + ep_h * 16;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int c2 = ep_h * 16 + j;
-      sO2[(slot * C::N2 + c2) * C::OW2P + x] = fmaxf(v[j] + sB2[c2], 0.f);
-    }
+    for (int j = 0; j < 16; j++)
+      if (ep_h * 16 + j < C::QP) q[j] = v[j];
   };
-  // L3 (FP32 SIMT) for the output rows completed by tile b: 4 px x RB rows x 2 ch per thread
-  auto layer3 = [&](int b) {
-    const int j0 = b * C::RB - (C::F3 - 1);
-    const int slot0 = ((j0 % C::RING) + C::RING) % C::RING;
-    float acc[C::RB][4];
+  // gather of the output rows completed by tile b:
+  // out3[j][x] = b3 + sum_{dy,dx} Q[j+dy][x+dx][dy*5+dx], two threads per pixel
+  auto gather = [&](int b) {
+    const int j = b * C::RB - (C::F3 - 1) + g_r;     // output row relative to R0
+    float acc = 0.f;
+    if (g_live && j >= 0) {
 #pragma unroll
-    for (int r = 0; r < C::RB; r++)
+      for (int dy = 0; dy < C::F3; dy++) {
+        const int slot = (j + dy) % C::RING;
+        const float* q = sQ + (slot * C::OW2 + g_x) * C::QP + dy * C::F3;
 #pragma unroll
-      for (int p = 0; p < 4; p++) acc[r][p] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const int c2 = cgi + 16 * i;
-      int slot = slot0;
-#pragma unroll
-      for (int jj = 0; jj < C::RB + C::F3 - 1; jj++) {
-        const float* vp = sO2 + (slot * C::N2 + c2) * C::OW2P + pxa * 4;
-        const float4 v0 = *reinterpret_cast<const float4*>(vp);
-        const float4 v1 = *reinterpret_cast<const float4*>(vp + 4);
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int r = 0; r < C::RB; r++) {
-          const int dy = jj - r;
-          if (dy >= 0 && dy < C::F3) {
-#pragma unroll
-            for (int dx = 0; dx < C::F3; dx++)
-#pragma unroll
-              for (int p = 0; p < 4; p++)
-                acc[r][p] = fmaf(vv[p + dx], w3r[i][dy][dx], acc[r][p]);
-          }
+        for (int dx = 0; dx < C::F3; dx++) {
+          const int tap = dy * C::F3 + dx;
+          if ((tap < 13) == (g_half == 0)) acc += q[dx * C::QP + dx];
         }
-        slot = slot + 1 == C::RING ? 0 : slot + 1;
       }
     }
-#pragma unroll
-    for (int r = 0; r < C::RB; r++)
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        float v = acc[r][p];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        acc[r][p] = v;
-      }
-    if (l3_live && cgi == 0) {
-#pragma unroll
-      for (int r = 0; r < C::RB; r++) {
-        const int j = j0 + r;
-        if (j >= 0 && j < rows_here) {
-          const int gy = R0 + j;
-#pragma unroll
-          for (int p = 0; p < 4; p++) {
-            const int gx = X0 + pxg * 4 + p;
-            if (gx < a.w3) dst[(size_t)gy * a.w3 + gx] = acc[r][p] + b3;
-          }
-        }
-      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (g_live && g_half == 0 && j >= 0 && j < rows_here) {
+      const int gx = X0 + g_x;
+      if (gx < a.w3) dst[(size_t)(R0 + j) * a.w3 + gx] = acc + b3;
     }
   };
 
@@ -353,22 +343,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
     fence_proxy_async();
   }
   tcgen05_fence_before();
-  __syncthreads();
+  __syncthreads();                                      // (S0) A1(0) complete
   if (is_worker) {
     for (int b = 0; b < n_blocks; b++) {
-      if (b > 0) {
-        mbar_wait(&bar2, (uint32_t)((b - 1) & 1));      // MMA-2(b-1) done
-        tcgen05_fence_after();
-        epilogue2(b - 1);
-        tcgen05_fence_before();
-        __syncthreads();                                // (B1) out2 rows of tile b-1 visible
-        layer3(b - 1);
-      }
       mbar_wait(&bar1, (uint32_t)(b & 1));              // MMA-1(b) done: D1 ready, A1 free
       tcgen05_fence_after();
       epilogue1();
       tcgen05_fence_before();
-      __syncthreads();                                  // (B2) A2 complete, D1 fully read
+      __syncthreads();                                  // (SA) A2 complete -> MMA-2(b)
       if (b + 1 < n_blocks) {
         float pre = 0.f;
         int pre_idx = -1;
@@ -378,31 +360,43 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
         fence_proxy_async();
       }
       tcgen05_fence_before();
-      __syncthreads();                                  // (B3) A1(b+1) complete
+      __syncthreads();                                  // (SB) A1(b+1) complete -> MMA-1(b+1)
+      if (b > 0) {
+        mbar_wait(&bar3, (uint32_t)((b - 1) & 1));      // MMA-3(b-1) done: Q tile ready, A3 free
+        tcgen05_fence_after();
+        epilogue3(b - 1);
+      }
+      mbar_wait(&bar2, (uint32_t)(b & 1));              // MMA-2(b) done: D2 ready
+      tcgen05_fence_after();
+      epilogue2();
+      tcgen05_fence_before();
+      __syncthreads();                                  // (SC) A3 complete, D3 read -> MMA-3(b)
+      if (b > 0) gather(b - 1);
     }
-    mbar_wait(&bar2, (uint32_t)((n_blocks - 1) & 1));
+    mbar_wait(&bar3, (uint32_t)((n_blocks - 1) & 1));
     tcgen05_fence_after();
-    epilogue2(n_blocks - 1);
-    tcgen05_fence_before();
-    __syncthreads();                                    // (B4)
-    layer3(n_blocks - 1);
+    epilogue3(n_blocks - 1);
+    __syncthreads();                                    // (SD)
+    gather(n_blocks - 1);
   } else {
     const bool issuer = lane == 0;
+    if (issuer) issue_mma1();                           // tile 0
+    __syncwarp();
     for (int b = 0; b < n_blocks; b++) {
-      if (issuer) issue_mma1();                         // A1(b) ready; D1 free since epilogue1(b-1)
-      __syncwarp();
-      if (b > 0) {
-        tcgen05_fence_before();
-        __syncthreads();                                // (B1)
-      }
       tcgen05_fence_before();
-      __syncthreads();                                  // (B2)
-      if (issuer) issue_mma2();                         // A2(b) ready; D2 free since epilogue2(b-1)
+      __syncthreads();                                  // (SA)
+      if (issuer) issue_mma2();
       __syncwarp();
       tcgen05_fence_before();
-      __syncthreads();                                  // (B3)
+      __syncthreads();                                  // (SB)
+      if (issuer && b + 1 < n_blocks) issue_mma1();
+      __syncwarp();
+      tcgen05_fence_before();
+      __syncthreads();                                  // (SC)
+      if (issuer) issue_mma3();
+      __syncwarp();
     }
-    __syncthreads();                                    // (B4)
+    __syncthreads();                                    // (SD)
   }
 
   tcgen05_fence_before();

@@ -32,7 +32,8 @@ namespace fused_tc {
 
 struct Cfg {
   static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
-  static constexpr int NW = 256;               // worker threads (im2col, epilogues, L3)
+  static constexpr int NW = 512;               // worker threads (im2col, epilogues, gather)
+  static constexpr int PARTS = NW / 128;        // workers per tile row / warps per TMEM lane quarter
   static constexpr int NT = NW + 32;           // + one warp that only issues the MMAs
   static constexpr int OW2 = 64, RB = 2;
   static constexpr int OW3 = OW2 - (F3 - 1);
@@ -152,13 +153,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
 
   // im2col role: row m of the tile and half of the K chunks
   const int im_m = tid & (C::M - 1);
-  const int im_half = tid >> 7;              // 0: chunks 0..10, 1: chunks 11..21
+  const int im_part = tid >> 7;              // which quarter of the 22 K chunks
   const int im_r = im_m / C::OW2, im_x = im_m % C::OW2;
   // epilogue role: TMEM lane quarter + column half
-  const int ep_q = warp & 3, ep_h = warp >> 2;
+  const int ep_q = warp & 3, ep_h = (warp >> 2) & 3;   // lane quarter, column part (0..3)
   const int ep_m = ep_q * 32 + lane;
   // gather role: two threads per output pixel of the tile's RB x OW3 outputs
-  const int g_px = tid >> 1, g_half = tid & 1;
+  const int g_px = tid >> 2, g_part = tid & 3;   // four threads per output pixel
   const bool g_live = g_px < C::RB * C::OW3;
   const int g_r = g_live ? g_px / C::OW3 : 0, g_x = g_live ? g_px % C::OW3 : 0;
 
@@ -176,11 +177,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
     }
     // the K half is a compile-time constant inside `half`, so every (dy, dx) below is too and
     // rowp[] stays in registers
-    auto half = [&](auto half_tag) {
-      constexpr int H = decltype(half_tag)::value;
+    auto part = [&](auto part_tag) {
+      constexpr int PI = decltype(part_tag)::value;
+      constexpr int C0 = PI == 0 ? 0 : PI == 1 ? 6 : PI == 2 ? 12 : 17;   // 6 + 6 + 5 + 5 chunks
+      constexpr int C1 = PI == 0 ? 6 : PI == 1 ? 12 : PI == 2 ? 17 : 22;
 #pragma unroll
-      for (int cc = 0; cc < 11; cc++) {
-        const int c = H * 11 + cc;      // 16-byte K chunk
+      for (int c = C0; c < C1; c++) {   // 16-byte K chunk
         float hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -197,10 +199,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
         *reinterpret_cast<float4*>(sA1l + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
     };
-    if (im_half == 0)
-      half(std::integral_constant<int, 0>{});
+    if (im_part == 0)
+      part(std::integral_constant<int, 0>{});
+    else if (im_part == 1)
+      part(std::integral_constant<int, 1>{});
+    else if (im_part == 2)
+      part(std::integral_constant<int, 2>{});
     else
-      half(std::integral_constant<int, 1>{});
+      part(std::integral_constant<int, 3>{});
   };
   // MMA-1: D1 = A1 * W1^T  (33 x M128 N64 K8), one thread.  A k-step advances every operand by
   // two 128-byte core matrices = 16 in the descriptor's 16-byte address units.
@@ -235,20 +241,17 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   // epilogue 1: A2 = split(relu(D1 + b1)) -> tensor memory
   auto epilogue1 = [&]() {
     const uint32_t lane_base = (uint32_t)(ep_q * 32) << 16;
+    const int c0 = ep_h * 16;
+    float v[16];
+    tmem_ld16(tmem + lane_base + C::cD1 + c0, v);
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-      float v[16];
-      const int c0 = ep_h * 32 + g * 16;
-      tmem_ld16(tmem + lane_base + C::cD1 + c0, v);
+    for (int h8 = 0; h8 < 2; h8++) {
+      float hi[8], lo[8];
 #pragma unroll
-      for (int h8 = 0; h8 < 2; h8++) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          split_tf32(fmaxf(v[h8 * 8 + j] + sB1[c0 + h8 * 8 + j], 0.f), hi[j], lo[j]);
-        tmem_st8(tmem + lane_base + C::cA2h + c0 + h8 * 8, hi);
-        tmem_st8(tmem + lane_base + C::cA2l + c0 + h8 * 8, lo);
-      }
+      for (int j = 0; j < 8; j++)
+        split_tf32(fmaxf(v[h8 * 8 + j] + sB1[c0 + h8 * 8 + j], 0.f), hi[j], lo[j]);
+      tmem_st8(tmem + lane_base + C::cA2h + c0 + h8 * 8, hi);
+      tmem_st8(tmem + lane_base + C::cA2l + c0 + h8 * 8, lo);
     }
     tmem_st_wait();
   };
@@ -269,34 +272,29 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
   // epilogue 2: A3 = split(relu(D2 + b2)) -> tensor memory
   auto epilogue2 = [&]() {
     const uint32_t lane_base = (uint32_t)(ep_q * 32) << 16;
-    const int c0 = ep_h * 16;
-    float v[16];
-    tmem_ld16(tmem + lane_base + C::cD2 + c0, v);
+    const int c0 = ep_h * 8;
+    float v[8], hi[8], lo[8];
+    tmem_ld8(tmem + lane_base + C::cD2 + c0, v);
 #pragma unroll
-    for (int h8 = 0; h8 < 2; h8++) {
-      float hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        split_tf32(fmaxf(v[h8 * 8 + j] + sB2[c0 + h8 * 8 + j], 0.f), hi[j], lo[j]);
-      tmem_st8(tmem + lane_base + C::cA3h + c0 + h8 * 8, hi);
-      tmem_st8(tmem + lane_base + C::cA3l + c0 + h8 * 8, lo);
-    }
+    for (int j = 0; j < 8; j++) split_tf32(fmaxf(v[j] + sB2[c0 + j], 0.f), hi[j], lo[j]);
+    tmem_st8(tmem + lane_base + C::cA3h + c0, hi);
+    tmem_st8(tmem + lane_base + C::cA3l + c0, lo);
     tmem_st_wait();
   };
   // epilogue 3 of tile b: Q rows (25 tap products per out2 pixel) -> ring in shared memory
   auto epilogue3 = [&](int b) {
-    const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + C::cD3 + ep_h * 16;
-    float v[16];
-    tmem_ld16(taddr, v);
+    const uint32_t taddr = tmem + ((uint32_t)(ep_q * 32) << 16) + C::cD3 + ep_h * 8;
+    float v[8];
+    tmem_ld8(taddr, v);
     const int r = ep_m / C::OW2, x = ep_m % C::OW2;
     const int slot = (b * C::RB + r) % C::RING;
-    float* q = sQ + (slot * C::OW2 + x) * C::QP + ep_h * 16;
+    float* q = sQ + (slot * C::OW2 + x) * C::QP + ep_h * 8;
 #pragma unroll
-    for (int j = 0; j < 16; j++)
-      if (ep_h * 16 + j < C::QP) q[j] = v[j];
+    for (int j = 0; j < 8; j++)
+      if (ep_h * 8 + j < C::QP) q[j] = v[j];
   };
   // gather of the output rows completed by tile b:
-  // out3[j][x] = b3 + sum_{dy,dx} Q[j+dy][x+dx][dy*5+dx], two threads per pixel
+  // out3[j][x] = b3 + sum_{dy,dx} Q[j+dy][x+dx][dy*5+dx], four threads per pixel
   auto gather = [&](int b) {
     const int j = b * C::RB - (C::F3 - 1) + g_r;     // output row relative to R0
     float acc = 0.f;
@@ -308,12 +306,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_tc_kernel(fused::Arg
 #pragma unroll
         for (int dx = 0; dx < C::F3; dx++) {
           const int tap = dy * C::F3 + dx;
-          if ((tap < 13) == (g_half == 0)) acc += q[dx * C::QP + dx];
+          if (tap % 4 == g_part) acc += q[dx * C::QP + dx];
         }
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (g_live && g_half == 0 && j >= 0 && j < rows_here) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (g_live && g_part == 0 && j >= 0 && j < rows_here) {
       const int gx = X0 + g_x;
       if (gx < a.w3) dst[(size_t)(R0 + j) * a.w3 + gx] = acc + b3;
     }

@@ -78,6 +78,7 @@ struct srcnn_ctx {
   // fused inference implementation: tensor cores (tcgen05, 3xTF32) where instantiated, unless
   // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
   bool fused_use_tc = true;
+  bool fused_use_ws = true;   // warp-specialised variant of the tensor-core kernel (default)
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand

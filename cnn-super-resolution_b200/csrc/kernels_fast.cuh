@@ -8,6 +8,7 @@
 #include "context.cuh"
 #include "fused_forward.cuh"
 #include "fused_forward_tc.cuh"
+#include "fused_forward_ws.cuh"
 #include "train_kernels.cuh"
 
 #include <cstdlib>
@@ -56,8 +57,10 @@ __global__ void update_all_kernel(UpdateAllArgs a) {
 inline int configure(srcnn_ctx* ctx) {
   SRCNN_TRY(fused::configure());
   SRCNN_TRY(fused_tc::configure());
+  SRCNN_TRY(fused_ws::configure());
   const char* impl = std::getenv("SRCNN_FUSED_IMPL");
   ctx->fused_use_tc = !(impl && std::strcmp(impl, "simt") == 0);
+  ctx->fused_use_ws = !(impl && std::strcmp(impl, "tc") == 0);   // "tc" = lockstep variant
   return SRCNN_OK;
 }
 
@@ -95,7 +98,8 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
-  if (ctx->fused_use_tc && fused_tc::supported(n1, n2, f1, f2, f3)) return fused_tc::launch(ctx, a, S);
+  if (ctx->fused_use_tc && fused_tc::supported(n1, n2, f1, f2, f3))
+    return ctx->fused_use_ws ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
   return fused::launch(ctx, n1, n2, a, S);
 }
 

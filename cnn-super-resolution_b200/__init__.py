@@ -16,7 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libsrcnn_b200.so")
+LIB_PATH = os.environ.get("SRCNN_B200_LIB") or os.path.join(HERE, "libsrcnn_b200.so")
 HEADER = os.path.join(ROOT, "include", "srcnn_b200.h")
 
 NULL_MEM = 1 << 30

@@ -9,8 +9,8 @@
 //   MMA  (issuer)    16     wait a2_full(b) -> MMA-2(b); wait a1_full(b+1) -> MMA-1(b+1);
 //                           wait a3_full(b) -> MMA-3(b)        (tcgen05.commit -> bar1/2/3)
 //   E1   (epilogue1) 0..3   wait MMA-1(b) -> D1 -> relu/split -> A2 (TMEM) -> arrive a2_full
-//   E23  (epi 2+3)   4..7   wait MMA-3(b-1) -> Q rows -> ring; gather out3 rows of tile b-1;
-//                           wait MMA-2(b) -> D2 -> relu/split -> A3 (TMEM) -> arrive a3_full
+//   E2   (epilogue2) 4..7   wait MMA-2(b) -> D2 -> relu/split -> A3 (TMEM) -> arrive a3_full
+//   E3   (epi3+gath) 17..20 wait MMA-3(b) -> Q rows -> ring (arrive d3_free); gather out3 rows
 //
 // Buffer hand-over needs no extra "free" barriers: E1 arrives on a2_full(b) only after it has
 // read D1(b), and the issuer waits for a2_full(b) before MMA-1(b+1), so D1 is free by then; the
@@ -29,7 +29,7 @@ namespace fused_ws {
 
 struct Cfg {
   static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
-  static constexpr int NT = 17 * 32;
+  static constexpr int NT = 21 * 32;
   static constexpr int OW2 = 64, RB = 2;
   static constexpr int OW3 = OW2 - (F3 - 1);
   static constexpr int IW = OW2 + F1 - 1, IWP = IW + 4;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
   float* sQ = smem + C::oQ;
   // bar1[i]: MMA-1 into D1 buffer i done (one barrier per buffer: a waiter is never more than
   // one phase behind); bar2/bar3: MMA-2 / MMA-3 done; aN_full: operand of layer N ready
-  __shared__ __align__(8) uint64_t bar1[2], bar2, bar3, a1_full, a2_full, a3_full;
+  __shared__ __align__(8) uint64_t bar1[2], bar2, bar3, a1_full, a2_full, a3_full, d3_free;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
     mbar_init(&a1_full, 256);
     mbar_init(&a2_full, 128);
     mbar_init(&a3_full, 128);
+    mbar_init(&d3_free, 128);
   }
   fence_proxy_async();   // the weight operands are read by the tensor core (async proxy)
   tcgen05_fence_before();
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
         pre_idx = (rr % C::IR) * C::IWP + xx;
       }
       if (b > 0) mbar_wait(&bar1[(b - 1) & 1], (uint32_t)(((b - 1) >> 1) & 1));   // MMA-1(b-1) done: A1 free
+#ifndef EXP_SKIP_IM2COL
       im2col(b);
+#endif
       fence_proxy_async();
       mbar_arrive(&a1_full);
       if (pre_idx >= 0) sIn[pre_idx] = pre;                   // rows of tile b+1
@@ -235,9 +238,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
         uint64_t bh = make_desc_kmajor(sW1h, 0, 128, sbo), bl = make_desc_kmajor(sW1l, 0, 128, sbo);
 #pragma unroll
         for (int ks = 0; ks < C::K1 / 8; ks++) {
+#ifndef EXP_MMA_THIRD
           mma_tf32(d1, al, bh, idesc1, ks > 0);
           mma_tf32(d1, ah, bl, idesc1, 1);
           mma_tf32(d1, ah, bh, idesc1, 1);
+#else
+          mma_tf32(d1, ah, bh, idesc1, ks > 0);
+#endif
           ah += 16; al += 16; bh += 16; bl += 16;
         }
         mma_commit(&bar1[b & 1]);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
       // that tile has completed AND the accumulator it overwrites has been consumed:
       //   MMA-1(t): a1_full(t);  D1[t&1] was read by E1(t-2)  <=> MMA-2(t-2) already issued
       //   MMA-2(t): a2_full(t);  D2 was read by E23(t-1)      <=> MMA-3(t-1) already issued
-      //   MMA-3(t): a3_full(t);  D3 was read by E23(t-1)      <=> implied by a3_full(t)
+      //   MMA-3(t): a3_full(t);  D3 was read by E3(t-1)       <=> d3_free(t-1)
       int n1 = 0, n2 = 0, n3 = 0;
       while (n3 < n_tiles) {
         bool did = false;
@@ -286,7 +293,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
           n2++;
           did = true;
         }
-        if (n3 < n2 && mbar_test(&a3_full, (uint32_t)(n3 & 1))) {
+        if (n3 < n2 && mbar_test(&a3_full, (uint32_t)(n3 & 1)) &&
+            (n3 == 0 || mbar_test(&d3_free, (uint32_t)((n3 - 1) & 1)))) {
           tcgen05_fence_after();
           issue_mma3();
           n3++;
@@ -303,6 +311,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
       if (b > 0) mbar_wait(&bar2, (uint32_t)((b - 1) & 1));    // MMA-2(b-1) done: A2 free
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 64u * (uint32_t)(b & 1);
+#ifdef EXP_SKIP_E1
+      if (b < 0)
+#endif
 #pragma unroll 1
       for (int g = 0; g < 4; g++) {
         float v[16];
@@ -322,28 +333,50 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
       mbar_arrive(&a2_full);
     }
   } else if (warp < 8) {
-    // ============================ E23: epilogue 3 + gather of tile b-1, epilogue 2 of tile b =
+    // ============================ E2: A3 = split(relu(D2 + b2)) -> TMEM ====================
     const int q4 = warp - 4;
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
-    const int et = tid - 128;                 // 0..127
+    for (int b = 0; b < n_tiles; b++) {
+      mbar_wait(&bar2, (uint32_t)(b & 1));                     // MMA-2(b) done
+      if (b > 0) mbar_wait(&bar3, (uint32_t)((b - 1) & 1));    // MMA-3(b-1) done: A3 free
+      tcgen05_fence_after();
+      float v[32];
+      tmem_ld16(tmem + lane_base + C::cD2, v);
+      tmem_ld16(tmem + lane_base + C::cD2 + 16, v + 16);
+#pragma unroll
+      for (int h8 = 0; h8 < 4; h8++) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          split_tf32(fmaxf(v[h8 * 8 + j] + sB2[h8 * 8 + j], 0.f), hi[j], lo[j]);
+        tmem_st8(tmem + lane_base + C::cA3h + h8 * 8, hi);
+        tmem_st8(tmem + lane_base + C::cA3l + h8 * 8, lo);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&a3_full);
+    }
+  } else if (warp >= 17) {
+    // ============================ E3: Q rows -> ring, 25-term gather -> out3 =================
+    const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int et = tid - 17 * 32;             // 0..127
     const int ep_m = q4 * 32 + lane;          // tile row of this thread's TMEM lane
     const int ep_r = ep_m / C::OW2, ep_x = ep_m % C::OW2;
     const int g_r = et / C::OW3, g_x = et % C::OW3;   // gather: one thread per output pixel
     const bool g_live = et < C::RB * C::OW3;
-    auto epilogue3_and_gather = [&](int b) {   // b = tile whose Q rows have just been produced
-      mbar_wait(&bar3, (uint32_t)(b & 1));
+    for (int b = 0; b < n_tiles; b++) {
+      mbar_wait(&bar3, (uint32_t)(b & 1));                     // MMA-3(b) done: Q tile in D3
       tcgen05_fence_after();
+      float v[32];
+      tmem_ld16(tmem + lane_base + C::cD3, v);
+      tmem_ld16(tmem + lane_base + C::cD3 + 16, v + 16);
+      tcgen05_fence_before();
+      mbar_arrive(&d3_free);                                   // D3 may be overwritten
       const int slot = (b * C::RB + ep_r) % C::RING;
       float* q = sQ + (slot * C::OW2 + ep_x) * C::QP;
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        float v[16];
-        tmem_ld16(tmem + lane_base + C::cD3 + g * 16, v);
-#pragma unroll
-        for (int j = 0; j < 16; j++)
-          if (g * 16 + j < C::QP) q[g * 16 + j] = v[j];
-      }
-      tcgen05_fence_before();
+      for (int j = 0; j < C::QP; j++) q[j] = v[j];
       named_bar_sync(C::BAR_E23, 128);          // Q rows of tile b visible to the gather
       const int j = b * C::RB - (C::F3 - 1) + (g_live ? g_r : 0);
       if (g_live && j >= 0 && j < rows_here) {
@@ -362,30 +395,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_ws_kernel(fused::Arg
         const int gx = X0 + g_x;
         if (gx < a.w3) dst[(size_t)(R0 + j) * a.w3 + gx] = (acc0 + acc1) + b3;
       }
-    };
-    for (int b = 0; b < n_tiles; b++) {
-      if (b > 0) epilogue3_and_gather(b - 1);
-      mbar_wait(&bar2, (uint32_t)(b & 1));                     // MMA-2(b) done
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int g = 0; g < 2; g++) {
-        float v[16];
-        tmem_ld16(tmem + lane_base + C::cD2 + g * 16, v);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; h8++) {
-          float hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            split_tf32(fmaxf(v[h8 * 8 + j] + sB2[g * 16 + h8 * 8 + j], 0.f), hi[j], lo[j]);
-          tmem_st8(tmem + lane_base + C::cA3h + g * 16 + h8 * 8, hi);
-          tmem_st8(tmem + lane_base + C::cA3l + g * 16 + h8 * 8, lo);
-        }
-      }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&a3_full);
     }
-    epilogue3_and_gather(n_tiles - 1);
   }
 
   tcgen05_fence_before();

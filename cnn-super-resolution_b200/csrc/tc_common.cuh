@@ -16,16 +16,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- operand split -------------------------------------------------------------------------
-// hi = x rounded to TF32 (10 explicit mantissa bits), lo = (x - hi) rounded to TF32.
-// x - hi is exact in FP32, so hi + lo reproduces x to ~2^-21 relative.
+// hi = x rounded to TF32 (10 explicit mantissa bits, round-half-away on the magnitude: add half
+// an ulp to the bit pattern, clear the 13 low bits), lo = x - hi (exact in FP32).  The tensor
+// core ignores the 13 low mantissa bits of a TF32 operand, so lo needs no rounding of its own:
+// |x - (hi + trunc(lo))| <= 2^-21 |x|.  `cvt.rna.tf32.f32` is NOT used: sm_100a has no such
+// instruction, ptxas expands each one to VIADD + FSETP + SEL + LOP3 (9 instructions per split
+// instead of 3), and the split is the inner loop of every SIMT role of the fused kernels.
+// Non-finite inputs are not preserved (inf becomes NaN); the path never produces them.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 
 // ---- canonical K-major, no-swizzle operand layout ------------------------------------------

@@ -77,8 +77,7 @@ struct srcnn_ctx {
   uint64_t launch_count = 0;
   // fused inference implementation: tensor cores (tcgen05, 3xTF32) where instantiated, unless
   // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
-  bool fused_use_tc = true;
-  bool fused_use_ws = true;   // warp-specialised variant of the tensor-core kernel (default)
+  int fused_impl = 3;   // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand

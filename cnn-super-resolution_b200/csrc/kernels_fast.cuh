@@ -9,6 +9,7 @@
 #include "fused_forward.cuh"
 #include "fused_forward_tc.cuh"
 #include "fused_forward_ws.cuh"
+#include "fused_forward_pl.cuh"
 #include "train_kernels.cuh"
 
 #include <cstdlib>
@@ -58,9 +59,13 @@ inline int configure(srcnn_ctx* ctx) {
   SRCNN_TRY(fused::configure());
   SRCNN_TRY(fused_tc::configure());
   SRCNN_TRY(fused_ws::configure());
+  SRCNN_TRY(fused_pl::configure());
+  // A/B switch between the generations of the fused kernel (default: the newest)
   const char* impl = std::getenv("SRCNN_FUSED_IMPL");
-  ctx->fused_use_tc = !(impl && std::strcmp(impl, "simt") == 0);
-  ctx->fused_use_ws = !(impl && std::strcmp(impl, "tc") == 0);   // "tc" = lockstep variant
+  ctx->fused_impl = 3;                                           // "pl": plane operands
+  if (impl && std::strcmp(impl, "simt") == 0) ctx->fused_impl = 0;
+  if (impl && std::strcmp(impl, "tc") == 0) ctx->fused_impl = 1;  // lockstep tcgen05
+  if (impl && std::strcmp(impl, "ws") == 0) ctx->fused_impl = 2;  // warp-specialised, im2col
   return SRCNN_OK;
 }
 
@@ -98,8 +103,10 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
-  if (ctx->fused_use_tc && fused_tc::supported(n1, n2, f1, f2, f3))
-    return ctx->fused_use_ws ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
+  if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
+    if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
+    return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
+  }
   return fused::launch(ctx, n1, n2, a, S);
 }
 

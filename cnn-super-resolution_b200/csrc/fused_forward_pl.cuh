@@ -15,17 +15,20 @@
 //    packed pixels H(r)[c] = in[r][c..c+3].  Every input pixel is written 8 times (hi/lo x 4
 //    quads... 2 planes) instead of 176 times, and the planes are shared by consecutive tiles.
 //  * a tcgen05.mma costs its issuing thread ~57 cycles whatever its shape, and the tensor pipe
-//    accepts instructions from several threads: each layer has its OWN issuer warp, and layer
-//    1 is issued as  A_hi x [W_hi; W_lo] (N = 128) + A_lo x W_hi (N = 64): 22 instructions per
-//    tile instead of 33; the epilogue adds the two 64-column halves.
+//    accepts instructions from several threads: each layer has its OWN issuer warp, and every
+//    layer is issued as  A_hi x [W_hi; W_lo] (N doubled) + A_lo x W_hi: two instructions per
+//    K-step instead of three (46 per tile instead of 69); the epilogue adds the two halves.
+//  * the split A operand of the next layer is written in place over the accumulator it was
+//    computed from, and every TMEM buffer exists twice, so no stage ever waits for the stage
+//    behind it to release a buffer of the SAME tile parity before two tiles later.
 //  * the operand split costs 3 instructions (tc_common.cuh) instead of 9.
 //
 //   role (warps)      per tile b (= out2 row R0+b of the strip)
 //   IM   12..16       input row b+8 -> H(b+8), Qd(b+5) (hi/lo)                 -> p_full
-//   I1   17           MMA-1(b): 11 K-steps x 2 passes -> D1[b&1]               -> bar1, p_free
-//   E1   0..3         D1 -> +b1, relu, split -> A2 (TMEM)                      -> d1_free, a2_full
-//   I2   18           MMA-2(b): 8 K-steps x 3 passes (A2 in TMEM) -> D2        -> bar2
-//   E2   4..7         D2 -> +b2, relu, split -> A3 (TMEM)                      -> d2_free, a3_full
+//   I1   17           MMA-1(b): 11 K-steps x 2 -> D1[b&1]                      -> bar1, p_free
+//   E1   0..3         D1 -> +b1, relu, split -> A2 (in place)                  -> a2_full
+//   I2   18           MMA-2(b): 8 K-steps x 2 (A2 in TMEM) -> D2[b&1]          -> bar2
+//   E2   4..7         D2 -> +b2, relu, split -> A3 (in place)                  -> a3_full
 //   I3   19           MMA-3(b): tap GEMM Q[px][25] = out2[px][:] . W3[tap][:]  -> bar3
 //   E3   8..11        D3 -> Q row in smem -> out3 row b-4 += 25-term gather    -> d3_free
 #pragma once
@@ -59,18 +62,19 @@ struct Cfg {
   static constexpr int oQh = oHl + RH * PF;
   static constexpr int oQl = oQh + RQ * PF;
   static constexpr int oW1 = oQl + RQ * PF;      // [128][K1]: rows 0..63 W_hi, 64..127 W_lo
-  static constexpr int oW2h = oW1 + 2 * N1 * K1;
-  static constexpr int oW2l = oW2h + N2 * K2;
-  static constexpr int oW3h = oW2l + N2 * K2;
-  static constexpr int oW3l = oW3h + NT3 * N2;
-  static constexpr int oB1 = oW3l + NT3 * N2;
+  static constexpr int oW2 = oW1 + 2 * N1 * K1;  // [64][K2]: rows 0..31 W_hi, 32..63 W_lo
+  static constexpr int oW3 = oW2 + 2 * N2 * K2;  // [64][N2]: rows = taps (25 of 32), hi then lo
+  static constexpr int oB1 = oW3 + 2 * NT3 * N2;
   static constexpr int oB2 = oB1 + N1;
   static constexpr int oQs = oB2 + N2;           // 2 staged Q rows [M][QP]
   static constexpr int TOTAL = oQs + 2 * M * QP;
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)TOTAL;
-  // tensor memory columns
-  static constexpr uint32_t cD1 = 0 /* + 128 * (b & 1) */, cA2h = 256, cA2l = 320, cD2 = 384,
-                            cD3 = 416, cA3h = 448, cA3l = 480;
+  // tensor memory columns, every buffer twice (+ its size * (b & 1)).  The split A operand of
+  // the next layer is written IN PLACE over the accumulator it was computed from:
+  //   D1: [0,64) A_hi.W_hi + A_lo.W_hi, [64,128) A_hi.W_lo   ->  A2: [0,64) hi, [64,128) lo
+  //   D2: [0,32) + [32,64) likewise                          ->  A3: [0,32) hi, [32,64) lo
+  //   D3: [0,32) + [32,64) (25 taps of 32 used)
+  static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr int BAR_E3 = 1;
 };
@@ -89,6 +93,18 @@ __host__ __device__ __forceinline__ int tap_of(int s, int j, int e) {
   else { if (j) return -1; dy = 4 + e; dx = 8; }               // Qd(y+4)[c+8], [c+9] = pad
   return dy * Cfg::F1 + dx;
 }
+
+#ifdef PL_TIMING
+#define PL_T0 long long _tw[4] = {0, 0, 0, 0}; const long long _tstart = clock64();
+#define PL_WAIT(i, ...) { const long long _t = clock64(); __VA_ARGS__; _tw[i] += clock64() - _t; }
+#define PL_REPORT(name) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) \
+    printf("%-3s warp %2d: total %8lld  wait0 %8lld  wait1 %8lld  wait2 %8lld  tiles %d\n", name, warp, \
+           clock64() - _tstart, _tw[0], _tw[1], _tw[2], n_tiles);
+#else
+#define PL_T0
+#define PL_WAIT(i, ...) __VA_ARGS__;
+#define PL_REPORT(name)
+#endif
 
 using fused_ws::mbar_arrive;
 using fused_ws::named_bar_sync;
@@ -112,17 +128,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   using namespace tc;
   extern __shared__ __align__(128) float smem[];
   float* sW1 = smem + C::oW1;
-  float* sW2h = smem + C::oW2h;
-  float* sW2l = smem + C::oW2l;
-  float* sW3h = smem + C::oW3h;
-  float* sW3l = smem + C::oW3l;
+  float* sW2 = smem + C::oW2;
+  float* sW3 = smem + C::oW3;
   float* sB1 = smem + C::oB1;
   float* sB2 = smem + C::oB2;
   float* sQs = smem + C::oQs;
   // p_full[i]/p_free[i]: planes of tile b (i = b&3) written / no longer read by MMA-1(b);
-  // barN: MMA-N done; dN_free: accumulator N drained; aN_full: A operand of layer N written
-  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], d1_free[2], a2_full, bar2,
-      d2_free, a3_full, bar3, d3_free;
+  // barN[i]: MMA-N of a tile with b&1 == i done; aN_full[i]: A operand of layer N written;
+  // d3_free[i]: D3 buffer i drained.  Every TMEM buffer exists twice (tile parity).
+  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2],
+      a3_full[2], bar3[2], d3_free[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,7 +146,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   const float* img = a.in + (size_t)blockIdx.z * a.w * a.h;
   float* dst = a.out + (size_t)blockIdx.z * a.w3 * a.h3;
 
-  // ---- stage parameters (all threads): B operands split into TF32 hi/lo, [n][k] canonical ----
+  // ---- stage parameters (all threads): B operands [n][k] canonical, rows 0..N-1 the TF32 hi
+  // parts, rows N..2N-1 the lo parts (one N=2N MMA evaluates A_hi.W_hi and A_hi.W_lo) ----------
   for (int i = tid; i < 2 * C::N1 * C::K1; i += C::NT) {
     const int n = i / C::K1, k = i % C::K1;
     const int t = tap_of(k >> 3, (k >> 2) & 1, k & 3);
@@ -139,19 +155,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     split_tf32(t >= 0 ? __ldg(a.pw1 + t * C::N1 + (n & (C::N1 - 1))) : 0.f, hi, lo);
     sW1[kmajor_offset(n, k, C::K1)] = n < C::N1 ? hi : lo;
   }
-  for (int i = tid; i < C::N2 * C::K2; i += C::NT) {
+  for (int i = tid; i < 2 * C::N2 * C::K2; i += C::NT) {
     const int n = i / C::K2, k = i % C::K2;
     float hi, lo;
-    split_tf32(__ldg(a.pw2 + k * C::N2 + n), hi, lo);
-    sW2h[kmajor_offset(n, k, C::K2)] = hi;
-    sW2l[kmajor_offset(n, k, C::K2)] = lo;
+    split_tf32(__ldg(a.pw2 + k * C::N2 + (n & (C::N2 - 1))), hi, lo);
+    sW2[kmajor_offset(n, k, C::K2)] = n < C::N2 ? hi : lo;
   }
-  for (int i = tid; i < C::NT3 * C::N2; i += C::NT) {
-    const int n = i / C::N2, k = i % C::N2;   // n = tap dy*5+dx, k = channel
+  for (int i = tid; i < 2 * C::NT3 * C::N2; i += C::NT) {
+    const int n = i / C::N2, k = i % C::N2;   // n & 31 = tap dy*5+dx, k = channel
+    const int tap = n & (C::NT3 - 1);
     float hi, lo;
-    split_tf32(n < C::QP ? __ldg(a.pw3 + n * C::N2 + k) : 0.f, hi, lo);
-    sW3h[kmajor_offset(n, k, C::N2)] = hi;
-    sW3l[kmajor_offset(n, k, C::N2)] = lo;
+    split_tf32(tap < C::QP ? __ldg(a.pw3 + tap * C::N2 + k) : 0.f, hi, lo);
+    sW3[kmajor_offset(n, k, C::N2)] = n < C::NT3 ? hi : lo;
   }
   for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i);
   for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i);
@@ -168,14 +183,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&bar1[i], 1);
-      mbar_init(&d1_free[i], 128);
+      mbar_init(&a2_full[i], 128);
+      mbar_init(&bar2[i], 1);
+      mbar_init(&a3_full[i], 128);
+      mbar_init(&bar3[i], 1);
+      mbar_init(&d3_free[i], 128);
     }
-    mbar_init(&a2_full, 128);
-    mbar_init(&bar2, 1);
-    mbar_init(&d2_free, 128);
-    mbar_init(&a3_full, 128);
-    mbar_init(&bar3, 1);
-    mbar_init(&d3_free, 128);
   }
   fence_proxy_async();   // the weight operands are read by the tensor core (async proxy)
   tcgen05_fence_before();
@@ -222,6 +235,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) v[e] = ld(C::F1 - 1, e);
+    PL_T0
     for (int b = 0; b < n_tiles; b++) {
       float nv[4];
 #pragma unroll
@@ -230,7 +244,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
 #pragma unroll
       for (int e = 0; e < 4; e++) split_tf32(v[e], h[e], l[e]);
       // H(b+8) replaces H(b+4) (last read by MMA-1(b-4)), Qd(b+5) replaces Qd(b-3) (MMA-1(b-3))
-      if (b >= 3) mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1));
+      if (b >= 3) PL_WAIT(0, mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1)))
       if (active) {
         const int sh = b & (C::RH - 1), sq = (b + 5) & (C::RQ - 1);
         *reinterpret_cast<float4*>(sHh + sh * C::PF) = make_float4(h[0], h[1], h[2], h[3]);
@@ -245,13 +259,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
 #pragma unroll
       for (int e = 0; e < 4; e++) v[e] = nv[e];
     }
+    PL_REPORT("IM")
   } else if (warp == C::W_I1) {
     // ============================ I1: layer-1 MMA issuer ===================================
     if (lane == 0) {
       const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::N1);   // A_hi x [W_hi; W_lo]
       const uint32_t idesc_lo = make_idesc_tf32(C::M, C::N1);       // A_lo x W_hi
-      const uint32_t wsbo = 128 * (C::K1 / 4);
-      const uint64_t wdesc = make_desc_kmajor(sW1, 0, 128, wsbo);
+      const uint64_t wdesc = make_desc_kmajor(sW1, 0, 128, 128 * (C::K1 / 4));
       const uint32_t aHh = smem_u32(smem + C::oHh), aHl = smem_u32(smem + C::oHl);
       const uint32_t aQh = smem_u32(smem + C::oQh), aQl = smem_u32(smem + C::oQl);
       constexpr uint32_t PB = C::PF * 4;   // bytes per plane
@@ -260,9 +274,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
                ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
       };
+      PL_T0
       for (int t = 0; t < n_tiles; t++) {
-        mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1));
-        if (t >= 2) mbar_wait(&d1_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+        PL_WAIT(0, mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1)))
+        // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
+        if (t >= 2) PL_WAIT(1, mbar_wait(&bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
         tcgen05_fence_after();
         const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
         const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * PB;
@@ -285,50 +301,59 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         mma_commit(&bar1[t & 1]);
         mma_commit(&p_free[t & 3]);
       }
+      PL_REPORT("I1")
     }
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(C::M, C::N2);
-      const uint32_t sbo = 128 * (C::K2 / 4);
-      const uint64_t bh0 = make_desc_kmajor(sW2h, 0, 128, sbo), bl0 = make_desc_kmajor(sW2l, 0, 128, sbo);
+      const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::N2);   // A2_hi x [W2_hi; W2_lo]
+      const uint32_t idesc_lo = make_idesc_tf32(C::M, C::N2);       // A2_lo x W2_hi
+      const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 4));
+      PL_T0
       for (int t = 0; t < n_tiles; t++) {
-        mbar_wait(&a2_full, (uint32_t)(t & 1));
-        if (t > 0) mbar_wait(&d2_free, (uint32_t)((t - 1) & 1));
+        PL_WAIT(0, mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1)))
+        // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
+        if (t >= 2) PL_WAIT(1, mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
         tcgen05_fence_after();
+        const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
+        const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
 #pragma unroll
         for (int ks = 0; ks < C::K2 / 8; ks++) {
-          mma_tf32_ts(tmem + C::cD2, tmem + C::cA2l + ks * 8, bh0 + 16 * ks, idesc, ks > 0);
-          mma_tf32_ts(tmem + C::cD2, tmem + C::cA2h + ks * 8, bl0 + 16 * ks, idesc, 1);
-          mma_tf32_ts(tmem + C::cD2, tmem + C::cA2h + ks * 8, bh0 + 16 * ks, idesc, 1);
+          mma_tf32_ts(d2, a2 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_tf32_ts(d2, a2 + C::N1 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
         }
-        mma_commit(&bar2);
+        mma_commit(&bar2[t & 1]);
       }
+      PL_REPORT("I2")
     }
   } else if (warp == C::W_I3) {
     // ============================ I3: layer-3 tap-GEMM issuer (A3 in TMEM) =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(C::M, C::NT3);
-      const uint32_t sbo = 128 * (C::N2 / 4);
-      const uint64_t bh0 = make_desc_kmajor(sW3h, 0, 128, sbo), bl0 = make_desc_kmajor(sW3l, 0, 128, sbo);
+      const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::NT3);
+      const uint32_t idesc_lo = make_idesc_tf32(C::M, C::NT3);
+      const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::N2 / 4));
+      PL_T0
       for (int t = 0; t < n_tiles; t++) {
-        mbar_wait(&a3_full, (uint32_t)(t & 1));
-        if (t > 0) mbar_wait(&d3_free, (uint32_t)((t - 1) & 1));
+        PL_WAIT(0, mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1)))
+        if (t >= 2) PL_WAIT(1, mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
         tcgen05_fence_after();
+        const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+        const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
 #pragma unroll
         for (int ks = 0; ks < C::N2 / 8; ks++) {
-          mma_tf32_ts(tmem + C::cD3, tmem + C::cA3l + ks * 8, bh0 + 16 * ks, idesc, ks > 0);
-          mma_tf32_ts(tmem + C::cD3, tmem + C::cA3h + ks * 8, bl0 + 16 * ks, idesc, 1);
-          mma_tf32_ts(tmem + C::cD3, tmem + C::cA3h + ks * 8, bh0 + 16 * ks, idesc, 1);
+          mma_tf32_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_tf32_ts(d3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
         }
-        mma_commit(&bar3);
+        mma_commit(&bar3[t & 1]);
       }
+      PL_REPORT("I3")
     }
   } else if (warp < C::W_E2) {
-    // ============================ E1: A2 = split(relu(D1 + b1)) -> TMEM ====================
+    // ============================ E1: A2 = split(relu(D1 + b1)), in place ==================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    PL_T0
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
+      PL_WAIT(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
 #pragma unroll 1
@@ -337,10 +362,6 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         tmem_ld16_nowait(d1 + g * 16, va);              // A_hi.W_hi + A_lo.W_hi
         tmem_ld16_nowait(d1 + C::N1 + g * 16, vb);      // A_hi.W_lo
         tmem_ld_wait();
-        if (g == 0 && b > 0) {
-          mbar_wait(&bar2, (uint32_t)((b - 1) & 1));    // MMA-2(b-1) done: A2 free
-          tcgen05_fence_after();
-        }
 #pragma unroll
         for (int h8 = 0; h8 < 2; h8++) {
           float hi[8], lo[8];
@@ -350,44 +371,45 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
 #pragma unroll
           for (int j = 0; j < 8; j++)
             split_tf32(fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + bias[j], 0.f), hi[j], lo[j]);
-          tmem_st8(tmem + lane_base + C::cA2h + g * 16 + h8 * 8, hi);
-          tmem_st8(tmem + lane_base + C::cA2l + g * 16 + h8 * 8, lo);
+          tmem_st8(d1 + g * 16 + h8 * 8, hi);
+          tmem_st8(d1 + C::N1 + g * 16 + h8 * 8, lo);
         }
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&d1_free[b & 1]);
-      mbar_arrive(&a2_full);
+      mbar_arrive(&a2_full[b & 1]);
     }
+    PL_REPORT("E1")
   } else if (warp < C::W_E3) {
-    // ============================ E2: A3 = split(relu(D2 + b2)) -> TMEM ====================
+    // ============================ E2: A3 = split(relu(D2 + b2)), in place ==================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    PL_T0
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar2, (uint32_t)(b & 1));                     // MMA-2(b) done
+      PL_WAIT(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
       tcgen05_fence_after();
-      float v[32];
-      tmem_ld16_nowait(tmem + lane_base + C::cD2, v);
-      tmem_ld16_nowait(tmem + lane_base + C::cD2 + 16, v + 16);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&d2_free);                                   // D2 may be overwritten
-      if (b > 0) {
-        mbar_wait(&bar3, (uint32_t)((b - 1) & 1));             // MMA-3(b-1) done: A3 free
-        tcgen05_fence_after();
-      }
+      const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
 #pragma unroll
-      for (int h8 = 0; h8 < 4; h8++) {
-        float hi[8], lo[8];
+      for (int g = 0; g < 2; g++) {
+        float va[16], vb[16];
+        tmem_ld16_nowait(d2 + g * 16, va);
+        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-          split_tf32(fmaxf(v[h8 * 8 + j] + sB2[h8 * 8 + j], 0.f), hi[j], lo[j]);
-        tmem_st8(tmem + lane_base + C::cA3h + h8 * 8, hi);
-        tmem_st8(tmem + lane_base + C::cA3l + h8 * 8, lo);
+        for (int h8 = 0; h8 < 2; h8++) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            split_tf32(fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + sB2[g * 16 + h8 * 8 + j], 0.f),
+                       hi[j], lo[j]);
+          tmem_st8(d2 + g * 16 + h8 * 8, hi);
+          tmem_st8(d2 + C::N2 + g * 16 + h8 * 8, lo);
+        }
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&a3_full);
+      mbar_arrive(&a3_full[b & 1]);
     }
+    PL_REPORT("E2")
   } else if (warp < C::W_IM) {
     // ============================ E3: Q row -> smem, 25-term gather -> out3 ================
     // thread x owns output column X0+x; the partial sums of the four output rows that still
@@ -396,19 +418,23 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     const int x = (warp & 3) * 32 + lane;
     const bool live = x < C::OW3 && X0 + x < a.w3;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    PL_T0
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar3, (uint32_t)(b & 1));                     // MMA-3(b) done: Q row in D3
+      PL_WAIT(0, mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-3(b) done
       tcgen05_fence_after();
-      float v[32];
-      tmem_ld16_nowait(tmem + lane_base + C::cD3, v);
-      tmem_ld16_nowait(tmem + lane_base + C::cD3 + 16, v + 16);
+      const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
+      float v[32], w[32];
+      tmem_ld16_nowait(d3, v);
+      tmem_ld16_nowait(d3 + 16, v + 16);
+      tmem_ld16_nowait(d3 + 32, w);
+      tmem_ld16_nowait(d3 + 48, w + 16);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&d3_free);                                   // D3 may be overwritten
+      mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
-      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j];
-      named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j] + w[j];
+      PL_WAIT(1, named_bar_sync(C::BAR_E3, 128))               // Q row visible to its neighbours
       float r[C::F3];
       if (x < C::OW3) {
 #pragma unroll
@@ -434,6 +460,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       if (b >= C::F3 - 1 && live)
         dst[(size_t)(R0 + b - (C::F3 - 1)) * a.w3 + X0 + x] = done + b3;
     }
+    PL_REPORT("E3")
   }
 
   tcgen05_fence_before();

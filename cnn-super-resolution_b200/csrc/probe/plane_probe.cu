@@ -279,6 +279,68 @@ __global__ void __launch_bounds__(128) mma_time_multi_kernel(int n_issuers, int 
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// the MMA mix of one tile of the plane kernel, one issuer warp per layer, no data dependencies:
+// mask bit 0: I1 (11 x [SS N128 + SS N64]), bit 1: I2 (24 TS N32), bit 2: I3 (12 TS N32),
+// bit 3: I1 issues unstacked (33 x SS N64) instead
+__global__ void __launch_bounds__(128) mma_mix_kernel(int mask, int reps, long long* cycles) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float* s = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar[4];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid / 32;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) s[i] = 0.f;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) for (int i = 0; i < 4; i++) mbar_init(&bar[i], 1);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  float* A = s;                     // planes
+  float* B = s + 16 * 1024;         // at 64 KB: 128 x 88 x 4 = 45 KB
+  float* B2 = s + 30 * 1024;        // at 120 KB
+  long long t0 = clock64();
+  if ((tid & 31) == 0 && ((mask >> warp) & 1) && warp < 3) {
+    const uint32_t id32 = make_idesc_tf32(M, 32), id64 = make_idesc_tf32(M, 64), id128 = make_idesc_tf32(M, 128);
+    for (int r = 0; r < reps; r++) {
+      if (warp == 0) {
+        if (mask & 8) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+            for (int p = 0; p < 3; p++)
+              mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16 + (p & 1) * 8192, 16, 128),
+                       make_desc_kmajor(B, ks * 256, 128, 2816), id64, (ks | p) > 0);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16, 16, 128),
+                     make_desc_kmajor(B, ks * 256, 128, 2816), id128, ks > 0);
+            mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16 + 8192, 16, 128),
+                     make_desc_kmajor(B, ks * 256, 128, 2816), id64, 1);
+          }
+        }
+      } else if (warp == 1) {
+#pragma unroll
+        for (int i = 0; i < 24; i++)
+          mma_tf32_ts(tmem + 384, tmem + 256 + (i / 3) * 8, make_desc_kmajor(B2, (i / 3) * 256, 128, 2048), id32, i > 0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+          mma_tf32_ts(tmem + 416, tmem + 448 + (i / 3) * 8, make_desc_kmajor(B2, 8192 + (i / 3) * 256, 128, 1024), id32, i > 0);
+      }
+    }
+    mma_commit(&bar[warp]);
+    mbar_wait(&bar[warp], 0);
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (tid == 0) *cycles = t1 - t0;
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main() {
   // ---------------- correctness of the plane descriptors
   std::vector<float> in(12 * IN_W), W(81 * N1);
@@ -326,7 +388,7 @@ int main() {
                           "SS f16 planes N128", "TS tf32 N8", "SS tf32 planes N128",
                           "SS tf32 planes N256", "TS tf32 N128", "TS f16 N64"};
   for (int grid : {1})
-    for (int mode = 3; mode < 4; mode++)
+    for (int mode = 3; mode < 3; mode++)
       for (int sync_each = 0; sync_each < 2; sync_each++) {
         const int reps = 200;
         mma_time_kernel<<<grid, 128, 200 * 1024>>>(mode, reps, sync_each, dcy);
@@ -350,6 +412,16 @@ int main() {
     cudaMemcpy(&cy, dcy, 8, cudaMemcpyDeviceToHost);
     printf("TS tf32 N32, 24 MMAs per rep split over %d issuing warps: %8.1f cyc/rep  %6.1f cyc/mma\n", ni,
            (double)cy / 200, (double)cy / 200 / 24);
+  }
+  cudaFuncSetAttribute(mma_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  for (int mask : {1, 2, 4, 3, 6, 7, 9, 11, 15}) {
+    mma_mix_kernel<<<1, 128, 160 * 1024>>>(mask, 200, dcy);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("MIX FAIL: %s\n", cudaGetErrorString(e)); return 1; }
+    long long cy;
+    cudaMemcpy(&cy, dcy, 8, cudaMemcpyDeviceToHost);
+    printf("mix mask %2d (%s%s%s%s): %8.1f cyc/tile\n", mask, mask & 1 ? "I1 " : "", mask & 2 ? "I2 " : "",
+           mask & 4 ? "I3 " : "", mask & 8 ? "unstacked" : "", (double)cy / 200);
   }
   return rc;
 }

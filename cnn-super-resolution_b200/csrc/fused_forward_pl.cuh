@@ -51,9 +51,10 @@ struct Cfg {
   static constexpr int PW = 144;                 // plane entries (16 bytes each)
   static constexpr int PF = PW * 4;              // floats per plane
   static constexpr int RQ = 8, RH = 4;           // ring slots: quad planes, H planes
-  static constexpr int W_E1 = 0, W_E2 = 4, W_E3 = 8, W_IM = 12, N_IM = 5, W_I1 = 17, W_I2 = 18,
-                       W_I3 = 19;
+  static constexpr int W_E1 = 0, N_E1 = 4, W_E2 = 4, W_E3 = 8, W_IM = 12, N_IM = 5, W_I1 = 17,
+                       W_I2 = 18, W_I3 = 19;
   static constexpr int NT = 20 * 32;
+  static constexpr int E1_CH = N1 / (N_E1 / 4);  // channels per E1 warp
   static constexpr int IM_THREADS = N_IM * 32;
   // shared memory carve-up (floats).  The H ring lies BELOW the quad ring: one K-step pairs a
   // chunk of H with a chunk of Qd through a (positive) leading-dimension byte offset.
@@ -119,6 +120,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float v[16]) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// one lane of the (converged) warp; ptxas then knows the guarded tcgen05.mma sequence is
+// executed by a single thread and does not wrap every instruction in an ELECT/branch loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&bar1[i], 1);
-      mbar_init(&a2_full[i], 128);
+      mbar_init(&a2_full[i], C::N_E1 * 32);
       mbar_init(&bar2[i], 1);
       mbar_init(&a3_full[i], 128);
       mbar_init(&bar3[i], 1);
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     PL_REPORT("IM")
   } else if (warp == C::W_I1) {
     // ============================ I1: layer-1 MMA issuer ===================================
-    if (lane == 0) {
+    {
       const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::N1);   // A_hi x [W_hi; W_lo]
       const uint32_t idesc_lo = make_idesc_tf32(C::M, C::N1);       // A_lo x W_hi
       const uint64_t wdesc = make_desc_kmajor(sW1, 0, 128, 128 * (C::K1 / 4));
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * PB;
         const uint32_t s0 = (uint32_t)(t & (C::RQ - 1)) * PB;
         const uint32_t s4 = (uint32_t)((t + 4) & (C::RQ - 1)) * PB;
+        if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < C::KS1; s++) {
           uint32_t ah, al, lbo_h, lbo_l;
@@ -300,12 +316,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         }
         mma_commit(&bar1[t & 1]);
         mma_commit(&p_free[t & 3]);
+        }
+        __syncwarp();
       }
       PL_REPORT("I1")
     }
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
-    if (lane == 0) {
+    {
       const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::N2);   // A2_hi x [W2_hi; W2_lo]
       const uint32_t idesc_lo = make_idesc_tf32(C::M, C::N2);       // A2_lo x W2_hi
       const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 4));
@@ -317,18 +335,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         tcgen05_fence_after();
         const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
         const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < C::K2 / 8; ks++) {
-          mma_tf32_ts(d2, a2 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_tf32_ts(d2, a2 + C::N1 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          for (int ks = 0; ks < C::K2 / 8; ks++) {
+            mma_tf32_ts(d2, a2 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+            mma_tf32_ts(d2, a2 + C::N1 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          }
+          mma_commit(&bar2[t & 1]);
         }
-        mma_commit(&bar2[t & 1]);
+        __syncwarp();
       }
       PL_REPORT("I2")
     }
   } else if (warp == C::W_I3) {
     // ============================ I3: layer-3 tap-GEMM issuer (A3 in TMEM) =================
-    if (lane == 0) {
+    {
       const uint32_t idesc_hi = make_idesc_tf32(C::M, 2 * C::NT3);
       const uint32_t idesc_lo = make_idesc_tf32(C::M, C::NT3);
       const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::N2 / 4));
@@ -339,40 +360,53 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         tcgen05_fence_after();
         const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
         const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < C::N2 / 8; ks++) {
-          mma_tf32_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_tf32_ts(d3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          for (int ks = 0; ks < C::N2 / 8; ks++) {
+            mma_tf32_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+            mma_tf32_ts(d3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          }
+          mma_commit(&bar3[t & 1]);
         }
-        mma_commit(&bar3[t & 1]);
+        __syncwarp();
       }
       PL_REPORT("I3")
     }
-  } else if (warp < C::W_E2) {
+  } else if (warp < C::W_E1 + C::N_E1) {
     // ============================ E1: A2 = split(relu(D1 + b1)), in place ==================
+    // warp w works on TMEM lane quarter w&3 (the quarter a warp may access) and on channels
+    // E1_CH*(w>>2) .. +E1_CH-1, 16 at a time.  Measured (probe/tmem_bw_probe.cu, and A/B runs of
+    // this kernel): a tcgen05.ld/st round trip is ~125/~100 cycles, but TMEM traffic of the
+    // epilogue warps stalls the MMA pipe (the two add up), so neither 8 E1 warps (1.65 ms) nor
+    // fetching 32 channels ahead (1.53 ms) beats this plain loop (1.49 ms on C3).
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int ch0 = (warp >> 2) * C::E1_CH;
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
       tcgen05_fence_after();
-      const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
+#ifdef EXP_NO_E1
+      if (b < 0)
+#endif
 #pragma unroll 1
-      for (int g = 0; g < 4; g++) {
+      for (int c16 = 0; c16 < C::E1_CH; c16 += 16) {
+        const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1) + ch0 + c16;
         float va[16], vb[16];
-        tmem_ld16_nowait(d1 + g * 16, va);              // A_hi.W_hi + A_lo.W_hi
-        tmem_ld16_nowait(d1 + C::N1 + g * 16, vb);      // A_hi.W_lo
+        tmem_ld16_nowait(d1, va);                       // A_hi.W_hi + A_lo.W_hi
+        tmem_ld16_nowait(d1 + C::N1, vb);               // A_hi.W_lo
         tmem_ld_wait();
 #pragma unroll
         for (int h8 = 0; h8 < 2; h8++) {
           float hi[8], lo[8];
-          const float4 ba = *reinterpret_cast<const float4*>(sB1 + g * 16 + h8 * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(sB1 + g * 16 + h8 * 8 + 4);
+          const float* bp = sB1 + ch0 + c16 + h8 * 8;
+          const float4 ba = *reinterpret_cast<const float4*>(bp);
+          const float4 bb = *reinterpret_cast<const float4*>(bp + 4);
           const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
           for (int j = 0; j < 8; j++)
             split_tf32(fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + bias[j], 0.f), hi[j], lo[j]);
-          tmem_st8(d1 + g * 16 + h8 * 8, hi);
-          tmem_st8(d1 + C::N1 + g * 16 + h8 * 8, lo);
+          tmem_st8(d1 + h8 * 8, hi);
+          tmem_st8(d1 + C::N1 + h8 * 8, lo);
         }
       }
       tmem_st_wait();
@@ -388,6 +422,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       PL_WAIT(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
       tcgen05_fence_after();
       const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
+#ifdef EXP_NO_E2
+      if (b < 0)
+#endif
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         float va[16], vb[16];
@@ -432,11 +469,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       tcgen05_fence_before();
       mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
+#ifdef EXP_NO_E3
+      if (b < 0)
+#endif
 #pragma unroll
       for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j] + w[j];
       PL_WAIT(1, named_bar_sync(C::BAR_E3, 128))               // Q row visible to its neighbours
       float r[C::F3];
+#ifdef EXP_NO_E3
+      if (b < 0) {
+#else
       if (x < C::OW3) {
+#endif
 #pragma unroll
         for (int dy = 0; dy < C::F3; dy++) {
           float s0 = 0.f, s1 = 0.f;

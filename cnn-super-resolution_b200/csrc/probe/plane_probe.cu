@@ -279,10 +279,11 @@ __global__ void __launch_bounds__(128) mma_time_multi_kernel(int n_issuers, int 
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// the MMA mix of one tile of the plane kernel, one issuer warp per layer, no data dependencies:
-// mask bit 0: I1 (11 x [SS N128 + SS N64]), bit 1: I2 (24 TS N32), bit 2: I3 (12 TS N32),
-// bit 3: I1 issues unstacked (33 x SS N64) instead
-__global__ void __launch_bounds__(128) mma_mix_kernel(int mask, int reps, long long* cycles) {
+// the MMA mix of one tile of the plane kernel (22 SS + 16 TS + 8 TS), one issuer warp per layer,
+// accumulation chains as in the kernel, no epilogues / no data dependencies between layers.
+// mask bit 0: I1, bit 1: I2, bit 2: I3;  variant 1: I1 alternates two accumulators (two tiles
+// interleaved) instead of one dependent chain
+__global__ void __launch_bounds__(128) mma_mix_kernel(int mask, int variant, int reps, long long* cycles) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* s = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bar[4];
@@ -299,43 +300,50 @@ __global__ void __launch_bounds__(128) mma_mix_kernel(int mask, int reps, long l
   float* A = s;                     // planes
   float* B = s + 16 * 1024;         // at 64 KB: 128 x 88 x 4 = 45 KB
   float* B2 = s + 30 * 1024;        // at 120 KB
-  long long t0 = clock64();
   if ((tid & 31) == 0 && ((mask >> warp) & 1) && warp < 3) {
     const uint32_t id32 = make_idesc_tf32(M, 32), id64 = make_idesc_tf32(M, 64), id128 = make_idesc_tf32(M, 128);
+    const uint64_t a0 = make_desc_kmajor(A, 0, 16, 128), b0 = make_desc_kmajor(B, 0, 128, 2816);
+    const uint64_t w2 = make_desc_kmajor(B2, 0, 128, 2048), w3 = make_desc_kmajor(B2, 16384, 128, 1024);
+    long long t0 = clock64();
     for (int r = 0; r < reps; r++) {
       if (warp == 0) {
-        if (mask & 8) {
+        const uint32_t d = tmem + 128 * (r & 1);
+        if (variant == 0) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ks++)
-#pragma unroll
-            for (int p = 0; p < 3; p++)
-              mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16 + (p & 1) * 8192, 16, 128),
-                       make_desc_kmajor(B, ks * 256, 128, 2816), id64, (ks | p) > 0);
+          for (int ks = 0; ks < KS; ks++) {
+            mma_tf32(d, a0 + 2 * ks, b0 + 16 * ks, id128, ks > 0);
+            mma_tf32(d, a0 + 512 + 2 * ks, b0 + 16 * ks, id64, 1);
+          }
         } else {
 #pragma unroll
           for (int ks = 0; ks < KS; ks++) {
-            mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16, 16, 128),
-                     make_desc_kmajor(B, ks * 256, 128, 2816), id128, ks > 0);
-            mma_tf32(tmem, make_desc_kmajor(A, (ks % 3) * 2304 + (ks & 7) * 16 + 8192, 16, 128),
-                     make_desc_kmajor(B, ks * 256, 128, 2816), id64, 1);
+            mma_tf32(tmem, a0 + 2 * ks, b0 + 16 * ks, id128, ks > 0);
+            mma_tf32(tmem + 128, a0 + 144 + 2 * ks, b0 + 16 * ks, id128, ks > 0);
+            mma_tf32(tmem, a0 + 512 + 2 * ks, b0 + 16 * ks, id64, 1);
+            mma_tf32(tmem + 128, a0 + 656 + 2 * ks, b0 + 16 * ks, id64, 1);
           }
+          r++;
         }
       } else if (warp == 1) {
+        const uint32_t d = tmem + 256 + 64 * (r & 1), a2 = tmem + 128 * (r & 1);
 #pragma unroll
-        for (int i = 0; i < 24; i++)
-          mma_tf32_ts(tmem + 384, tmem + 256 + (i / 3) * 8, make_desc_kmajor(B2, (i / 3) * 256, 128, 2048), id32, i > 0);
+        for (int ks = 0; ks < 8; ks++) {
+          mma_tf32_ts(d, a2 + ks * 8, w2 + 16 * ks, id64, ks > 0);
+          mma_tf32_ts(d, a2 + 64 + ks * 8, w2 + 16 * ks, id32, 1);
+        }
       } else {
+        const uint32_t d = tmem + 384 + 64 * (r & 1), a3 = tmem + 256 + 64 * (r & 1);
 #pragma unroll
-        for (int i = 0; i < 12; i++)
-          mma_tf32_ts(tmem + 416, tmem + 448 + (i / 3) * 8, make_desc_kmajor(B2, 8192 + (i / 3) * 256, 128, 1024), id32, i > 0);
+        for (int ks = 0; ks < 4; ks++) {
+          mma_tf32_ts(d, a3 + ks * 8, w3 + 16 * ks, id64, ks > 0);
+          mma_tf32_ts(d, a3 + 32 + ks * 8, w3 + 16 * ks, id32, 1);
+        }
       }
     }
     mma_commit(&bar[warp]);
     mbar_wait(&bar[warp], 0);
+    cycles[warp] = clock64() - t0;
   }
-  __syncthreads();
-  long long t1 = clock64();
-  if (tid == 0) *cycles = t1 - t0;
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -404,7 +412,7 @@ int main() {
                (double)cy / reps / n_mma[mode]);
       }
   cudaFuncSetAttribute(mma_time_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int ni : {1, 2, 4}) {
+  for (int ni : {1}) {
     mma_time_multi_kernel<<<1, 128, 64 * 1024>>>(ni, 200, dcy);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("MULTI FAIL: %s\n", cudaGetErrorString(e)); return 1; }
@@ -414,14 +422,20 @@ int main() {
            (double)cy / 200, (double)cy / 200 / 24);
   }
   cudaFuncSetAttribute(mma_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  for (int mask : {1, 2, 4, 3, 6, 7, 9, 11, 15}) {
-    mma_mix_kernel<<<1, 128, 160 * 1024>>>(mask, 200, dcy);
-    e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("MIX FAIL: %s\n", cudaGetErrorString(e)); return 1; }
-    long long cy;
-    cudaMemcpy(&cy, dcy, 8, cudaMemcpyDeviceToHost);
-    printf("mix mask %2d (%s%s%s%s): %8.1f cyc/tile\n", mask, mask & 1 ? "I1 " : "", mask & 2 ? "I2 " : "",
-           mask & 4 ? "I3 " : "", mask & 8 ? "unstacked" : "", (double)cy / 200);
+  {
+    long long* d4;
+    cudaMalloc(&d4, 32);
+    for (int variant = 0; variant < 2; variant++)
+      for (int mask : {1, 2, 4, 3, 5, 6, 7}) {
+        cudaMemset(d4, 0, 32);
+        mma_mix_kernel<<<1, 128, 160 * 1024>>>(mask, variant, 200, d4);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("MIX FAIL: %s\n", cudaGetErrorString(e)); return 1; }
+        long long cy[4];
+        cudaMemcpy(cy, d4, 32, cudaMemcpyDeviceToHost);
+        printf("mix variant %d mask %d: per tile  I1 %7.1f  I2 %7.1f  I3 %7.1f\n", variant, mask,
+               cy[0] / 200.0, cy[1] / 200.0, cy[2] / 200.0);
+      }
   }
   return rc;
 }

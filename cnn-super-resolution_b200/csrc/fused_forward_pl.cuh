@@ -51,9 +51,12 @@ struct Cfg {
   static constexpr int PW = 144;                 // plane entries (16 bytes each)
   static constexpr int PF = PW * 4;              // floats per plane
   static constexpr int RQ = 8, RH = 4;           // ring slots: quad planes, H planes
-  static constexpr int W_E1 = 0, N_E1 = 4, W_E2 = 4, W_E3 = 8, W_IM = 12, N_IM = 5, W_I1 = 17,
-                       W_I2 = 18, W_I3 = 19;
-  static constexpr int NT = 20 * 32;
+#ifndef PL_N_E1
+#define PL_N_E1 4
+#endif
+  static constexpr int W_E1 = 0, N_E1 = PL_N_E1, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4,
+                       N_IM = 5, W_I1 = W_IM + N_IM, W_I2 = W_I1 + 1, W_I3 = W_I2 + 1;
+  static constexpr int NT = (W_I3 + 1) * 32;
   static constexpr int E1_CH = N1 / (N_E1 / 4);  // channels per E1 warp
   static constexpr int IM_THREADS = N_IM * 32;
   // shared memory carve-up (floats).  The H ring lies BELOW the quad ring: one K-step pairs a
@@ -95,6 +98,14 @@ __host__ __device__ __forceinline__ int tap_of(int s, int j, int e) {
   return dy * Cfg::F1 + dx;
 }
 
+#ifdef PL_TRACE
+// event timeline of tiles 100..103 of CTA (0,0,0): PL_EV(tile, event id)
+__device__ long long pl_trace[8][16];
+#define PL_EV(t, e) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) >= 100 && (t) < 108 && lane == 0) \
+    pl_trace[(t) - 100][e] = clock64();
+#else
+#define PL_EV(t, e) {}
+#endif
 #ifdef PL_TIMING
 #define PL_T0 long long _tw[4] = {0, 0, 0, 0}; const long long _tstart = clock64();
 #define PL_WAIT(i, ...) { const long long _t = clock64(); __VA_ARGS__; _tw[i] += clock64() - _t; }
@@ -271,6 +282,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       ql0 = ql1; ql1 = ql2; ql2 = l[0];
       fence_proxy_async();
       mbar_arrive(&p_full[b & 3]);
+      if (warp == C::W_IM) PL_EV(b, 12)
 #pragma unroll
       for (int e = 0; e < 4; e++) v[e] = nv[e];
     }
@@ -299,6 +311,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * PB;
         const uint32_t s0 = (uint32_t)(t & (C::RQ - 1)) * PB;
         const uint32_t s4 = (uint32_t)((t + 4) & (C::RQ - 1)) * PB;
+        PL_EV(t, 0)
         if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < C::KS1; s++) {
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         mma_commit(&p_free[t & 3]);
         }
         __syncwarp();
+        PL_EV(t, 1)
       }
       PL_REPORT("I1")
     }
@@ -335,6 +349,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         tcgen05_fence_after();
         const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
         const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+        PL_EV(t, 4)
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::K2 / 8; ks++) {
@@ -344,6 +359,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
           mma_commit(&bar2[t & 1]);
         }
         __syncwarp();
+        PL_EV(t, 5)
       }
       PL_REPORT("I2")
     }
@@ -360,6 +376,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         tcgen05_fence_after();
         const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
         const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+        PL_EV(t, 8)
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < C::N2 / 8; ks++) {
@@ -369,6 +386,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
           mma_commit(&bar3[t & 1]);
         }
         __syncwarp();
+        PL_EV(t, 9)
       }
       PL_REPORT("I3")
     }
@@ -377,13 +395,15 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     // warp w works on TMEM lane quarter w&3 (the quarter a warp may access) and on channels
     // E1_CH*(w>>2) .. +E1_CH-1, 16 at a time.  Measured (probe/tmem_bw_probe.cu, and A/B runs of
     // this kernel): a tcgen05.ld/st round trip is ~125/~100 cycles, but TMEM traffic of the
-    // epilogue warps stalls the MMA pipe (the two add up), so neither 8 E1 warps (1.65 ms) nor
-    // fetching 32 channels ahead (1.53 ms) beats this plain loop (1.49 ms on C3).
+    // epilogue warps disturbs the MMA stream, so neither 8 E1 warps (1.65 ms), nor fetching 32
+    // channels ahead (1.53 ms), nor a software-pipelined chunk loop (1.56 ms) beats this plain
+    // loop (1.49 ms on C3).
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int ch0 = (warp >> 2) * C::E1_CH;
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
+      if (warp == 0) PL_EV(b, 2)
       tcgen05_fence_after();
 #ifdef EXP_NO_E1
       if (b < 0)
@@ -412,6 +432,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a2_full[b & 1]);
+      if (warp == 0) PL_EV(b, 3)
     }
     PL_REPORT("E1")
   } else if (warp < C::W_E3) {
@@ -420,6 +441,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
+      if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
       const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
 #ifdef EXP_NO_E2
@@ -445,6 +467,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a3_full[b & 1]);
+      if (warp == C::W_E2) PL_EV(b, 7)
     }
     PL_REPORT("E2")
   } else if (warp < C::W_IM) {
@@ -458,6 +481,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-3(b) done
+      if (warp == C::W_E3) PL_EV(b, 10)
       tcgen05_fence_after();
       const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
       float v[32], w[32];
@@ -503,6 +527,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       acc3 = r[0];
       if (b >= C::F3 - 1 && live)
         dst[(size_t)(R0 + b - (C::F3 - 1)) * a.w3 + X0 + x] = done + b3;
+      if (warp == C::W_E3) PL_EV(b, 11)
     }
     PL_REPORT("E3")
   }
@@ -510,6 +535,17 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+#ifdef PL_TRACE
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles > 108) {
+    const long long t0 = pl_trace[0][12];
+    for (int t = 0; t < 8; t++)
+      printf("tile %d: IM %6lld | I1 %6lld..%6lld | E1 %6lld..%6lld | I2 %6lld..%6lld | E2 %6lld..%6lld | I3 %6lld..%6lld | E3 %6lld..%6lld\n",
+             100 + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
+             pl_trace[t][3] - t0, pl_trace[t][4] - t0, pl_trace[t][5] - t0, pl_trace[t][6] - t0,
+             pl_trace[t][7] - t0, pl_trace[t][8] - t0, pl_trace[t][9] - t0, pl_trace[t][10] - t0,
+             pl_trace[t][11] - t0);
+  }
+#endif
 }
 
 inline int configure() {

@@ -26,6 +26,13 @@ __device__ __forceinline__ void ld_x<32>(uint32_t taddr, uint32_t* r) {
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr));
 }
+// 16x256b.x4: a warp reads 16 lanes x (4 x 256 bits) = 16 registers per thread
+__device__ __forceinline__ void ld_16x256_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void st_x8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
                "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(512) tmem_bw_kernel(int mode, int n_warps, int
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int stop;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid & 31;
-  for (int i = tid; i < 64 * 1024 / 4; i += 512) s[i] = 0.f;
+  for (int i = tid; i < 100 * 1024 / 4; i += 512) s[i] = 0.f;
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) { mbar_init(&bar, 1); stop = 0; }
   fence_proxy_async();
@@ -58,7 +65,11 @@ __global__ void __launch_bounds__(512) tmem_bw_kernel(int mode, int n_warps, int
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
   uint32_t acc = 0;
-  if (warp < n_warps) {
+  if (n_warps == 0 && warp == 0) {
+    long long t0 = clock64();
+    while (clock64() - t0 < 400000) {}
+    if (lane == 0) { out[0] = clock64() - t0; stop = 1; }
+  } else if (warp < n_warps) {
     const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64;
     uint32_t r[32];
     for (int i = 0; i < 32; i++) r[i] = tid + i;
@@ -69,25 +80,28 @@ __global__ void __launch_bounds__(512) tmem_bw_kernel(int mode, int n_warps, int
       else if (mode == 2) { st_x8(base, r); st_x8(base + 8, r + 8); st_x8(base + 16, r + 16); st_x8(base + 24, r + 24);
                             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
       else if (mode == 3) { st_x32(base, r); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-      else { ld_x<32>(base, r); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      else if (mode == 4) { ld_x<32>(base, r); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
              st_x32(base + 32, r); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+      else { ld_16x256_x4(base, r); ld_16x256_x4(base + ((uint32_t)16 << 16), r + 16);
+             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
       acc += r[0] ^ r[7] ^ r[16] ^ r[31];
     }
     long long t1 = clock64();
     if (lane == 0) out[warp] = t1 - t0;
     if (warp == 0 && lane == 0) stop = 1;
-  } else if (warp == 15 && mma) {
+  } else if (warp >= 14 && mma) {
+    // two issuers of SS N=128 MMAs (pipe-bound at ~65 cycles per MMA when undisturbed)
     if (lane == 0) {
-      const uint32_t id64 = make_idesc_tf32(128, 64);
-      const uint64_t bd = make_desc_kmajor(s, 0, 128, 2048);
+      const uint32_t id128 = make_idesc_tf32(128, 128);
+      const uint64_t ad = make_desc_kmajor(s, 0, 16, 128), bd = make_desc_kmajor(s, 16384, 128, 2816);
+      const uint32_t d = tmem + 256 + 128 * (warp - 14);
       long long n = 0;
       while (!stop) {
-        for (int i = 0; i < 8; i++) mma_tf32_ts(tmem + 448, tmem + 384 + i * 8, bd + 16 * i, id64, 1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) mma_tf32(d, ad + 2 * i, bd + 16 * i, id128, 1);
         n += 8;
-        mma_commit(&bar);
-        mbar_wait(&bar, (uint32_t)((n / 8 - 1) & 1));
       }
-      out[15] = n;
+      out[warp] = n;
     }
   }
   if (acc == 0x12345) sink[tid] = acc;
@@ -101,24 +115,24 @@ int main() {
   uint32_t* sink;
   cudaMalloc(&d, 16 * 8);
   cudaMalloc(&sink, 512 * 4);
-  cudaFuncSetAttribute(tmem_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  const char* names[5] = {"ld 2 x x16", "ld x32", "st 4 x x8", "st x32", "ld x32 + st x32"};
+  cudaFuncSetAttribute(tmem_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const char* names[6] = {"ld 2 x x16", "ld x32", "st 4 x x8", "st x32", "ld x32 + st x32", "ld 2 x 16x256b.x4"};
   const int reps = 2000;
-  for (int mma = 0; mma < 2; mma++)
-    for (int mode = 0; mode < 5; mode++)
-      for (int nw : {1, 4, 8}) {
+  for (int mma = 1; mma < 2; mma++)
+    for (int mode = 0; mode < 6; mode++)
+      for (int nw : {0, 4, 8}) {
         cudaMemset(d, 0, 128);
-        tmem_bw_kernel<<<1, 512, 64 * 1024>>>(mode, nw, mma, reps, d, sink);
+        tmem_bw_kernel<<<1, 512, 100 * 1024>>>(mode, nw, mma, reps, d, sink);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("FAIL %s\n", cudaGetErrorString(e)); return 1; }
         long long h[16];
         cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost);
         long long mx = 0;
-        for (int i = 0; i < nw; i++) mx = h[i] > mx ? h[i] : mx;
+        for (int i = 0; i < (nw ? nw : 1); i++) mx = h[i] > mx ? h[i] : mx;
         const double bytes = (double)reps * nw * 32 * 32 * 4 * (mode == 4 ? 2 : 1);
         printf("%s %-16s %d warps: %7.1f cyc per 32-col access/warp, %6.1f B/cyc/SM%s\n", mma ? "with MMA" : "no MMA  ",
                names[mode], nw, (double)mx / reps, bytes / mx, mma ? "" : "");
-        if (mma) printf("      (%lld MMAs issued meanwhile = %.1f cyc/MMA)\n", h[15], h[15] ? (double)mx / h[15] : 0.0);
+        if (mma) printf("      (%lld MMAs issued meanwhile = %.1f cyc/MMA of the pipe)\n", h[14] + h[15], (h[14] + h[15]) ? (double)mx / (h[14] + h[15]) : 0.0);
       }
   return 0;
 }

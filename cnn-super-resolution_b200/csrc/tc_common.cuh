@@ -170,17 +170,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+// The suspend-time hint lets the hardware park the waiting thread until the phase completes
+// (or the hint expires) instead of returning early and spinning: the fused kernels keep ~15
+// warps waiting per SM, and their retry loops take issue slots from the single threads that
+// issue the MMAs.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 

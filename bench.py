@@ -41,10 +41,10 @@ LR = np.array([1e-4, 1e-4, 1e-5], np.float32)   # example_config.json:8-10
 FWD_FLOP_C3 = 2 * ((IMG - 8) ** 2 * 81 * 64 + (IMG - 8) ** 2 * 64 * 32 + (IMG - 12) ** 2 * 25 * 32)
 FUSED_BYTES_C3 = 4 * (IMG * IMG + (IMG - PAD) ** 2)
 TRAIN_FLOP_PER_PATCH = 23.05e6
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused_tc launch on C3 (ncu --set full,
-# profiles/r1_fused_tc_ncu_summary.txt): 67.2 MB read (the input, once) + 29.5 MB written back
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused launch on C3 (ncu --set full,
+# profiles/r1k_fused_pl_ncu_summary.txt): 67.7 MB read (the input, once) + 28.6 MB written back
 # during the launch (the rest of the 66.7 MB output is still dirty in the 126 MB L2 at exit)
-TRAFFIC_NCU_BYTES = 96.7e6
+TRAFFIC_NCU_BYTES = 96.2e6
 
 
 def peaks():
@@ -332,12 +332,12 @@ def run_ours(args, rank, world, local_rank):
     use_tc = fused and os.environ.get("SRCNN_FUSED_IMPL", "tc") != "simt"
     # Dominant kernel of the primary workload = the fused forward launch (one per step and
     # rank; its launch duration IS the step time measured above with CUDA events).  It moves
-    # 8 B/pixel, so it is compute-bound: layers 1-2 (90 % of the FLOPs) run on the tensor
-    # cores as 3xTF32 -- three TF32 MMAs per product, each at half the bf16 rate, i.e. the
-    # precision the path needs costs 6x a bf16 MMA -- layer 3 on the FP32 pipe.
+    # 8 B/pixel, so it is compute-bound: all three layers run on the tensor cores as 3xTF32
+    # (layer 3 as a tap GEMM + 25-term gather) -- three TF32 products per FP32 product, each
+    # at half the bf16 rate, i.e. the precision the path needs costs 6x a bf16 MMA.
     if use_tc:
         roofline = {
-            "kernel": "forward_fused_tc_kernel (tcgen05 3xTF32 L1+L2, FP32 SIMT L3)",
+            "kernel": "forward_fused_pl_kernel (tcgen05 3xTF32 on all three layers, plane operands)",
             "bound": "tensor", "achieved": achieved_tf, "peak": bf16_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / bf16_peak, "traffic": TRAFFIC_NCU_BYTES * frac_img,
             "peak_kind": peak_kind + " dense bf16 (MEASURED_PEAKS.json)",

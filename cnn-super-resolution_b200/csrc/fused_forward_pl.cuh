@@ -149,7 +149,22 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Args a, int rpc) {
+// BATCH = true: the input is a batch of S small samples [S][ph][pw] (training patches).  The
+// kernel then works on the VIRTUAL image [ph][S*pw] made of the samples laid side by side, so
+// that a 128-pixel tile is filled whatever the sample width; columns whose window straddles two
+// samples are computed and dropped (pw-8 of every pw columns are kept: 76 % for 33x33).
+// Optionally the n1- and n2-channel maps are written to HBM ([S][h1][w1][N1], [S][h2][w2][N2]):
+// that is the forward pass of a training step (ConfigBasedDataPipeline.cpp:165-168), whose
+// activations are needed again by backpropagate().
+struct BatchExt {
+  float* out1;   // may be null
+  float* out2;   // may be null
+  int S, pw, ph;
+};
+
+template <bool BATCH>
+__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Args a, int rpc,
+                                                                      BatchExt bx) {
   using C = Cfg;
   using namespace tc;
   extern __shared__ __align__(128) float smem[];
@@ -169,8 +184,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int X0 = blockIdx.x * C::OW3;
   const int R0 = blockIdx.y * rpc;
-  const float* img = a.in + (size_t)blockIdx.z * a.w * a.h;
-  float* dst = a.out + (size_t)blockIdx.z * a.w3 * a.h3;
+  const float* img = BATCH ? a.in : a.in + (size_t)blockIdx.z * a.w * a.h;
+  float* dst = BATCH ? a.out : a.out + (size_t)blockIdx.z * a.w3 * a.h3;
 
   // ---- stage parameters (all threads): B operands [n][k] canonical, rows 0..N-1 the TF32 hi
   // parts, rows N..2N-1 the lo parts (one N=2N MMA evaluates A_hi.W_hi and A_hi.W_lo) ----------
@@ -236,8 +251,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     float* sHl = smem + C::oHl + c * 4;
     float* sQh = smem + C::oQh + c * 4;
     float* sQl = smem + C::oQl + c * 4;
+    // BATCH: virtual column gx+e -> (sample, column) once; a row is then one add away
+    long long boff[4];
+    if (BATCH) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int vx = gx + e;
+        const int smp = vx / bx.pw;
+        boff[e] = (active && vx < a.w) ? (long long)smp * bx.pw * bx.ph + (vx - smp * bx.pw) : -1;
+      }
+    }
     auto ld = [&](int r, int e) -> float {
       const int gy = R0 + r;
+      if (BATCH) return (boff[e] >= 0 && gy < a.h) ? __ldg(img + boff[e] + (long long)gy * bx.pw) : 0.f;
       return (active && gy < a.h && gx + e < a.w) ? __ldg(img + (size_t)gy * a.w + gx + e) : 0.f;
     };
     float qh0 = 0.f, qh1 = 0.f, qh2 = 0.f, ql0 = 0.f, ql1 = 0.f, ql2 = 0.f;
@@ -400,6 +426,15 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     // loop (1.49 ms on C3).
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int ch0 = (warp >> 2) * C::E1_CH;
+    // BATCH: this thread's pixel of the n1-channel map (row 0), or null when not kept
+    float* o1 = nullptr;
+    if (BATCH && bx.out1) {
+      const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w1 = bx.pw - (C::F1 - 1), h1 = bx.ph - (C::F1 - 1);
+      if (m < C::OW3 && vx < a.w && px < w1)
+        o1 = bx.out1 + (((size_t)smp * h1 + R0) * w1 + px) * C::N1 + ch0;
+    }
+    const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
@@ -422,11 +457,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
           const float4 ba = *reinterpret_cast<const float4*>(bp);
           const float4 bb = *reinterpret_cast<const float4*>(bp + 4);
           const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float act[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            split_tf32(fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + bias[j], 0.f), hi[j], lo[j]);
+          for (int j = 0; j < 8; j++) {
+            act[j] = fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + bias[j], 0.f);
+            split_tf32(act[j], hi[j], lo[j]);
+          }
           tmem_st8(d1 + h8 * 8, hi);
           tmem_st8(d1 + C::N1 + h8 * 8, lo);
+          if (BATCH && o1) {
+            float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + c16 + h8 * 8);
+            q[0] = make_float4(act[0], act[1], act[2], act[3]);
+            q[1] = make_float4(act[4], act[5], act[6], act[7]);
+          }
         }
       }
       tmem_st_wait();
@@ -438,6 +481,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   } else if (warp < C::W_E3) {
     // ============================ E2: A3 = split(relu(D2 + b2)), in place ==================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* o2 = nullptr;
+    if (BATCH && bx.out2) {
+      const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w2 = bx.pw - (C::F1 - 1), h2 = bx.ph - (C::F1 - 1);
+      if (m < C::OW3 && vx < a.w && px < w2)
+        o2 = bx.out2 + (((size_t)smp * h2 + R0) * w2 + px) * C::N2;
+    }
+    const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
@@ -456,12 +507,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
 #pragma unroll
         for (int h8 = 0; h8 < 2; h8++) {
           float hi[8], lo[8];
+          float act[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            split_tf32(fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + sB2[g * 16 + h8 * 8 + j], 0.f),
-                       hi[j], lo[j]);
+          for (int j = 0; j < 8; j++) {
+            act[j] = fmaxf((va[h8 * 8 + j] + vb[h8 * 8 + j]) + sB2[g * 16 + h8 * 8 + j], 0.f);
+            split_tf32(act[j], hi[j], lo[j]);
+          }
           tmem_st8(d2 + g * 16 + h8 * 8, hi);
           tmem_st8(d2 + C::N2 + g * 16 + h8 * 8, lo);
+          if (BATCH && o2) {
+            float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16 + h8 * 8);
+            q[0] = make_float4(act[0], act[1], act[2], act[3]);
+            q[1] = make_float4(act[4], act[5], act[6], act[7]);
+          }
         }
       }
       tmem_st_wait();
@@ -476,7 +534,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
     // miss out2 rows live in its registers (acc0 = oldest).
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int x = (warp & 3) * 32 + lane;
-    const bool live = x < C::OW3 && X0 + x < a.w3;
+    bool live = x < C::OW3 && X0 + x < a.w3;
+    size_t o3 = (size_t)R0 * a.w3 + X0 + x;   // output row 0 of this thread's column
+    size_t o3_row = (size_t)a.w3;
+    if (BATCH) {
+      const int vx = X0 + x, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w3 = bx.pw - (C::F1 + C::F3 - 2), h3 = bx.ph - (C::F1 + C::F3 - 2);
+      live = live && px < w3;
+      o3 = ((size_t)smp * h3 + R0) * w3 + px;
+      o3_row = (size_t)w3;
+    }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
@@ -526,7 +593,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       acc2 = acc3 + r[1];
       acc3 = r[0];
       if (b >= C::F3 - 1 && live)
-        dst[(size_t)(R0 + b - (C::F3 - 1)) * a.w3 + X0 + x] = done + b3;
+        dst[o3 + (size_t)(b - (C::F3 - 1)) * o3_row] = done + b3;
       if (warp == C::W_E3) PL_EV(b, 11)
     }
     PL_REPORT("E3")
@@ -549,7 +616,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
 }
 
 inline int configure() {
-  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_pl_kernel,
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_pl_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_pl_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::SMEM_BYTES));
   return SRCNN_OK;
@@ -581,7 +651,21 @@ inline int rows_per_cta(int w3, int h3, int S, int sm_count) {
 inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S) {
   const int rpc = rows_per_cta(a.w3, a.h3, S, ctx->sm_count > 0 ? ctx->sm_count : 148);
   dim3 grid((a.w3 + Cfg::OW3 - 1) / Cfg::OW3, (a.h3 + rpc - 1) / rpc, S);
-  forward_fused_pl_kernel<<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc);
+  forward_fused_pl_kernel<false><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc,
+                                                                                 BatchExt{});
+  return SRCNN_OK;
+}
+
+// a batch of S samples of pw x ph pixels as one virtual image; out1/out2 may be null
+inline int launch_batch(srcnn_ctx* ctx, const fused::Args& a, int S, float* out1, float* out2) {
+  fused::Args v = a;
+  const int pad = Cfg::F1 + Cfg::F3 - 2;
+  v.w = S * a.w;
+  v.w3 = S * a.w - pad;
+  const int rpc = rows_per_cta(v.w3, v.h3, 1, ctx->sm_count > 0 ? ctx->sm_count : 148);
+  dim3 grid((v.w3 + Cfg::OW3 - 1) / Cfg::OW3, (v.h3 + rpc - 1) / rpc, 1);
+  forward_fused_pl_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
+      v, rpc, BatchExt{out1, out2, S, a.w, a.h});
   return SRCNN_OK;
 }
 

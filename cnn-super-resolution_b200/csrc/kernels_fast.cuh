@@ -104,10 +104,31 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
   if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
+    // batches of small samples (validation patches) go through the virtual-image variant
+    if (ctx->fused_impl == 3 && S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30))
+      return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
     if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
     return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
   }
   return fused::launch(ctx, n1, n2, a, S);
+}
+
+inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
+  return ctx->fused_impl == 3 && fused_pl::supported(n1, n2, f1, f2, f3);
+}
+
+// forward pass of a training chunk: all three layers in one launch, n1/n2-channel maps kept.
+// returns 1 when it launched, 0 when there is no instantiation for the shape
+inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
+                               const float* in, float* out1, float* out2, float* out3,
+                               const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* w3, const float* b3, int in_w, int in_h, int S) {
+  if (ctx->fused_impl != 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
+  if ((long long)S * in_w >= (1LL << 30)) return 0;
+  fused::Args a{in, out3, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
+                in_h - (f1 + f2 + f3 - 3)};
+  const int rc = fused_pl::launch_batch(ctx, a, S, out1, out2);
+  return rc == SRCNN_OK ? 1 : rc;
 }
 
 }  // namespace fast

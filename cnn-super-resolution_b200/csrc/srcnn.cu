@@ -681,6 +681,31 @@ int carve(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem work, int w, int h, in
 // wrapped handles are always the last six table entries: drop them again so a long
 // training run does not grow the table
 void uncarve(srcnn_ctx* ctx) { ctx->allocs.resize(ctx->allocs.size() - 6); }
+
+// forward of a training chunk through the fused tensor-core kernel, activations kept
+// (replaces the three execute_layer calls of ConfigBasedDataPipeline.cpp:200-241)
+int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, const Work& wk,
+                              int w, int h, int S, int* launched) {
+  const Dims d = net_dims(net, w, h);
+  const float *pin, *w1, *b1, *w2, *b2, *w3, *b3;
+  float *o1, *o2, *o3;
+  SRCNN_TRY(resolve(ctx, in, sizeof(float) * (size_t)S * w * h, &pin, "input luma"));
+  SRCNN_TRY(resolve(ctx, wk.out1, sizeof(float) * (size_t)S * d.w1 * d.h1 * net->n1, &o1, "out1"));
+  SRCNN_TRY(resolve(ctx, wk.out2, sizeof(float) * (size_t)S * d.w2 * d.h2 * net->n2, &o2, "out2"));
+  SRCNN_TRY(resolve(ctx, wk.out3, sizeof(float) * (size_t)S * d.w3 * d.h3, &o3, "out3"));
+  SRCNN_TRY(resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1"));
+  SRCNN_TRY(resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1"));
+  SRCNN_TRY(resolve(ctx, net->w[1], sizeof(float) * (size_t)net->f2 * net->f2 * net->n1 * net->n2, &w2, "w2"));
+  SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
+  SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
+  SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
+  LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+  const int rc = fast::forward_train_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin,
+                                           o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S);
+  if (rc < 0) return rc;
+  *launched = rc;
+  return rc ? check_launch("forward_train_fused") : SRCNN_OK;
+}
 }  // namespace
 
 int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
@@ -693,9 +718,14 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
   SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
   int rc = SRCNN_OK;
   // forward, keeping the activations (ConfigBasedDataPipeline.cpp:200-241)
-  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, in, wk.out1, net->w[0], net->b[0], 1, net->n1, net->f1, 0, w, h, S);
-  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out1, wk.out2, net->w[1], net->b[1], net->n1, net->n2, net->f2, 0, d.w1, d.h1, S);
-  if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
+  int fused_fwd = 0;
+  if (fast::fused_train_supported(ctx, net->n1, net->n2, net->f1, net->f2, net->f3))
+    rc = forward_train_fused_entry(ctx, net, in, wk, w, h, S, &fused_fwd);
+  if (!fused_fwd) {
+    if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, in, wk.out1, net->w[0], net->b[0], 1, net->n1, net->f1, 0, w, h, S);
+    if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out1, wk.out2, net->w[1], net->b[1], net->n1, net->n2, net->f2, 0, d.w1, d.h1, S);
+    if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
+  }
   // deltas (ConfigBasedDataPipeline.cpp:258-285)
   if (rc == SRCNN_OK) rc = srcnn_last_layer_delta(ctx, gt, wk.out3, wk.d3, w, h, d.w3, d.h3, S);
   if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d3, wk.out2, wk.d2, net->w[2], net->n2, net->f3, 1, d.w2, d.h2, S);

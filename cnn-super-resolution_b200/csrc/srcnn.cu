@@ -682,6 +682,29 @@ int carve(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem work, int w, int h, in
 // training run does not grow the table
 void uncarve(srcnn_ctx* ctx) { ctx->allocs.resize(ctx->allocs.size() - 6); }
 
+// last_layer_delta + deltas(layer 2) + backpropagate(layer 3) in one launch (+ the reduce)
+int backward3_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem gt, const Work& wk,
+                          int w, int h, int S, int* launched) {
+  const Dims d = net_dims(net, w, h);
+  const float *pgt, *o3, *o2, *w3;
+  float *pd3, *pd2, *gw, *gb;
+  SRCNN_TRY(resolve(ctx, gt, sizeof(float) * (size_t)S * w * h, &pgt, "ground truth"));
+  SRCNN_TRY(resolve(ctx, wk.out3, sizeof(float) * (size_t)S * d.w3 * d.h3, &o3, "out3"));
+  SRCNN_TRY(resolve(ctx, wk.out2, sizeof(float) * (size_t)S * d.w2 * d.h2 * net->n2, &o2, "out2"));
+  SRCNN_TRY(resolve(ctx, wk.d3, sizeof(float) * (size_t)S * d.w3 * d.h3, &pd3, "d3"));
+  SRCNN_TRY(resolve(ctx, wk.d2, sizeof(float) * (size_t)S * d.w2 * d.h2 * net->n2, &pd2, "d2"));
+  SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
+  SRCNN_TRY(resolve(ctx, net->grad_w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &gw, "grad_w3"));
+  SRCNN_TRY(resolve(ctx, net->grad_b[2], sizeof(float), &gb, "grad_b3"));
+  LaunchScope scope(ctx, SRCNN_K_BACKPROPAGATE, 2);
+  const int rc = train::bwd3_fused(ctx, pgt, o3, o2, w3, pd3, pd2, gw, gb, net->n2, net->f3, w, h,
+                                   d.w3, d.h3, S);
+  if (rc < 0) return rc;
+  *launched = rc;
+  if (!rc) scope.n_launches = 0;
+  return rc ? check_launch("bwd3_fused") : SRCNN_OK;
+}
+
 // forward of a training chunk through the fused tensor-core kernel, activations kept
 // (replaces the three execute_layer calls of ConfigBasedDataPipeline.cpp:200-241)
 int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, const Work& wk,
@@ -727,11 +750,17 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
     if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
   }
   // deltas (ConfigBasedDataPipeline.cpp:258-285)
-  if (rc == SRCNN_OK) rc = srcnn_last_layer_delta(ctx, gt, wk.out3, wk.d3, w, h, d.w3, d.h3, S);
-  if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d3, wk.out2, wk.d2, net->w[2], net->n2, net->f3, 1, d.w2, d.h2, S);
+  // last-layer delta, layer-2 deltas and layer-3 gradients share one pass over out2 when the
+  // samples are patch-sized (ConfigBasedDataPipeline.cpp:258-270, 287-295)
+  int fused_b3 = 0;
+  if (rc == SRCNN_OK) rc = backward3_fused_entry(ctx, net, gt, wk, w, h, S, &fused_b3);
+  if (!fused_b3) {
+    if (rc == SRCNN_OK) rc = srcnn_last_layer_delta(ctx, gt, wk.out3, wk.d3, w, h, d.w3, d.h3, S);
+    if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d3, wk.out2, wk.d2, net->w[2], net->n2, net->f3, 1, d.w2, d.h2, S);
+  }
   if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d2, wk.out1, wk.d1, net->w[1], net->n1, net->f2, net->n2, d.w1, d.h1, S);
   // gradients (ConfigBasedDataPipeline.cpp:287-320)
-  if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
+  if (!fused_b3 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d2, wk.out1, net->grad_w[1], net->grad_b[1], net->n2, net->n1, net->f2, d.w2, d.h2, S);
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
   uncarve(ctx);

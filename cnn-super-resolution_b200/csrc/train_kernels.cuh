@@ -257,6 +257,130 @@ __global__ void __launch_bounds__(NT) n1_gradw_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) dst[F * F * k] = gb;
 }
 
+// ------------------------------------------------------------------ fused backward of layer 3 --
+// One pass over out2 for: last_layer_delta (src/kernel/last_layer_delta.cl:14-50, quirk Q2 kept),
+// the deltas of layer 2 (src/kernel/layer_deltas.cl:42-127 with n_next = 1) and the weight/bias
+// gradient of layer 3 (src/kernel/backpropagate.cl:56-114 with n = 1).  All three consume the
+// same 5x5 window of d3 around an out2 pixel:
+//     d2[j][i][c]       = [out2[j][i][c] > 0] * sum_{dy,dx} W3[dy][dx][c] * d3[j-dy][i-dx]
+//     gW3[dy][dx][c]   += out2[j][i][c] * d3[j-dy][i-dx]
+// A CTA (5 warps) takes one sample at a time: d3 is computed into a zero-padded shared-memory
+// map, warp w walks the out2 rows w, w+5, .. with lane = channel; the window slides through
+// registers (5 LDS per pixel for 50 FFMA).  Weight-gradient sums stay in registers across the
+// samples of a CTA (fixed order) and leave as ONE partial vector per CTA -> deterministic.
+constexpr int B3_WARPS = 5, B3_NT = 32 * B3_WARPS, B3_F = 5;
+template <int CPL>
+__global__ void __launch_bounds__(B3_NT) bwd3_fused_kernel(
+    const float* __restrict__ gt, const float* __restrict__ out3, const float* __restrict__ out2,
+    const float* __restrict__ W3, float* __restrict__ d3, float* __restrict__ d2,
+    float* __restrict__ partial, int k, int gt_w, int gt_h, int w3, int h3, int S) {
+  constexpr int F = B3_F, T = F * F;
+  extern __shared__ float b3_smem[];
+  const int ow = w3 + F - 1, oh = h3 + F - 1;       // out2 / d2 extent
+  const int pw = w3 + 2 * (F - 1), ph = h3 + 2 * (F - 1);
+  float* P = b3_smem;                               // [ph][pw] zero-padded d3
+  float* red = b3_smem + ((pw * ph + 3) & ~3);      // [B3_WARPS][T * k] at the end
+  __shared__ float gb_part[B3_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pad = (gt_w - w3) / 2;
+  float wt[CPL][T], acc[CPL][T];
+#pragma unroll
+  for (int j = 0; j < CPL; j++) {
+    const int c = lane + 32 * j;
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      wt[j][t] = c < k ? __ldg(W3 + t * k + c) : 0.f;
+      acc[j][t] = 0.f;
+    }
+  }
+  float gb = 0.f;   // thread 0 only
+  for (int i = threadIdx.x; i < pw * ph; i += B3_NT) P[i] = 0.f;
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    __syncthreads();   // previous sample's readers are done with P
+    // ---- d3 of this sample -> P (interior), global d3, bias-gradient sum
+    float part = 0.f;
+    for (int i = threadIdx.x; i < w3 * h3; i += B3_NT) {
+      const int y = i / w3, x = i - y * w3;
+      const float o = __ldg(out3 + (long long)s * w3 * h3 + i);
+      const float t = __ldg(gt + ((long long)s * gt_h + y + pad) * gt_w + pad + x);
+      const float dv = o > 0.f ? o - t : 0.f;
+      P[(y + F - 1) * pw + x + F - 1] = dv;
+      d3[(long long)s * w3 * h3 + i] = dv;
+      part += dv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) gb_part[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < B3_WARPS; w++) t += gb_part[w];
+      gb += t;
+    }
+    // ---- out2 rows of this warp
+    const float* o2s = out2 + (long long)s * ow * oh * k;
+    float* d2s = d2 + (long long)s * ow * oh * k;
+    for (int j = warp; j < oh; j += B3_WARPS) {
+      // window rows: d3 row j-dy lives in P row j-dy+F-1; column i-dx+F-1 = i+t, t = F-1-dx
+      const float* prow[F];
+#pragma unroll
+      for (int dy = 0; dy < F; dy++) prow[dy] = P + (j - dy + F - 1) * pw;
+      float win[F][F];   // win[dy][(i + t) % F] = column i+t of row dy, t = 0..F-1
+#pragma unroll
+      for (int dy = 0; dy < F; dy++)
+#pragma unroll
+        for (int t = 0; t < F - 1; t++) win[dy][t] = prow[dy][t];
+      for (int i0 = 0; i0 < ow; i0 += F) {
+#pragma unroll
+        for (int u = 0; u < F; u++) {
+          const int i = i0 + u;
+          if (i < ow) {
+#pragma unroll
+            for (int dy = 0; dy < F; dy++) win[dy][(u + F - 1) % F] = prow[dy][i + F - 1];
+#pragma unroll
+            for (int jc = 0; jc < CPL; jc++) {
+              const int c = lane + 32 * jc;
+              if (c < k) {
+                const long long idx = ((long long)j * ow + i) * k + c;
+                const float v = __ldg(o2s + idx);
+                float dsum = 0.f;
+#pragma unroll
+                for (int dy = 0; dy < F; dy++)
+#pragma unroll
+                  for (int dx = 0; dx < F; dx++) {
+                    const float dv = win[dy][(u + F - 1 - dx) % F];
+                    dsum = fmaf(wt[jc][dy * F + dx], dv, dsum);
+                    acc[jc][dy * F + dx] = fmaf(v, dv, acc[jc][dy * F + dx]);
+                  }
+                d2s[idx] = v > 0.f ? dsum : 0.f;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- one partial per CTA: warps folded in warp order
+  __syncthreads();
+#pragma unroll
+  for (int jc = 0; jc < CPL; jc++) {
+    const int c = lane + 32 * jc;
+    if (c < k)
+#pragma unroll
+      for (int t = 0; t < T; t++) red[(warp * T + t) * k + c] = acc[jc][t];
+  }
+  __syncthreads();
+  float* dst = partial + (long long)blockIdx.x * (T * k + 1);
+  for (int i = threadIdx.x; i < T * k; i += B3_NT) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < B3_WARPS; w++) t += red[w * T * k + i];
+    dst[i] = t;
+  }
+  if (threadIdx.x == 0) dst[T * k] = gb;
+}
+
 // ------------------------------------------------------------------ gW of f=1 / k=1 layers ---
 // gW[m][n] += sum_p A[p][m] * d[p][n];  gB[n] += sum_p d[p][n]       (p over all pixels)
 //   MODE 0 (f = 1, layer 2): A[p][m] = in[p][m]                       m < K
@@ -558,6 +682,34 @@ inline int gradw(srcnn_ctx* ctx, const float* d, const float* in, float* grad_w,
   const int total = (Mw + 1) * n;
   partial_reduce_kernel<<<(total + RED_OUT - 1) / RED_OUT, RED_OUT * RED_WARPS, 0, ctx->stream>>>(
       (const float*)ctx->splitk_scratch, grad_w, grad_b, Mw, n, count);
+  return 1;
+}
+
+// fused backward of the last layer (f = 5, n = 1); returns 1 when it launched, 0 when not
+// handled.  d2 / d3 receive the deltas, grad_w3 / grad_b3 are accumulated into.
+inline int bwd3_fused(srcnn_ctx* ctx, const float* gt, const float* out3, const float* out2,
+                      const float* W3, float* d3, float* d2, float* grad_w, float* grad_b, int k,
+                      int f, int gt_w, int gt_h, int w3, int h3, int S) {
+  if (f != B3_F || (k != 16 && k != 32 && k != 64)) return 0;
+  const int pw = w3 + 2 * (f - 1), ph = h3 + 2 * (f - 1);
+  const size_t smem = sizeof(float) * (((size_t)pw * ph + 3) / 4 * 4 + (size_t)B3_WARPS * f * f * k);
+  if (smem > 96 * 1024) return 0;   // image-sized samples: the per-kernel path handles them
+  const int count = (int)std::min<long long>(S, 4LL * ctx->sm_count);
+  const int Mw = f * f * k;
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
+                           sizeof(float) * (size_t)count * (Mw + 1)));
+  float* part = (float*)ctx->splitk_scratch;
+  if (k <= 32) {
+    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd3_fused_kernel<1><<<count, B3_NT, smem, ctx->stream>>>(gt, out3, out2, W3, d3, d2, part, k,
+                                                             gt_w, gt_h, w3, h3, S);
+  } else {
+    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd3_fused_kernel<2><<<count, B3_NT, smem, ctx->stream>>>(gt, out3, out2, W3, d3, d2, part, k,
+                                                             gt_w, gt_h, w3, h3, S);
+  }
+  partial_reduce_kernel<<<(Mw + 1 + RED_OUT - 1) / RED_OUT, RED_OUT * RED_WARPS, 0, ctx->stream>>>(
+      part, grad_w, grad_b, Mw, 1, count);
   return 1;
 }
 

@@ -422,7 +422,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=512, help="patches per training chunk")
+    ap.add_argument("--chunk", type=int, default=2048,
+                    help="patches per training chunk (the reference chunks an epoch in two: "
+                         "src/Main_cl.cpp:93,128-129)")
     ap.add_argument("--ref-rows", type=int, default=128)
     ap.add_argument("--ref-patches", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -120,6 +120,7 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->copy_in) {
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
+    if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
     for (int i = 0; i < 8; i++) {
       cudaEventDestroy(ctx->ev_in[i]);
       cudaEventDestroy(ctx->ev_k[i]);
@@ -582,19 +583,25 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   SRCNN_REQUIRE(fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3),
                 "srcnn_infer_rows_host needs a fused instantiation for %d-%d-%d n1=%d n2=%d",
                 net->f1, net->f2, net->f3, net->n1, net->n2);
-  // The band is cut into sub-bands of whole 128-row CTA strips; upload (copy-in stream),
-  // fused forward (context stream) and download (copy-out stream) of consecutive sub-bands
-  // overlap, so a large image costs ~max(H2D, compute, D2H) instead of their sum.  Every
-  // sub-band is the same valid-convolution problem with a halo, so the result is bit-identical
-  // to a single launch.
+  // The band is cut into sub-bands; upload (copy-in stream), fused forward (two alternating
+  // compute streams, so the tail wave of one sub-band overlaps the head of the next) and
+  // download (copy-out stream) of consecutive sub-bands overlap, so a large image costs
+  // ~max(H2D, compute, D2H) + a short head and tail instead of their sum: the first and the
+  // last sub-band are small because their upload / download is exposed.  Every sub-band is the
+  // same valid-convolution problem with a halo, so the result is bit-identical to a single
+  // launch.
   constexpr int kMaxSub = 8;
+  static const float kShare[6] = {0.08f, 0.19f, 0.23f, 0.23f, 0.19f, 0.08f};
   int n_sub = band_out_h >= 1024 ? 6 : 1;
-  int rows_per = ((band_out_h + n_sub - 1) / n_sub + 127) / 128 * 128;
-  n_sub = (band_out_h + rows_per - 1) / rows_per;
-  if (n_sub > kMaxSub) n_sub = kMaxSub;
+  int sub_r0[kMaxSub + 1] = {0};
+  for (int i = 0, acc = 0; i < n_sub; i++) {
+    acc += n_sub == 1 ? band_out_h : (int)(kShare[i] * band_out_h + 0.5f);
+    sub_r0[i + 1] = i + 1 == n_sub ? band_out_h : std::min(acc, band_out_h);
+  }
   if (n_sub > 1 && !ctx->copy_in) {
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxSub; i++) {
       SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
       SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
@@ -619,8 +626,12 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[0], 0));
-  for (int i = 0; i < n_sub; i++) {
-    const int r0 = i * rows_per, r1 = std::min(band_out_h, r0 + rows_per);   // band-relative
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->compute2, ctx->ev_k[0], 0));
+  cudaStream_t main_stream = ctx->stream;
+  int rc = SRCNN_OK;
+  for (int i = 0; i < n_sub && rc == SRCNN_OK; i++) {
+    const int r0 = sub_r0[i], r1 = sub_r0[i + 1];   // band-relative output rows
+    if (r1 <= r0) continue;
     // input rows [r0 + (i ? halo : 0), r1 + halo): disjoint pieces that tile the band
     const int in0 = r0 + (i ? halo : 0), in1 = r1 + halo;
     SRCNN_CUDA(cudaMemcpyAsync(din + (size_t)in0 * in_w,
@@ -628,23 +639,28 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
                                sizeof(float) * (size_t)(in1 - in0) * in_w, cudaMemcpyHostToDevice,
                                ctx->copy_in));
     SRCNN_CUDA(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
-    SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+    cudaStream_t cs = (i & 1) ? ctx->compute2 : main_stream;
+    SRCNN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_in[i], 0));
     {
       LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
-      SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
-                                    din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2,
-                                    b2, w3, b3, in_w, r1 - r0 + halo, 1));
-      SRCNN_TRY(check_launch("forward_fused"));
+      ctx->stream = cs;   // the launch helpers use the context stream
+      rc = fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
+                               din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2, b2,
+                               w3, b3, in_w, r1 - r0 + halo, 1);
+      ctx->stream = main_stream;
+      if (rc == SRCNN_OK) rc = check_launch("forward_fused");
     }
-    SRCNN_CUDA(cudaEventRecord(ctx->ev_k[i], ctx->stream));
+    if (rc != SRCNN_OK) break;
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_k[i], cs));
     SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
     SRCNN_CUDA(cudaMemcpyAsync(host_out + (size_t)r0 * d.w3, dout + (size_t)r0 * d.w3,
                                sizeof(float) * (size_t)(r1 - r0) * d.w3, cudaMemcpyDeviceToHost,
                                ctx->copy_out));
   }
   SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->compute2));
   SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
-  return SRCNN_OK;
+  return rc;
 }
 
 size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S) {

@@ -81,6 +81,7 @@ inline bool forward_layer(srcnn_ctx* ctx, const float* in, float* out, const flo
 
 inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
                    const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
+  if (train::f1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S)) return true;
   return train::n1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S);
 }
 

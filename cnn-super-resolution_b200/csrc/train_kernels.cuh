@@ -257,6 +257,81 @@ __global__ void __launch_bounds__(NT) n1_gradw_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) dst[F * F * k] = gb;
 }
 
+// ------------------------------------------------------------------ delta below an f=1 layer --
+// target[p][n] = [lo[p][n] > 0] * sum_k W[n][k] * dn[p][k]      (p over all S*oh*ow pixels)
+// reference: src/kernel/layer_deltas.cl:42-127 with f_next = 1 (layer 2 of 9-1-5): a plain
+// [P x K] . [K x N] GEMM with the ReLU mask of the layer's own output as epilogue.
+// CTA = 128 pixels x N outputs, 256 threads, thread tile 8 px x (N/8) outputs; the dn tile is
+// staged transposed ([k][px]) so every inner-loop access is a conflict-free LDS.128.
+template <int N, int K>
+__global__ void __launch_bounds__(256) f1_deltas_kernel(const float* __restrict__ dn,
+                                                        const float* __restrict__ lo,
+                                                        float* __restrict__ target,
+                                                        const float* __restrict__ W, long long P) {
+  constexpr int PX = 128, TN = N / 8, PITCH = PX + 4;
+  __shared__ __align__(16) float sW[K][N];        // sW[k][n] = W[n][k]
+  __shared__ __align__(16) float sD[K][PITCH];    // sD[k][px]
+  const int tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PX;
+  for (int i = tid; i < N * K; i += 256) {
+    const int n = i / K, k = i - n * K;
+    sW[k][n] = __ldg(W + i);
+  }
+  {
+    // lane = pixel (consecutive banks), one 16-byte K-quad per step
+    const int px = tid & (PX - 1), q0 = tid >> 7;
+    const long long p = p0 + px;
+#pragma unroll
+    for (int q = q0; q < K / 4; q += 2) {
+      const float4 v = p < P ? __ldg(reinterpret_cast<const float4*>(dn + p * K) + q)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      sD[4 * q + 0][px] = v.x;
+      sD[4 * q + 1][px] = v.y;
+      sD[4 * q + 2][px] = v.z;
+      sD[4 * q + 3][px] = v.w;
+    }
+  }
+  __syncthreads();
+  // 256 threads = 8 output groups (tx) x 32 pixel groups (ty) of 4 pixels
+  const int tx = tid & 7, ty = tid >> 3;
+  constexpr int TP = PX / 32;              // pixels per thread
+  static_assert(TP == 4 && TN % 4 == 0, "float4 accesses");
+  float acc[TP][TN];
+#pragma unroll
+  for (int i = 0; i < TP; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < K; k++) {
+    float a[TP], b[TN];
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sD[k][ty * TP]);
+#pragma unroll
+    for (int j = 0; j < TN; j += 4)
+      *reinterpret_cast<float4*>(b + j) = *reinterpret_cast<const float4*>(&sW[k][tx * TN + j]);
+#pragma unroll
+    for (int i = 0; i < TP; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < TP; i++) {
+    const long long p = p0 + ty * TP + i;
+    if (p < P) {
+      const long long base = p * N + tx * TN;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 o = __ldg(reinterpret_cast<const float4*>(lo + base + j));
+        float4 r;
+        r.x = o.x > 0.f ? acc[i][j + 0] : 0.f;
+        r.y = o.y > 0.f ? acc[i][j + 1] : 0.f;
+        r.z = o.z > 0.f ? acc[i][j + 2] : 0.f;
+        r.w = o.w > 0.f ? acc[i][j + 3] : 0.f;
+        *reinterpret_cast<float4*>(target + base + j) = r;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fused backward of layer 3 --
 // One pass over out2 for: last_layer_delta (src/kernel/last_layer_delta.cl:14-50, quirk Q2 kept),
 // the deltas of layer 2 (src/kernel/layer_deltas.cl:42-127 with n_next = 1) and the weight/bias
@@ -331,7 +406,26 @@ __global__ void __launch_bounds__(B3_NT) bwd3_fused_kernel(
       for (int dy = 0; dy < F; dy++)
 #pragma unroll
         for (int t = 0; t < F - 1; t++) win[dy][t] = prow[dy][t];
+      // out2 values of the next group of F pixels are fetched while this group is processed
+      // (one warp has ~4 peers per scheduler: an exposed global load costs ~150 issue slots)
+      float vn[CPL][F];
+#pragma unroll
+      for (int jc = 0; jc < CPL; jc++)
+#pragma unroll
+        for (int u = 0; u < F; u++) {
+          const int c = lane + 32 * jc;
+          vn[jc][u] = (c < k && u < ow) ? __ldg(o2s + ((long long)j * ow + u) * k + c) : 0.f;
+        }
       for (int i0 = 0; i0 < ow; i0 += F) {
+        float vc[CPL][F];
+#pragma unroll
+        for (int jc = 0; jc < CPL; jc++)
+#pragma unroll
+          for (int u = 0; u < F; u++) {
+            vc[jc][u] = vn[jc][u];
+            const int c = lane + 32 * jc, i = i0 + F + u;
+            vn[jc][u] = (c < k && i < ow) ? __ldg(o2s + ((long long)j * ow + i) * k + c) : 0.f;
+          }
 #pragma unroll
         for (int u = 0; u < F; u++) {
           const int i = i0 + u;
@@ -342,18 +436,20 @@ __global__ void __launch_bounds__(B3_NT) bwd3_fused_kernel(
             for (int jc = 0; jc < CPL; jc++) {
               const int c = lane + 32 * jc;
               if (c < k) {
-                const long long idx = ((long long)j * ow + i) * k + c;
-                const float v = __ldg(o2s + idx);
-                float dsum = 0.f;
+                const float v = vc[jc][u];
+                float ds[F];   // one chain per filter row, folded in a fixed order
 #pragma unroll
-                for (int dy = 0; dy < F; dy++)
+                for (int dy = 0; dy < F; dy++) {
+                  ds[dy] = 0.f;
 #pragma unroll
                   for (int dx = 0; dx < F; dx++) {
                     const float dv = win[dy][(u + F - 1 - dx) % F];
-                    dsum = fmaf(wt[jc][dy * F + dx], dv, dsum);
+                    ds[dy] = fmaf(wt[jc][dy * F + dx], dv, ds[dy]);
                     acc[jc][dy * F + dx] = fmaf(v, dv, acc[jc][dy * F + dx]);
                   }
-                d2s[idx] = v > 0.f ? dsum : 0.f;
+                }
+                const float dsum = ((ds[0] + ds[1]) + (ds[2] + ds[3])) + ds[4];
+                d2s[((long long)j * ow + i) * k + c] = v > 0.f ? dsum : 0.f;
               }
             }
           }
@@ -647,6 +743,24 @@ inline bool n1_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* t
     n1_deltas_kernel<5, 1><<<grid, NT, 0, ctx->stream>>>(dn, lo, target, W, n_curr, ow, oh, S);
   else
     n1_deltas_kernel<5, 2><<<grid, NT, 0, ctx->stream>>>(dn, lo, target, W, n_curr, ow, oh, S);
+  return true;
+}
+
+// deltas below an f = 1 layer; returns true when it launched
+inline bool f1_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
+                      const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
+  if (f_next != 1) return false;
+  const long long P = (long long)S * ow * oh;
+  const unsigned grid = (unsigned)((P + 127) / 128);
+  if ((reinterpret_cast<uintptr_t>(dn) | reinterpret_cast<uintptr_t>(lo) |
+       reinterpret_cast<uintptr_t>(target)) & 15u)
+    return false;
+  if (n_curr == 64 && n_next == 32)
+    f1_deltas_kernel<64, 32><<<grid, 256, 0, ctx->stream>>>(dn, lo, target, W, P);
+  else if (n_curr == 32 && n_next == 16)
+    f1_deltas_kernel<32, 16><<<grid, 256, 0, ctx->stream>>>(dn, lo, target, W, P);
+  else
+    return false;
   return true;
 }
 

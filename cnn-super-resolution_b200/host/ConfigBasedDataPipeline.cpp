@@ -189,6 +189,16 @@ float ConfigBasedDataPipeline::execute_batch(bool backpropagate__, GpuAllocation
       _context->copy_buffer(s.expected_luma, _ground_truth_gpu_buf, offset);
       offset += w * h * sizeof(float);
     }
+    if (backpropagate__ && !_context->is_running_profile_mode()) {
+      // forward() + backpropagate() of the chunk as ONE call into the device layer (fused
+      // tensor-core forward that keeps out1/out2, fused backward of the last layer); the
+      // `profile` mode keeps the per-kernel sequence so that its per-kernel totals stay
+      // meaningful (src/opencl/Kernel.cpp:108-116)
+      train_chunk(gpu_alloc.layer_1, gpu_alloc.layer_2, gpu_alloc.layer_3, w, h, in_batch);
+      _context->block();
+      i += in_batch;
+      continue;
+    }
     cl_event forward_ev =
         forward(gpu_alloc.layer_1, gpu_alloc.layer_2, gpu_alloc.layer_3, w, h, in_batch);
     if (backpropagate__) {
@@ -205,6 +215,47 @@ float ConfigBasedDataPipeline::execute_batch(bool backpropagate__, GpuAllocation
     i += in_batch;
   }
   return validation_error;
+}
+
+void ConfigBasedDataPipeline::ensure_gradients_on_device(LayerData& data, LayerAllocationPool& pool) {
+  if (pool.accumulating_grad_w == gpu_nullptr) {
+    pool.accumulating_grad_w = _context->allocate(CL_MEM_READ_WRITE, sizeof(float) * data.weight_size());
+    _context->zeros_float(pool.accumulating_grad_w, true);
+  }
+  if (pool.accumulating_grad_b == gpu_nullptr) {
+    pool.accumulating_grad_b = _context->allocate(CL_MEM_READ_WRITE, sizeof(float) * data.bias_size());
+    _context->zeros_float(pool.accumulating_grad_b, true);
+  }
+}
+
+void ConfigBasedDataPipeline::train_chunk(LayerAllocationPool& l1, LayerAllocationPool& l2,
+                                          LayerAllocationPool& l3, size_t w, size_t h,
+                                          size_t sample_count) {
+  check_initialized(DataPipeline::LOAD_KERNEL_LAYERS);
+  if (sample_count > _mini_batch_size)
+    throw std::runtime_error("Allocation pool out of bounds exception");
+  srcnn_net net{};
+  net.n1 = (int)_config->n1; net.n2 = (int)_config->n2;
+  net.f1 = (int)_config->f1; net.f2 = (int)_config->f2; net.f3 = (int)_config->f3;
+  LayerData* layers[3] = {&layer_data_1, &layer_data_2, &layer_data_3};
+  LayerAllocationPool* pools[3] = {&l1, &l2, &l3};
+  for (int i = 0; i < 3; i++) {
+    ensure_parameters_on_device(*layers[i], *pools[i]);
+    ensure_gradients_on_device(*layers[i], *pools[i]);
+    net.w[i] = _context->mem(pools[i]->weights);
+    net.b[i] = _context->mem(pools[i]->bias);
+    net.grad_w[i] = _context->mem(pools[i]->accumulating_grad_w);
+    net.grad_b[i] = _context->mem(pools[i]->accumulating_grad_b);
+    net.prev_dw[i] = net.prev_db[i] = SRCNN_NULL_MEM;
+  }
+  _context->check_status(
+      srcnn_train_chunk_buffers(_context->c_ctx(), &net, _context->mem(_forward_gpu_buf),
+                                _context->mem(_ground_truth_gpu_buf), (int)w, (int)h,
+                                (int)sample_count, _context->mem(_out_1_gpu_buf),
+                                _context->mem(_out_2_gpu_buf), _context->mem(_out_3_gpu_buf),
+                                _context->mem(_delta_1_gpu_buf), _context->mem(_delta_2_gpu_buf),
+                                _context->mem(_delta_3_gpu_buf)),
+      "train chunk");
 }
 
 cl_event ConfigBasedDataPipeline::backpropagate(LayerAllocationPool& l1, LayerAllocationPool& l2,

@@ -68,6 +68,10 @@ class ConfigBasedDataPipeline : public DataPipeline {
   cl_event backpropagate(LayerAllocationPool&, LayerAllocationPool&, LayerAllocationPool&,
                          size_t w, size_t h, size_t sample_count, cl_event* ev = nullptr);
   void ensure_parameters_on_device(LayerData&, LayerAllocationPool&);
+  void ensure_gradients_on_device(LayerData&, LayerAllocationPool&);
+  /** forward() + backpropagate() of one training chunk in one device-layer call */
+  void train_chunk(LayerAllocationPool&, LayerAllocationPool&, LayerAllocationPool&, size_t w,
+                   size_t h, size_t sample_count);
   void fill_random_parameters(LayerData&, ParametersDistribution&);
   size_t load_parameters_file(const char* const);
 

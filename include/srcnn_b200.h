@@ -217,6 +217,14 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
                       int w, int h, int S, srcnn_mem work);
 size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S);
 
+/* Same chunk, with the six activation / delta buffers owned by the caller -- the buffers
+ * ConfigBasedDataPipeline allocates itself (_out_1.._out_3, _delta_1.._delta_3,
+ * src/ConfigBasedDataPipeline.cpp:82-108), so that its forward() + backpropagate() pair for a
+ * training chunk is one call.  Every buffer must start 16-byte aligned. */
+int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
+                              int w, int h, int S, srcnn_mem out1, srcnn_mem out2,
+                              srcnn_mem out3, srcnn_mem d1, srcnn_mem d2, srcnn_mem d3);
+
 /* ConfigBasedDataPipeline::update_parameters (src/ConfigBasedDataPipeline.cpp:325-361) in
  * ONE launch: the three layers with lr[0..2], then the six accumulators are zeroed. */
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,

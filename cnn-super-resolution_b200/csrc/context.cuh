@@ -77,7 +77,10 @@ struct srcnn_ctx {
   uint64_t launch_count = 0;
   // fused inference implementation: tensor cores (tcgen05, 3xTF32) where instantiated, unless
   // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
-  int fused_impl = 3;   // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes
+  // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes (3xTF32), 4 planes (FP16 split)
+  int fused_impl = 4;
+  void* hp_scales = nullptr;          // ring of fused_hp::Scales blocks + their work words
+  unsigned long long hp_next = 0;
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand

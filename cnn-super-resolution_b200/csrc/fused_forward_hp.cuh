@@ -1,0 +1,686 @@
+// Fused SRCNN inference, FP16-split tensor-core version (9-1-5, n1=64, n2=32).
+//
+// Same structure as fused_forward_pl.cuh (plane operands, one MMA issuer per layer, in-place
+// TMEM operands, every buffer double) but every operand is split into two HALVES instead of two
+// TF32 terms:
+//     x * s = hi + lo / 2048        hi = half(x*s), lo = half((x*s - hi) * 2048)
+// with s a power of two that keeps both halves in the normal range.  x.w is evaluated as
+// hi.w_hi + (hi.w_lo + lo.w_hi) / 2048: the first product accumulates in one half of the
+// (stacked) accumulator, the two correction products -- which carry the extra factor 2048 -- in
+// the other, and the epilogue recombines them.  Accuracy is that of the 3xTF32 scheme (22
+// mantissa bits per operand; probe/f16_probe.cu: 2.5e-7 max error on a 9x9x64 tile), but
+//   * kind::f16 MMAs take K = 16 per instruction: 6 + 4 + 2 K-steps per tile instead of
+//     11 + 8 + 4, i.e. 24 instructions instead of 46, ~1 050 pipe cycles instead of ~2 050;
+//   * layer 1 reads "oct planes" O(s)[c] = rows s..s+7 of column c (8 halves = 16 bytes) and
+//     H8(r)[c] = in[r][c..c+7]: one O and one H8 plane per tile;
+//   * A2/A3 are packed half pairs: half the TMEM store traffic of the epilogues.
+//
+// Range.  The scales depend on the WEIGHTS only (computed on the device by hp_prepare_kernel
+// before every launch; data-independent, so a row-band partition of an image reproduces the
+// single-launch result bit for bit) and assume |input| < 64, 64x the luma range:
+//     sx = 2^9;  sw_l = 2^14 / pow2ceil(max|W_l|);  s_l = 2^14 / pow2ceil(bound on out_l)
+// with bound(out1) = max_n(|b1| + sum|W1|) * 64 and bound(out2) likewise from bound(out1).
+// hp_prepare_kernel also scans the input: if any |x| >= 64 (or non-finite) it clears the
+// `ok` flag, this kernel exits at once and the TF32 kernel -- launched right behind it with the
+// flag as its gate -- does the work instead.  No result ever depends on an FP16 overflow.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "context.cuh"
+#include "fused_forward.cuh"
+#include "fused_forward_pl.cuh"
+#include "tc_common.cuh"
+
+namespace srcnn {
+namespace fused_hp {
+
+struct Scales {
+  float sx, sw1, sw2, sw3, s1, s2;
+  float c1s;      // s1 / (sx * sw1): D1 -> out1 * s1
+  float c2s;      // s2 / (s1 * sw2): D2 -> out2 * s2
+  float c3;       // 1 / (s2 * sw3):  D3 -> Q
+  float inv_s1, inv_s2;
+  int ok;         // 1: the input is inside the FP16 domain, this kernel runs; 0: the TF32 one
+};
+
+struct Cfg {
+  static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
+  static constexpr int M = 128;
+  static constexpr int OW3 = M - (F3 - 1);
+  static constexpr int KS1 = 6, K1 = KS1 * 16;   // halves: 81 taps + 15 zero weights
+  static constexpr int K2 = N1, K3 = N2, NT3 = 32, QP = F3 * F3;
+  static constexpr int PW = 144;                 // plane entries (16 bytes = 8 halves each)
+  static constexpr int PB = PW * 16;             // bytes per plane
+  static constexpr int RO = 4, RH = 4;           // ring slots: oct planes, H8 planes
+  static constexpr int W_E1 = 0, N_E1 = 4, W_E2 = 4, W_E3 = 8, W_IM = 12, N_IM = 5, W_I1 = 17,
+                       W_I2 = 18, W_I3 = 19;
+  static constexpr int NT = 20 * 32;
+  static constexpr int IM_THREADS = N_IM * 32;
+  // shared memory carve-up (bytes).  The H8 ring lies ABOVE the oct ring: one K-step pairs the
+  // dx = 8 chunk of O with the first chunk of H8 through a positive leading-dimension offset.
+  static constexpr int oOh = 0;
+  static constexpr int oOl = oOh + RO * PB;
+  static constexpr int oHh = oOl + RO * PB;
+  static constexpr int oHl = oHh + RH * PB;
+  static constexpr int oW1 = oHl + RH * PB;          // [128][K1] halves: rows 0..63 hi, 64.. lo
+  static constexpr int oW2 = oW1 + 2 * N1 * K1 * 2;  // [64][K2]
+  static constexpr int oW3 = oW2 + 2 * N2 * K2 * 2;  // [64][K3]: rows = taps (25 of 32), hi, lo
+  static constexpr int oB1 = oW3 + 2 * NT3 * K3 * 2; // b1 * s1 (floats)
+  static constexpr int oB2 = oB1 + N1 * 4;           // b2 * s2
+  static constexpr int oQs = oB2 + N2 * 4;           // 2 staged Q rows [M][QP] floats
+  static constexpr int TOTAL = oQs + 2 * M * QP * 4;
+  static constexpr size_t SMEM_BYTES = (size_t)TOTAL;
+  // tensor memory columns (+ size * (b & 1)):
+  //   D1: [0,64) hi.w_hi, [64,128) corrections  ->  A2: [0,32) hi pairs, [64,96) lo pairs
+  //   D2: [0,32), [32,64)                       ->  A3: [0,16) hi pairs, [32,48) lo pairs
+  //   D3: [0,32), [32,64) (25 taps of 32 used)
+  static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr int BAR_E3 = 1;
+};
+
+// K-major canonical layout for 16-bit elements: core matrix = 8 rows x 16 bytes (8 halves);
+// returns the offset in halves of (row r, element k) of a [rows][K] operand
+__host__ __device__ __forceinline__ int kmajor16(int r, int k, int K) {
+  return (r >> 3) * (64 * (K >> 3)) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
+}
+// (K-step s, 16-byte chunk j, element e) of the layer-1 contraction -> filter tap, or -1.
+// chunks 0..8: O at dx = chunk (taps dy = e); chunk 9: H8 at dx' = 0 (taps (8, e));
+// chunk 10: H8 at dx' = 8 (tap (8,8) + 7 pads); chunk 11: pad
+__host__ __device__ __forceinline__ int tap16(int s, int j, int e) {
+  const int c = 2 * s + j;
+  if (c < 9) return e * Cfg::F1 + c;
+  if (c == 9) return 8 * Cfg::F1 + e;
+  if (c == 10) return e == 0 ? 8 * Cfg::F1 + 8 : -1;
+  return -1;
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int Mm, int Nn) {
+  // c_format = F32, a_format = b_format = F16, both K-major
+  return (1u << 4) | ((uint32_t)(Nn >> 3) << 17) | ((uint32_t)(Mm >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                           uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc,
+                                           uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// xs = hi + lo / 2048 (raw half bits)
+__device__ __forceinline__ void split_h(float xs, unsigned short& hi, unsigned short& lo) {
+  const __half h = __float2half_rn(xs);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn((xs - __half2float(h)) * 2048.f));
+}
+// two values -> packed pairs (element 0 in the low half: K index order)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) {
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t v[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+
+using fused_pl::BatchExt;
+using fused_pl::elect_one;
+using fused_pl::tmem_ld16_nowait;
+using fused_pl::tmem_ld_wait;
+using fused_ws::mbar_arrive;
+using fused_ws::named_bar_sync;
+
+// ---------------------------------------------------------------------------- prepare --------
+// Scans the input for the domain check and derives the scales from the parameters.  ws[0]: max
+// of the |x| bit patterns, ws[1]: finished-CTA counter (both left at zero for the next launch).
+__device__ __forceinline__ float pow2_scale(float bound) {   // 2^14 / pow2ceil(bound)
+  if (!(bound > 0.f) || !(bound < 1e30f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                 // bound = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+__global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict__ in, size_t n,
+                                                         fused::Args a, Scales* sc, unsigned* ws) {
+  __shared__ unsigned red_u[8];
+  __shared__ float red_f[8];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned m = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256)
+    m = max(m, __float_as_uint(fabsf(__ldg(in + i))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red_u[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) m = max(m, red_u[w]);
+    atomicMax(&ws[0], m);
+    __threadfence();
+    last = atomicAdd(&ws[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  auto block_max = [&](float v) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red_f[warp] = v;
+    __syncthreads();
+    float r = red_f[0];
+    for (int w = 1; w < 8; w++) r = fmaxf(r, red_f[w]);
+    return r;
+  };
+  constexpr float kInMax = 64.f;
+  float v = 0.f;
+  for (int i = tid; i < Cfg::F1 * Cfg::F1 * Cfg::N1; i += 256) v = fmaxf(v, fabsf(__ldg(a.pw1 + i)));
+  const float m1 = block_max(v);
+  v = 0.f;
+  for (int i = tid; i < Cfg::N1 * Cfg::N2; i += 256) v = fmaxf(v, fabsf(__ldg(a.pw2 + i)));
+  const float m2 = block_max(v);
+  v = 0.f;
+  for (int i = tid; i < Cfg::QP * Cfg::N2; i += 256) v = fmaxf(v, fabsf(__ldg(a.pw3 + i)));
+  const float m3 = block_max(v);
+  // bound on |out1[n]| and, from it, on |out2[n]|
+  v = 0.f;
+  if (tid < Cfg::N1) {
+    float s = 0.f;
+    for (int t = 0; t < Cfg::F1 * Cfg::F1; t++) s += fabsf(__ldg(a.pw1 + t * Cfg::N1 + tid));
+    v = s * kInMax + fabsf(__ldg(a.pb1 + tid));
+  }
+  const float bound1 = block_max(v);
+  v = 0.f;
+  if (tid < Cfg::N2) {
+    float s = 0.f;
+    for (int k = 0; k < Cfg::N1; k++) s += fabsf(__ldg(a.pw2 + k * Cfg::N2 + tid));
+    v = s * bound1 + fabsf(__ldg(a.pb2 + tid));
+  }
+  const float bound2 = block_max(v);
+  if (tid == 0) {
+    Scales s;
+    s.sx = 512.f;   // 64 * 512 = 2^15
+    s.sw1 = pow2_scale(m1);
+    s.sw2 = pow2_scale(m2);
+    s.sw3 = pow2_scale(m3);
+    s.s1 = pow2_scale(bound1);
+    s.s2 = pow2_scale(bound2);
+    s.c1s = s.s1 / (s.sx * s.sw1);
+    s.c2s = s.s2 / (s.s1 * s.sw2);
+    s.c3 = 1.f / (s.s2 * s.sw3);
+    s.inv_s1 = 1.f / s.s1;
+    s.inv_s2 = 1.f / s.s2;
+    const unsigned mx = atomicMax(&ws[0], 0u);
+    s.ok = (mx < __float_as_uint(kInMax * 0.999f) && bound2 < 1e30f) ? 1 : 0;
+    *sc = s;
+    ws[0] = 0;
+    ws[1] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------- main kernel ----
+template <bool BATCH>
+__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Args a, int rpc,
+                                                                      BatchExt bx,
+                                                                      const Scales* scales) {
+  using C = Cfg;
+  using namespace tc;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const Scales sc = *scales;
+  if (!sc.ok) return;   // input outside the FP16 domain: the TF32 kernel behind us runs instead
+  __half* sW1 = reinterpret_cast<__half*>(smem_raw + C::oW1);
+  __half* sW2 = reinterpret_cast<__half*>(smem_raw + C::oW2);
+  __half* sW3 = reinterpret_cast<__half*>(smem_raw + C::oW3);
+  float* sB1 = reinterpret_cast<float*>(smem_raw + C::oB1);
+  float* sB2 = reinterpret_cast<float*>(smem_raw + C::oB2);
+  float* sQs = reinterpret_cast<float*>(smem_raw + C::oQs);
+  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2],
+      a3_full[2], bar3[2], d3_free[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int X0 = blockIdx.x * C::OW3;
+  const int R0 = blockIdx.y * rpc;
+  const float* img = BATCH ? a.in : a.in + (size_t)blockIdx.z * a.w * a.h;
+  float* dst = BATCH ? a.out : a.out + (size_t)blockIdx.z * a.w3 * a.h3;
+
+  // ---- stage parameters: B operands [n][k] canonical (16-bit), hi rows then lo rows ----------
+  for (int i = tid; i < 2 * C::N1 * C::K1; i += C::NT) {
+    const int n = i / C::K1, k = i % C::K1;
+    const int t = tap16(k >> 4, (k >> 3) & 1, k & 7);
+    unsigned short hi, lo;
+    split_h(t >= 0 ? __ldg(a.pw1 + t * C::N1 + (n & (C::N1 - 1))) * sc.sw1 : 0.f, hi, lo);
+    sW1[kmajor16(n, k, C::K1)] = __ushort_as_half(n < C::N1 ? hi : lo);
+  }
+  for (int i = tid; i < 2 * C::N2 * C::K2; i += C::NT) {
+    const int n = i / C::K2, k = i % C::K2;
+    unsigned short hi, lo;
+    split_h(__ldg(a.pw2 + k * C::N2 + (n & (C::N2 - 1))) * sc.sw2, hi, lo);
+    sW2[kmajor16(n, k, C::K2)] = __ushort_as_half(n < C::N2 ? hi : lo);
+  }
+  for (int i = tid; i < 2 * C::NT3 * C::K3; i += C::NT) {
+    const int n = i / C::K3, k = i % C::K3;   // n & 31 = tap dy*5+dx, k = channel
+    const int tap = n & (C::NT3 - 1);
+    unsigned short hi, lo;
+    split_h(tap < C::QP ? __ldg(a.pw3 + tap * C::N2 + k) * sc.sw3 : 0.f, hi, lo);
+    sW3[kmajor16(n, k, C::K3)] = __ushort_as_half(n < C::NT3 ? hi : lo);
+  }
+  for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i) * sc.s1;
+  for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i) * sc.s2;
+  // pad entries of the planes are read by the tensor core (times a zero weight): keep them finite
+  for (int i = tid; i < 2 * (C::RO + C::RH) * C::PB / 4; i += C::NT)
+    reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+  const float b3 = __ldg(a.pb3);
+
+  if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    if (smem_u32(smem_raw) & 127u) __trap();
+    for (int i = 0; i < 4; i++) {
+      mbar_init(&p_full[i], C::IM_THREADS);
+      mbar_init(&p_free[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&bar1[i], 1);
+      mbar_init(&a2_full[i], C::N_E1 * 32);
+      mbar_init(&bar2[i], 1);
+      mbar_init(&a3_full[i], 128);
+      mbar_init(&bar3[i], 1);
+      mbar_init(&d3_free[i], 128);
+    }
+  }
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int rows_here = min(rpc, a.h3 - R0);
+  const int n_tiles = rows_here + (C::F3 - 1);   // out2 rows R0 .. R0+rows_here+3
+
+  if (warp >= C::W_IM && warp < C::W_IM + C::N_IM) {
+    // ============================ IM: plane producers =====================================
+    // thread c owns plane column c (image column X0+c): per input row r it writes
+    // H8(r)[c] = in[r][c..c+7] and O(r-7)[c] = (in[r-7..r][c]); the 7 older rows of the column
+    // live in registers as halves.
+    const int c = tid - C::W_IM * 32;
+    const bool active = c < C::PW;
+    const int gx = X0 + c;
+    uint8_t* pOh = smem_raw + C::oOh + c * 16;
+    uint8_t* pOl = smem_raw + C::oOl + c * 16;
+    uint8_t* pHh = smem_raw + C::oHh + c * 16;
+    uint8_t* pHl = smem_raw + C::oHl + c * 16;
+    long long boff[8];
+    if (BATCH) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int vx = gx + e;
+        const int smp = vx / bx.pw;
+        boff[e] = (active && vx < a.w) ? (long long)smp * bx.pw * bx.ph + (vx - smp * bx.pw) : -1;
+      }
+    }
+    auto ld = [&](int r, int e) -> float {
+      const int gy = R0 + r;
+      float v;
+      if (BATCH)
+        v = (boff[e] >= 0 && gy < a.h) ? __ldg(img + boff[e] + (long long)gy * bx.pw) : 0.f;
+      else
+        v = (active && gy < a.h && gx + e < a.w) ? __ldg(img + (size_t)gy * a.w + gx + e) : 0.f;
+      return v * sc.sx;
+    };
+    unsigned short hh[7], hl[7];   // rows r-7 .. r-1 of this column
+    {
+      float pv[C::F1 - 1];
+#pragma unroll
+      for (int r = 0; r < C::F1 - 1; r++) pv[r] = ld(r, 0);
+      unsigned short h7, l7;
+#pragma unroll
+      for (int r = 0; r < C::F1 - 2; r++) split_h(pv[r], hh[r], hl[r]);
+      split_h(pv[C::F1 - 2], h7, l7);
+      if (active) {   // O(0) = rows 0..7
+        *reinterpret_cast<uint4*>(pOh) = make_uint4(pack2(hh[0], hh[1]), pack2(hh[2], hh[3]),
+                                                    pack2(hh[4], hh[5]), pack2(hh[6], h7));
+        *reinterpret_cast<uint4*>(pOl) = make_uint4(pack2(hl[0], hl[1]), pack2(hl[2], hl[3]),
+                                                    pack2(hl[4], hl[5]), pack2(hl[6], l7));
+      }
+#pragma unroll
+      for (int r = 0; r < 6; r++) { hh[r] = hh[r + 1]; hl[r] = hl[r + 1]; }
+      hh[6] = h7; hl[6] = l7;
+    }
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = ld(C::F1 - 1, e);
+    for (int b = 0; b < n_tiles; b++) {
+      float nv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) nv[e] = (b + 1 < n_tiles) ? ld(b + C::F1, e) : 0.f;
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) split_h2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
+      const unsigned short nh = (unsigned short)(ph[0] & 0xffffu), nl = (unsigned short)(pl[0] & 0xffffu);
+      // H8(b+8) replaces H8(b+4) (MMA-1(b-4)), O(b+1) replaces O(b-3) (MMA-1(b-3))
+      if (b >= 3) mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1));
+      if (active) {
+        const int sh = b & (C::RH - 1), so = (b + 1) & (C::RO - 1);
+        *reinterpret_cast<uint4*>(pHh + sh * C::PB) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(pHl + sh * C::PB) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        *reinterpret_cast<uint4*>(pOh + so * C::PB) = make_uint4(
+            pack2(hh[0], hh[1]), pack2(hh[2], hh[3]), pack2(hh[4], hh[5]), pack2(hh[6], nh));
+        *reinterpret_cast<uint4*>(pOl + so * C::PB) = make_uint4(
+            pack2(hl[0], hl[1]), pack2(hl[2], hl[3]), pack2(hl[4], hl[5]), pack2(hl[6], nl));
+      }
+#pragma unroll
+      for (int r = 0; r < 6; r++) { hh[r] = hh[r + 1]; hl[r] = hl[r + 1]; }
+      hh[6] = nh; hl[6] = nl;
+      fence_proxy_async();
+      mbar_arrive(&p_full[b & 3]);
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = nv[e];
+    }
+  } else if (warp == C::W_I1) {
+    // ============================ I1: layer-1 MMA issuer ===================================
+    const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::N1);   // A_hi x [W_hi; W_lo]
+    const uint32_t idesc_lo = make_idesc_f16(C::M, C::N1);       // A_lo x W_hi
+    const uint64_t wdesc = make_desc_kmajor(sW1, 0, 128, 128 * (C::K1 / 8));
+    const uint32_t aOh = smem_u32(smem_raw + C::oOh), aOl = smem_u32(smem_raw + C::oOl);
+    const uint32_t aHh = smem_u32(smem_raw + C::oHh), aHl = smem_u32(smem_raw + C::oHl);
+    auto adesc = [](uint32_t addr, uint32_t lbo) -> uint64_t {
+      return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+             ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    };
+    for (int t = 0; t < n_tiles; t++) {
+      mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1));
+      // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
+      if (t >= 2) mbar_wait(&bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      tcgen05_fence_after();
+      const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
+      const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
+      const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * C::PB;
+      if (elect_one()) {
+#pragma unroll
+        for (int s = 0; s < C::KS1; s++) {
+          uint32_t ah, al, lbo_h, lbo_l;
+          if (s < 4) { ah = aOh + so + 32 * s; al = aOl + so + 32 * s; lbo_h = lbo_l = 16; }
+          else if (s == 4) {
+            ah = aOh + so + 128; al = aOl + so + 128;
+            lbo_h = (aHh + sh) - ah; lbo_l = (aHl + sh) - al;
+          }
+          else { ah = aHh + sh + 128; al = aHl + sh + 128; lbo_h = lbo_l = 16; }
+          mma_f16_ss(d1, adesc(ah, lbo_h), wdesc + 16 * s, idesc_hi, s > 0);
+          mma_f16_ss(d1 + C::N1, adesc(al, lbo_l), wdesc + 16 * s, idesc_lo, 1);
+        }
+        mma_commit(&bar1[t & 1]);
+        mma_commit(&p_free[t & 3]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == C::W_I2) {
+    // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
+    const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::N2);
+    const uint32_t idesc_lo = make_idesc_f16(C::M, C::N2);
+    const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
+    for (int t = 0; t < n_tiles; t++) {
+      mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1));
+      // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
+      if (t >= 2) mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      tcgen05_fence_after();
+      const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
+      const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::K2 / 16; ks++) {
+          mma_f16_ts(d2, a2 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_f16_ts(d2 + C::N2, a2 + C::N1 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+        }
+        mma_commit(&bar2[t & 1]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == C::W_I3) {
+    // ============================ I3: layer-3 tap-GEMM issuer (A3 in TMEM) =================
+    const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::NT3);
+    const uint32_t idesc_lo = make_idesc_f16(C::M, C::NT3);
+    const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::K3 / 8));
+    for (int t = 0; t < n_tiles; t++) {
+      mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1));
+      if (t >= 2) mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      tcgen05_fence_after();
+      const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::K3 / 16; ks++) {
+          mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_f16_ts(d3 + C::NT3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+        }
+        mma_commit(&bar3[t & 1]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < C::W_E1 + C::N_E1) {
+    // ============================ E1: A2 = split(relu(out1) * s1), in place ================
+    // chunk g (16 channels) reads D1 columns [16g,16g+16) and [64+16g, ..) and then writes the
+    // hi pairs to [8g, 8g+8) and the lo pairs to [64+8g, ..): columns already consumed
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* o1 = nullptr;
+    if (BATCH && bx.out1) {
+      const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w1 = bx.pw - (C::F1 - 1), h1 = bx.ph - (C::F1 - 1);
+      if (m < C::OW3 && vx < a.w && px < w1)
+        o1 = bx.out1 + (((size_t)smp * h1 + R0) * w1 + px) * C::N1;
+    }
+    const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
+    for (int b = 0; b < n_tiles; b++) {
+      mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
+      tcgen05_fence_after();
+      const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
+#pragma unroll 1
+      for (int g = 0; g < C::N1 / 16; g++) {
+        float va[16], vb[16];
+        tmem_ld16_nowait(d1 + g * 16, va);              // hi.w_hi
+        tmem_ld16_nowait(d1 + C::N1 + g * 16, vb);      // (hi.w_lo + lo.w_hi) * 2048
+        tmem_ld_wait();
+        uint32_t hi[8], lo[8];
+        float act[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          act[j] = fmaxf(fmaf(fmaf(vb[j], 1.f / 2048.f, va[j]), sc.c1s, sB1[g * 16 + j]), 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
+        tmem_st8u(d1 + g * 8, hi);
+        tmem_st8u(d1 + C::N1 + g * 8, lo);
+        if (BATCH && o1) {
+          float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            q[j] = make_float4(act[4 * j] * sc.inv_s1, act[4 * j + 1] * sc.inv_s1,
+                               act[4 * j + 2] * sc.inv_s1, act[4 * j + 3] * sc.inv_s1);
+        }
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&a2_full[b & 1]);
+    }
+  } else if (warp < C::W_E3) {
+    // ============================ E2: A3 = split(relu(out2) * s2), in place ================
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* o2 = nullptr;
+    if (BATCH && bx.out2) {
+      const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w2 = bx.pw - (C::F1 - 1), h2 = bx.ph - (C::F1 - 1);
+      if (m < C::OW3 && vx < a.w && px < w2)
+        o2 = bx.out2 + (((size_t)smp * h2 + R0) * w2 + px) * C::N2;
+    }
+    const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
+    for (int b = 0; b < n_tiles; b++) {
+      mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
+      tcgen05_fence_after();
+      const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
+#pragma unroll
+      for (int g = 0; g < C::N2 / 16; g++) {
+        float va[16], vb[16];
+        tmem_ld16_nowait(d2 + g * 16, va);
+        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb);
+        tmem_ld_wait();
+        uint32_t hi[8], lo[8];
+        float act[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          act[j] = fmaxf(fmaf(fmaf(vb[j], 1.f / 2048.f, va[j]), sc.c2s, sB2[g * 16 + j]), 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
+        tmem_st8u(d2 + g * 8, hi);
+        tmem_st8u(d2 + C::N2 + g * 8, lo);
+        if (BATCH && o2) {
+          float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            q[j] = make_float4(act[4 * j] * sc.inv_s2, act[4 * j + 1] * sc.inv_s2,
+                               act[4 * j + 2] * sc.inv_s2, act[4 * j + 3] * sc.inv_s2);
+        }
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&a3_full[b & 1]);
+    }
+  } else if (warp < C::W_IM) {
+    // ============================ E3: Q row -> smem, 25-term gather -> out3 ================
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int x = (warp & 3) * 32 + lane;
+    bool live = x < C::OW3 && X0 + x < a.w3;
+    size_t o3 = (size_t)R0 * a.w3 + X0 + x;   // output row 0 of this thread's column
+    size_t o3_row = (size_t)a.w3;
+    if (BATCH) {
+      const int vx = X0 + x, smp = vx / bx.pw, px = vx - smp * bx.pw;
+      const int w3 = bx.pw - (C::F1 + C::F3 - 2), h3 = bx.ph - (C::F1 + C::F3 - 2);
+      live = live && px < w3;
+      o3 = ((size_t)smp * h3 + R0) * w3 + px;
+      o3_row = (size_t)w3;
+    }
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    for (int b = 0; b < n_tiles; b++) {
+      mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-3(b) done
+      tcgen05_fence_after();
+      const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
+      float v[32], w[32];
+      tmem_ld16_nowait(d3, v);
+      tmem_ld16_nowait(d3 + 16, v + 16);
+      tmem_ld16_nowait(d3 + 32, w);
+      tmem_ld16_nowait(d3 + 48, w + 16);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
+      float* qs = sQs + (b & 1) * (C::M * C::QP);
+#pragma unroll
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]) * sc.c3;
+      named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
+      float r[C::F3];
+      if (x < C::OW3) {
+#pragma unroll
+        for (int dy = 0; dy < C::F3; dy++) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int dx = 0; dx < C::F3; dx++) {
+            const float q = qs[(x + dx) * C::QP + dy * C::F3 + dx];
+            if (dx & 1) s1 += q; else s0 += q;
+          }
+          r[dy] = s0 + s1;
+        }
+      } else {
+#pragma unroll
+        for (int dy = 0; dy < C::F3; dy++) r[dy] = 0.f;
+      }
+      const float done = acc0 + r[4];
+      acc0 = acc1 + r[3];
+      acc1 = acc2 + r[2];
+      acc2 = acc3 + r[1];
+      acc3 = r[0];
+      if (b >= C::F3 - 1 && live)
+        dst[o3 + (size_t)(b - (C::F3 - 1)) * o3_row] = done + b3;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+inline int configure() {
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES));
+  return SRCNN_OK;
+}
+
+inline bool supported(int n1, int n2, int f1, int f2, int f3) {
+  return n1 == 64 && n2 == 32 && f1 == 9 && f2 == 1 && f3 == 5;
+}
+
+// the per-context ring of scale blocks: launches on different streams (the pipelined
+// host-buffer inference) must not share one
+inline int scale_slot(srcnn_ctx* ctx, Scales** sc, unsigned** ws) {
+  constexpr int kSlots = 32;
+  if (!ctx->hp_scales) {
+    SRCNN_CUDA(cudaMalloc(&ctx->hp_scales, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));
+    SRCNN_CUDA(cudaMemset(ctx->hp_scales, 0, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));
+  }
+  const int i = (int)(ctx->hp_next++ % kSlots);
+  *sc = reinterpret_cast<Scales*>(ctx->hp_scales) + i;
+  *ws = reinterpret_cast<unsigned*>(reinterpret_cast<Scales*>(ctx->hp_scales) + kSlots) + 2 * i;
+  return SRCNN_OK;
+}
+
+// prepare + FP16 kernel + (gated) TF32 kernel; `S` images, or a batch as one virtual image
+inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float* out1,
+                  float* out2) {
+  Scales* sc;
+  unsigned* ws;
+  SRCNN_TRY(scale_slot(ctx, &sc, &ws));
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  hp_prepare_kernel<<<2 * sms, 256, 0, ctx->stream>>>(a.in, (size_t)S * a.w * a.h, a, sc, ws);
+  BatchExt bx{};
+  bx.gate = &sc->ok;
+  if (batch) {
+    fused::Args v = a;
+    const int pad = Cfg::F1 + Cfg::F3 - 2;
+    v.w = S * a.w;
+    v.w3 = S * a.w - pad;
+    const int rpc = fused_pl::rows_per_cta(v.w3, v.h3, 1, sms);
+    dim3 grid((v.w3 + Cfg::OW3 - 1) / Cfg::OW3, (v.h3 + rpc - 1) / rpc, 1);
+    bx.out1 = out1;
+    bx.out2 = out2;
+    bx.S = S;
+    bx.pw = a.w;
+    bx.ph = a.h;
+    forward_fused_hp_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx, sc);
+    fused_pl::forward_fused_pl_kernel<true>
+        <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx);
+  } else {
+    const int rpc = fused_pl::rows_per_cta(a.w3, a.h3, S, sms);
+    dim3 grid((a.w3 + Cfg::OW3 - 1) / Cfg::OW3, (a.h3 + rpc - 1) / rpc, S);
+    forward_fused_hp_kernel<false><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx, sc);
+    fused_pl::forward_fused_pl_kernel<false>
+        <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx);
+  }
+  return SRCNN_OK;
+}
+
+}  // namespace fused_hp
+}  // namespace srcnn

@@ -10,6 +10,7 @@
 #include "fused_forward_tc.cuh"
 #include "fused_forward_ws.cuh"
 #include "fused_forward_pl.cuh"
+#include "fused_forward_hp.cuh"
 #include "train_kernels.cuh"
 
 #include <cstdlib>
@@ -60,9 +61,11 @@ inline int configure(srcnn_ctx* ctx) {
   SRCNN_TRY(fused_tc::configure());
   SRCNN_TRY(fused_ws::configure());
   SRCNN_TRY(fused_pl::configure());
+  SRCNN_TRY(fused_hp::configure());
   // A/B switch between the generations of the fused kernel (default: the newest)
   const char* impl = std::getenv("SRCNN_FUSED_IMPL");
-  ctx->fused_impl = 3;                                           // "pl": plane operands
+  ctx->fused_impl = 4;                                           // "hp": planes, FP16 split
+  if (impl && std::strcmp(impl, "pl") == 0) ctx->fused_impl = 3;  // planes, 3xTF32
   if (impl && std::strcmp(impl, "simt") == 0) ctx->fused_impl = 0;
   if (impl && std::strcmp(impl, "tc") == 0) ctx->fused_impl = 1;  // lockstep tcgen05
   if (impl && std::strcmp(impl, "ws") == 0) ctx->fused_impl = 2;  // warp-specialised, im2col
@@ -106,8 +109,9 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
                 in_h - (f1 + f2 + f3 - 3)};
   if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
     // batches of small samples (validation patches) go through the virtual-image variant
-    if (ctx->fused_impl == 3 && S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30))
-      return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
+    const bool as_batch = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30);
+    if (ctx->fused_impl == 4) return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr);
+    if (ctx->fused_impl == 3 && as_batch) return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
     if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
     return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
   }
@@ -115,7 +119,7 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
 }
 
 inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
-  return ctx->fused_impl == 3 && fused_pl::supported(n1, n2, f1, f2, f3);
+  return ctx->fused_impl >= 3 && fused_pl::supported(n1, n2, f1, f2, f3);
 }
 
 // forward pass of a training chunk: all three layers in one launch, n1/n2-channel maps kept.
@@ -124,11 +128,12 @@ inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, i
                                const float* in, float* out1, float* out2, float* out3,
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w3, const float* b3, int in_w, int in_h, int S) {
-  if (ctx->fused_impl != 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
+  if (ctx->fused_impl < 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
   if ((long long)S * in_w >= (1LL << 30)) return 0;
   fused::Args a{in, out3, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
-  const int rc = fused_pl::launch_batch(ctx, a, S, out1, out2);
+  const int rc = ctx->fused_impl == 4 ? fused_hp::launch(ctx, a, S, true, out1, out2)
+                                      : fused_pl::launch_batch(ctx, a, S, out1, out2);
   return rc == SRCNN_OK ? 1 : rc;
 }
 

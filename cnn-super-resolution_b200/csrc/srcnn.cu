@@ -118,6 +118,7 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->band_in) cudaFree(ctx->band_in);
   if (ctx->band_out) cudaFree(ctx->band_out);
   if (ctx->packed_params) cudaFree(ctx->packed_params);
+  if (ctx->hp_scales) cudaFree(ctx->hp_scales);
   if (ctx->copy_in) {
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);

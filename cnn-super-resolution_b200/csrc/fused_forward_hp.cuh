@@ -20,9 +20,9 @@
 // single-launch result bit for bit) and assume |input| < 64, 64x the luma range:
 //     sx = 2^9;  sw_l = 2^14 / pow2ceil(max|W_l|);  s_l = 2^14 / pow2ceil(bound on out_l)
 // with bound(out1) = max_n(|b1| + sum|W1|) * 64 and bound(out2) likewise from bound(out1).
-// hp_prepare_kernel also scans the input: if any |x| >= 64 (or non-finite) it clears the
-// `ok` flag, this kernel exits at once and the TF32 kernel -- launched right behind it with the
-// flag as its gate -- does the work instead.  No result ever depends on an FP16 overflow.
+// The plane producers check every input pixel they load: the first |x| >= 64 (or NaN) clears the
+// `ok` flag, and the TF32 kernel -- launched right behind this one with the flag as its gate --
+// redoes the whole launch.  No result ever depends on an FP16 overflow.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -53,9 +53,13 @@ struct Cfg {
   static constexpr int PW = 144;                 // plane entries (16 bytes = 8 halves each)
   static constexpr int PB = PW * 16;             // bytes per plane
   static constexpr int RO = 4, RH = 4;           // ring slots: oct planes, H8 planes
-  static constexpr int W_E1 = 0, N_E1 = 4, W_E2 = 4, W_E3 = 8, W_IM = 12, N_IM = 5, W_I1 = 17,
-                       W_I2 = 18, W_I3 = 19;
-  static constexpr int NT = 20 * 32;
+#ifndef HP_N_E1
+#define HP_N_E1 8
+#endif
+  static constexpr int W_E1 = 0, N_E1 = HP_N_E1, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4,
+                       N_IM = 5, W_I1 = W_IM + N_IM, W_I2 = W_I1 + 1, W_I3 = W_I2 + 1;
+  static constexpr int NT = (W_I3 + 1) * 32;
+  static constexpr int E1_CHUNKS = (N1 / 16) / (N_E1 / 4);   // 16-channel chunks per E1 warp
   static constexpr int IM_THREADS = N_IM * 32;
   // shared memory carve-up (bytes).  The H8 ring lies ABOVE the oct ring: one K-step pairs the
   // dx = 8 chunk of O with the first chunk of H8 through a positive leading-dimension offset.
@@ -72,7 +76,9 @@ struct Cfg {
   static constexpr int TOTAL = oQs + 2 * M * QP * 4;
   static constexpr size_t SMEM_BYTES = (size_t)TOTAL;
   // tensor memory columns (+ size * (b & 1)):
-  //   D1: [0,64) hi.w_hi, [64,128) corrections  ->  A2: [0,32) hi pairs, [64,96) lo pairs
+  //   D1: [0,64) hi.w_hi, [64,128) corrections  ->  A2: hi pairs of channels 16g..16g+15 at
+  //       a2col(g) = 32*(g/2) + 8*(g%2), lo pairs at 64 + a2col(g): inside the columns the SAME
+  //       E1 warp has already read, whether 4 or 8 warps share the 64 channels
   //   D2: [0,32), [32,64)                       ->  A3: [0,16) hi pairs, [32,48) lo pairs
   //   D3: [0,32), [32,64) (25 taps of 32 used)
   static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
@@ -139,6 +145,9 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t v[8]) {
       : "memory");
 }
 
+#ifdef PL_TRACE
+using fused_pl::pl_trace;
+#endif
 using fused_pl::BatchExt;
 using fused_pl::elect_one;
 using fused_pl::tmem_ld16_nowait;
@@ -147,36 +156,19 @@ using fused_ws::mbar_arrive;
 using fused_ws::named_bar_sync;
 
 // ---------------------------------------------------------------------------- prepare --------
-// Scans the input for the domain check and derives the scales from the parameters.  ws[0]: max
-// of the |x| bit patterns, ws[1]: finished-CTA counter (both left at zero for the next launch).
+// Derives the scales from the parameters (one CTA).  The domain check of the INPUT is done by
+// the plane producers of the main kernel, which see every pixel anyway: the first |x| >= 64 (or
+// NaN) clears `ok`, and the TF32 kernel launched behind redoes the launch.
+constexpr float kInMax = 64.f;
 __device__ __forceinline__ float pow2_scale(float bound) {   // 2^14 / pow2ceil(bound)
   if (!(bound > 0.f) || !(bound < 1e30f)) return 1.f;
   int e;
   frexpf(bound, &e);                 // bound = f * 2^e, f in [0.5, 1)
   return ldexpf(1.f, 14 - e);
 }
-__global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict__ in, size_t n,
-                                                         fused::Args a, Scales* sc, unsigned* ws) {
-  __shared__ unsigned red_u[8];
+__global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* sc) {
   __shared__ float red_f[8];
-  __shared__ bool last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned m = 0;
-  for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256)
-    m = max(m, __float_as_uint(fabsf(__ldg(in + i))));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) red_u[warp] = m;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 8; w++) m = max(m, red_u[w]);
-    atomicMax(&ws[0], m);
-    __threadfence();
-    last = atomicAdd(&ws[1], 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
   auto block_max = [&](float v) -> float {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -187,7 +179,6 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict
     for (int w = 1; w < 8; w++) r = fmaxf(r, red_f[w]);
     return r;
   };
-  constexpr float kInMax = 64.f;
   float v = 0.f;
   for (int i = tid; i < Cfg::F1 * Cfg::F1 * Cfg::N1; i += 256) v = fmaxf(v, fabsf(__ldg(a.pw1 + i)));
   const float m1 = block_max(v);
@@ -225,11 +216,9 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict
     s.c3 = 1.f / (s.s2 * s.sw3);
     s.inv_s1 = 1.f / s.s1;
     s.inv_s2 = 1.f / s.s2;
-    const unsigned mx = atomicMax(&ws[0], 0u);
-    s.ok = (mx < __float_as_uint(kInMax * 0.999f) && bound2 < 1e30f) ? 1 : 0;
+    // non-finite parameters: leave the launch to the TF32 kernel
+    s.ok = (bound2 < 1e30f && m3 < 1e30f) ? 1 : 0;
     *sc = s;
-    ws[0] = 0;
-    ws[1] = 0;
   }
 }
 
@@ -237,12 +226,12 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict
 template <bool BATCH>
 __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Args a, int rpc,
                                                                       BatchExt bx,
-                                                                      const Scales* scales) {
+                                                                      Scales* scales) {
   using C = Cfg;
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Scales sc = *scales;
-  if (!sc.ok) return;   // input outside the FP16 domain: the TF32 kernel behind us runs instead
+  if (!sc.ok) return;   // non-finite parameters: the TF32 kernel behind us runs instead
   __half* sW1 = reinterpret_cast<__half*>(smem_raw + C::oW1);
   __half* sW2 = reinterpret_cast<__half*>(smem_raw + C::oW2);
   __half* sW3 = reinterpret_cast<__half*>(smem_raw + C::oW3);
@@ -340,7 +329,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         v = (boff[e] >= 0 && gy < a.h) ? __ldg(img + boff[e] + (long long)gy * bx.pw) : 0.f;
       else
         v = (active && gy < a.h && gx + e < a.w) ? __ldg(img + (size_t)gy * a.w + gx + e) : 0.f;
-      return v * sc.sx;
+      return v;
+    };
+    // the domain check happens where a value is consumed, never where it is loaded: the loads
+    // of the next two rows stay in flight across a tile (HBM latency > one tile period)
+    auto in_domain = [&](float x) {
+      if (!(fabsf(x) < kInMax * 0.999f)) scales->ok = 0;   // outside the FP16 domain (or NaN)
     };
     unsigned short hh[7], hl[7];   // rows r-7 .. r-1 of this column
     {
@@ -349,8 +343,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       for (int r = 0; r < C::F1 - 1; r++) pv[r] = ld(r, 0);
       unsigned short h7, l7;
 #pragma unroll
-      for (int r = 0; r < C::F1 - 2; r++) split_h(pv[r], hh[r], hl[r]);
-      split_h(pv[C::F1 - 2], h7, l7);
+      for (int r = 0; r < C::F1 - 2; r++) {
+        in_domain(pv[r]);
+        split_h(pv[r] * sc.sx, hh[r], hl[r]);
+      }
+      in_domain(pv[C::F1 - 2]);
+      split_h(pv[C::F1 - 2] * sc.sx, h7, l7);
       if (active) {   // O(0) = rows 0..7
         *reinterpret_cast<uint4*>(pOh) = make_uint4(pack2(hh[0], hh[1]), pack2(hh[2], hh[3]),
                                                     pack2(hh[4], hh[5]), pack2(hh[6], h7));
@@ -361,16 +359,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       for (int r = 0; r < 6; r++) { hh[r] = hh[r + 1]; hl[r] = hl[r + 1]; }
       hh[6] = h7; hl[6] = l7;
     }
-    float v[8];
+    float v[8], nv[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = ld(C::F1 - 1, e);
-    for (int b = 0; b < n_tiles; b++) {
-      float nv[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) nv[e] = (b + 1 < n_tiles) ? ld(b + C::F1, e) : 0.f;
+    for (int e = 0; e < 8; e++) nv[e] = n_tiles > 1 ? ld(C::F1, e) : 0.f;
+    for (int b = 0; b < n_tiles; b++) {
+      float nnv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) nnv[e] = (b + 2 < n_tiles) ? ld(b + C::F1 + 1, e) : 0.f;
       uint32_t ph[4], pl[4];
 #pragma unroll
-      for (int e = 0; e < 4; e++) split_h2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
+      for (int e = 0; e < 8; e++) in_domain(v[e]);
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        split_h2(v[2 * e] * sc.sx, v[2 * e + 1] * sc.sx, ph[e], pl[e]);
       const unsigned short nh = (unsigned short)(ph[0] & 0xffffu), nl = (unsigned short)(pl[0] & 0xffffu);
       // H8(b+8) replaces H8(b+4) (MMA-1(b-4)), O(b+1) replaces O(b-3) (MMA-1(b-3))
       if (b >= 3) mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1));
@@ -388,8 +391,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       hh[6] = nh; hl[6] = nl;
       fence_proxy_async();
       mbar_arrive(&p_full[b & 3]);
+      if (warp == C::W_IM) PL_EV(b, 12)
 #pragma unroll
-      for (int e = 0; e < 8; e++) v[e] = nv[e];
+      for (int e = 0; e < 8; e++) { v[e] = nv[e]; nv[e] = nnv[e]; }
     }
   } else if (warp == C::W_I1) {
     // ============================ I1: layer-1 MMA issuer ===================================
@@ -410,6 +414,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
       const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
       const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * C::PB;
+      PL_EV(t, 0)
       if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < C::KS1; s++) {
@@ -427,6 +432,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         mma_commit(&p_free[t & 3]);
       }
       __syncwarp();
+      PL_EV(t, 1)
     }
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
@@ -440,15 +446,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tcgen05_fence_after();
       const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
       const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      PL_EV(t, 4)
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K2 / 16; ks++) {
-          mma_f16_ts(d2, a2 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_f16_ts(d2 + C::N2, a2 + C::N1 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          const uint32_t col = 32u * (ks >> 1) + 8u * (ks & 1);   // a2col(ks)
+          mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_f16_ts(d2 + C::N2, a2 + C::N1 + col, wdesc + 16 * ks, idesc_lo, 1);
         }
         mma_commit(&bar2[t & 1]);
       }
       __syncwarp();
+      PL_EV(t, 5)
     }
   } else if (warp == C::W_I3) {
     // ============================ I3: layer-3 tap-GEMM issuer (A3 in TMEM) =================
@@ -461,6 +470,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tcgen05_fence_after();
       const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
       const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+      PL_EV(t, 8)
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K3 / 16; ks++) {
@@ -470,12 +480,15 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         mma_commit(&bar3[t & 1]);
       }
       __syncwarp();
+      PL_EV(t, 9)
     }
   } else if (warp < C::W_E1 + C::N_E1) {
     // ============================ E1: A2 = split(relu(out1) * s1), in place ================
-    // chunk g (16 channels) reads D1 columns [16g,16g+16) and [64+16g, ..) and then writes the
-    // hi pairs to [8g, 8g+8) and the lo pairs to [64+8g, ..): columns already consumed
+    // warp w: TMEM lane quarter w&3, chunks g0 .. g0+E1_CHUNKS-1 of 16 channels.  Chunk g reads
+    // D1 columns [16g,16g+16) and [64+16g, ..), then writes its hi pairs to a2col(g) and its lo
+    // pairs to 64 + a2col(g): columns this warp has consumed
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int g0 = (warp >> 2) * C::E1_CHUNKS;
     float* o1 = nullptr;
     if (BATCH && bx.out1) {
       const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
@@ -486,10 +499,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
+      if (warp == 0) PL_EV(b, 2)
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
 #pragma unroll 1
-      for (int g = 0; g < C::N1 / 16; g++) {
+      for (int g = g0; g < g0 + C::E1_CHUNKS; g++) {
         float va[16], vb[16];
         tmem_ld16_nowait(d1 + g * 16, va);              // hi.w_hi
         tmem_ld16_nowait(d1 + C::N1 + g * 16, vb);      // (hi.w_lo + lo.w_hi) * 2048
@@ -501,8 +515,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
           act[j] = fmaxf(fmaf(fmaf(vb[j], 1.f / 2048.f, va[j]), sc.c1s, sB1[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-        tmem_st8u(d1 + g * 8, hi);
-        tmem_st8u(d1 + C::N1 + g * 8, lo);
+        const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
+        tmem_st8u(d1 + col, hi);
+        tmem_st8u(d1 + C::N1 + col, lo);
         if (BATCH && o1) {
           float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
 #pragma unroll
@@ -514,6 +529,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a2_full[b & 1]);
+      if (warp == 0) PL_EV(b, 3)
     }
   } else if (warp < C::W_E3) {
     // ============================ E2: A3 = split(relu(out2) * s2), in place ================
@@ -528,6 +544,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
+      if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
       const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
 #pragma unroll
@@ -556,6 +573,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a3_full[b & 1]);
+      if (warp == C::W_E2) PL_EV(b, 7)
     }
   } else if (warp < C::W_IM) {
     // ============================ E3: Q row -> smem, 25-term gather -> out3 ================
@@ -574,6 +592,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-3(b) done
+      if (warp == C::W_E3) PL_EV(b, 10)
       tcgen05_fence_after();
       const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
       float v[32], w[32];
@@ -611,12 +630,24 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       acc3 = r[0];
       if (b >= C::F3 - 1 && live)
         dst[o3 + (size_t)(b - (C::F3 - 1)) * o3_row] = done + b3;
+      if (warp == C::W_E3) PL_EV(b, 11)
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+#ifdef PL_TRACE
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles > 108) {
+    const long long t0 = pl_trace[0][12];
+    for (int t = 0; t < 8; t++)
+      printf("tile %d: IM %6lld | I1 %6lld..%6lld | E1 %6lld..%6lld | I2 %6lld..%6lld | E2 %6lld..%6lld | I3 %6lld..%6lld | E3 %6lld..%6lld\n",
+             100 + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
+             pl_trace[t][3] - t0, pl_trace[t][4] - t0, pl_trace[t][5] - t0, pl_trace[t][6] - t0,
+             pl_trace[t][7] - t0, pl_trace[t][8] - t0, pl_trace[t][9] - t0, pl_trace[t][10] - t0,
+             pl_trace[t][11] - t0);
+  }
+#endif
 }
 
 inline int configure() {
@@ -654,7 +685,8 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
   unsigned* ws;
   SRCNN_TRY(scale_slot(ctx, &sc, &ws));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
-  hp_prepare_kernel<<<2 * sms, 256, 0, ctx->stream>>>(a.in, (size_t)S * a.w * a.h, a, sc, ws);
+  (void)ws;
+  hp_prepare_kernel<<<1, 256, 0, ctx->stream>>>(a, sc);
   BatchExt bx{};
   bx.gate = &sc->ok;
   if (batch) {

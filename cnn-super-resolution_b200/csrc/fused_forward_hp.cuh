@@ -502,17 +502,22 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       if (warp == 0) PL_EV(b, 2)
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
-#pragma unroll 1
-      for (int g = g0; g < g0 + C::E1_CHUNKS; g++) {
-        float va[16], vb[16];
-        tmem_ld16_nowait(d1 + g * 16, va);              // hi.w_hi
-        tmem_ld16_nowait(d1 + C::N1 + g * 16, vb);      // (hi.w_lo + lo.w_hi) * 2048
-        tmem_ld_wait();
+      // all loads of this warp's chunks first (one TMEM round trip), then the conversions
+      float va[C::E1_CHUNKS][16], vb[C::E1_CHUNKS][16];
+#pragma unroll
+      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
+        tmem_ld16_nowait(d1 + (g0 + gl) * 16, va[gl]);
+        tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
+        const int g = g0 + gl;
         uint32_t hi[8], lo[8];
         float act[16];
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[j], 1.f / 2048.f, va[j]), sc.c1s, sB1[g * 16 + j]), 0.f);
+          act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c1s, sB1[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
@@ -547,17 +552,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
       const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
+      // all loads first (one TMEM round trip), then the conversions
+      float va[2][16], vb[2][16];
 #pragma unroll
-      for (int g = 0; g < C::N2 / 16; g++) {
-        float va[16], vb[16];
-        tmem_ld16_nowait(d2 + g * 16, va);
-        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb);
-        tmem_ld_wait();
+      for (int g = 0; g < 2; g++) {
+        tmem_ld16_nowait(d2 + g * 16, va[g]);
+        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb[g]);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
         uint32_t hi[8], lo[8];
         float act[16];
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[j], 1.f / 2048.f, va[j]), sc.c2s, sB2[g * 16 + j]), 0.f);
+          act[j] = fmaxf(fmaf(fmaf(vb[g][j], 1.f / 2048.f, va[g][j]), sc.c2s, sB2[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         tmem_st8u(d2 + g * 8, hi);
@@ -605,7 +614,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
-      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]) * sc.c3;
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]);
       named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
       float r[C::F3];
       if (x < C::OW3) {
@@ -628,8 +637,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       acc1 = acc2 + r[2];
       acc2 = acc3 + r[1];
       acc3 = r[0];
-      if (b >= C::F3 - 1 && live)
-        dst[o3 + (size_t)(b - (C::F3 - 1)) * o3_row] = done + b3;
+      if (b >= C::F3 - 1 && live)   // the scale of the tap GEMM is applied once, to the sum
+        dst[o3 + (size_t)(b - (C::F3 - 1)) * o3_row] = fmaf(done, sc.c3, b3);
       if (warp == C::W_E3) PL_EV(b, 11)
     }
   }

@@ -118,6 +118,11 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
   return fused::launch(ctx, n1, n2, a, S);
 }
 
+// kernels one fused forward call launches: the FP16-split path is prepare + main + gated TF32
+inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
+  return ctx->fused_impl == 4 && fused_hp::supported(n1, n2, f1, f2, f3) ? 3 : 1;
+}
+
 inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
   return ctx->fused_impl >= 3 && fused_pl::supported(n1, n2, f1, f2, f3);
 }

@@ -545,7 +545,7 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
     SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
     SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
     SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
-    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
     SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin, pout, w1,
                                   b1, w2, b2, w3, b3, in_w, in_h, S));
     return check_launch("forward_fused");
@@ -630,7 +630,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaMemcpyAsync(din, host_in + (size_t)out_row0 * in_w, in_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
     {
-      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
       SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, din, dout,
                                     w1, b1, w2, b2, w3, b3, in_w, band_in_h, 1));
       SRCNN_TRY(check_launch("forward_fused"));
@@ -659,7 +659,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     cudaStream_t cs = (i & 1) ? ctx->compute2 : main_stream;
     SRCNN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_in[i], 0));
     {
-      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
       ctx->stream = cs;   // the launch helpers use the context stream
       rc = fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
                                din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2, b2,
@@ -755,7 +755,7 @@ int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
   SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
   SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
   SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
-  LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED);
+  LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
   const int rc = fast::forward_train_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin,
                                            o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S);
   if (rc < 0) return rc;

@@ -42,9 +42,9 @@ FWD_FLOP_C3 = 2 * ((IMG - 8) ** 2 * 81 * 64 + (IMG - 8) ** 2 * 64 * 32 + (IMG - 
 FUSED_BYTES_C3 = 4 * (IMG * IMG + (IMG - PAD) ** 2)
 TRAIN_FLOP_PER_PATCH = 23.05e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused launch on C3 (ncu --set full,
-# profiles/r1k_fused_pl_ncu_summary.txt): 67.7 MB read (the input, once) + 28.6 MB written back
+# profiles/r1n_fused_hp_ncu_summary.txt): 67.2 MB read (the input, once) + 26.6 MB written back
 # during the launch (the rest of the 66.7 MB output is still dirty in the 126 MB L2 at exit)
-TRAFFIC_NCU_BYTES = 96.2e6
+TRAFFIC_NCU_BYTES = 93.8e6
 
 
 def peaks():
@@ -329,24 +329,30 @@ def run_ours(args, rank, world, local_rank):
     fp32_peak = 148 * 128 * 2 * sm_clock * 1e6 / 1e12
     achieved_gbs = alg_bytes / (inf_ms / 1e3) / 1e9
     achieved_tf = alg_flop / (inf_ms / 1e3) / 1e12
-    use_tc = fused and os.environ.get("SRCNN_FUSED_IMPL", "tc") != "simt"
-    # Dominant kernel of the primary workload = the fused forward launch (one per step and
-    # rank; its launch duration IS the step time measured above with CUDA events).  It moves
-    # 8 B/pixel, so it is compute-bound: all three layers run on the tensor cores as 3xTF32
-    # (layer 3 as a tap GEMM + 25-term gather) -- three TF32 products per FP32 product, each
-    # at half the bf16 rate, i.e. the precision the path needs costs 6x a bf16 MMA.
+    impl = os.environ.get("SRCNN_FUSED_IMPL", "hp")
+    use_tc = fused and impl != "simt"
+    # Dominant kernel of the primary workload = the fused forward launch (its duration is the
+    # step time measured above with CUDA events, minus two ~3 us helper launches).  It moves
+    # 8 B/pixel, so it is compute-bound: all three layers run on the tensor cores (layer 3 as a
+    # tap GEMM + 25-term gather) with error-compensated split operands, because the 1e-4
+    # tolerance rules out plain 16/19-bit inputs: every FP32 product costs THREE tensor-core
+    # products -- FP16 halves at the bf16 rate (default kernel), or TF32 at half that rate.
     if use_tc:
+        split = 6.0 if impl in ("pl", "ws", "tc") else 3.0
         roofline = {
-            "kernel": "forward_fused_pl_kernel (tcgen05 3xTF32 on all three layers, plane operands)",
+            "kernel": ("forward_fused_hp_kernel (tcgen05 kind::f16, FP16-split operands, all "
+                       "three layers)" if split == 3.0 else
+                       "forward_fused_%s_kernel (tcgen05 3xTF32, all three layers)" % impl),
             "bound": "tensor", "achieved": achieved_tf, "peak": bf16_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / bf16_peak, "traffic": TRAFFIC_NCU_BYTES * frac_img,
             "peak_kind": peak_kind + " dense bf16 (MEASURED_PEAKS.json)",
             "algorithmic_flop_per_launch": alg_flop,
-            "precision_ceiling_tflops": bf16_peak / 6.0,
-            "frac_of_precision_ceiling": achieved_tf / (bf16_peak / 6.0),
-            "note": "algorithmic FP32 FLOPs / launch time against the measured bf16 peak; "
-                    "3xTF32 issues 3 TF32 MMAs (half bf16 rate) per product, so peak/6 is "
-                    "the ceiling at the precision the 1e-4 tolerance requires",
+            "precision_ceiling_tflops": bf16_peak / split,
+            "frac_of_precision_ceiling": achieved_tf / (bf16_peak / split),
+            "note": "algorithmic FP32 FLOPs / launch time against the measured bf16 peak; the "
+                    "split-operand scheme the tolerance requires issues 3 tensor-core products "
+                    "per FP32 product (at the fp16/bf16 rate for the FP16-split kernel, at half "
+                    "of it for 3xTF32), so peak/%d is the ceiling at this precision" % split,
             "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": hbm_peak,
                     "frac": achieved_gbs / hbm_peak,
                     "algorithmic_bytes_per_launch": alg_bytes},

@@ -99,10 +99,11 @@ inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {
   return fused::supported(n1, n2, f1, f2, f3);
 }
 
+// `scales`: fused_hp::Scales block shared by a series of launches (or null)
 inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* in,
                          float* out, const float* w1, const float* b1, const float* w2,
                          const float* b2, const float* w3, const float* b3, int in_w, int in_h,
-                         int S) {
+                         int S, fused_hp::Scales* scales = nullptr) {
   if (!fused::supported(n1, n2, f1, f2, f3))
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
@@ -110,7 +111,8 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
   if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
     // batches of small samples (validation patches) go through the virtual-image variant
     const bool as_batch = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30);
-    if (ctx->fused_impl == 4) return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr);
+    if (ctx->fused_impl == 4)
+      return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr, scales);
     if (ctx->fused_impl == 3 && as_batch) return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
     if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
     return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
@@ -121,6 +123,17 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
 // kernels one fused forward call launches: the FP16-split path is prepare + main + gated TF32
 inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
   return ctx->fused_impl == 4 && fused_hp::supported(n1, n2, f1, f2, f3) ? 3 : 1;
+}
+
+// scales for a series of forward_fused launches with the same parameters (null when the
+// selected kernel needs none)
+inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* w1,
+                         const float* b1, const float* w2, const float* b2, const float* w3,
+                         const float* b3, fused_hp::Scales** out) {
+  *out = nullptr;
+  if (ctx->fused_impl != 4 || !fused_hp::supported(n1, n2, f1, f2, f3)) return SRCNN_OK;
+  fused::Args a{nullptr, nullptr, w1, b1, w2, b2, w3, b3, 0, 0, 0, 0};
+  return fused_hp::prepare(ctx, a, out);
 }
 
 inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {

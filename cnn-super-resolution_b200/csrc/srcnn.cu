@@ -639,6 +639,11 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     return SRCNN_OK;
   }
+  // one set of operand scales for all sub-bands (computed on the context stream, before the
+  // event the side streams wait for)
+  fused_hp::Scales* scales = nullptr;
+  SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
+                                b3, &scales));
   // order the side streams after whatever the context stream was doing with the buffers
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
@@ -663,7 +668,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
       ctx->stream = cs;   // the launch helpers use the context stream
       rc = fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
                                din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2, b2,
-                               w3, b3, in_w, r1 - r0 + halo, 1);
+                               w3, b3, in_w, r1 - r0 + halo, 1, scales);
       ctx->stream = main_stream;
       if (rc == SRCNN_OK) rc = check_launch("forward_fused");
     }

@@ -446,6 +446,53 @@ def test_inference_vs_oracle(ctx, port, cfg):
         ctx.release(m)
 
 
+def _fused_vs_oracle(ctx, port, params, x, w, h):
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    on = NetState(n1, n2, f1, f2, f3, params)
+    _, _, e3 = port.net_forward(on, x, w, h, 1)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    mi, mo = ctx.upload(x), ctx.alloc(4 * w3 * h3)
+    net.forward_fused(mi, mo, w, h, 1)
+    got = ctx.read(mo, (1, h3, w3))
+    ctx.release(mi)
+    ctx.release(mo)
+    return got, e3
+
+
+def test_fused_fp16_domain_fallback(ctx, port):
+    """The default fused kernel splits operands into FP16 halves with scales that assume
+    |input| < 64.  Inputs outside that domain must still give the reference's result: the
+    kernel flags them on the device and the 3xTF32 kernel launched behind it redoes the launch.
+    Also: inputs near the domain edge, and parameters far from O(1), stay within a RELATIVE
+    1e-5 of the oracle (the absolute 1e-4 of north_star is for luma-range data)."""
+    w, h = 200, 90
+    rng = np.random.default_rng(64)
+    params = make_params(rng, 64, 32, 9, 1, 5)
+    x = luma_image(rng, h, w)
+
+    def close(got, exp):
+        scale = max(1.0, float(np.abs(exp).max()))
+        assert np.isfinite(got).all()
+        assert float(np.abs(got - exp).max()) <= 1e-5 * scale + 1e-6
+
+    # one pixel far outside the domain, in the last strip / last rows
+    x1 = x.copy()
+    x1[h - 1, w - 1] = 1000.0
+    close(*_fused_vs_oracle(ctx, port, params, x1, w, h))
+    # everything outside the domain
+    close(*_fused_vs_oracle(ctx, port, params, (x * 400.0 - 100.0).astype(np.float32), w, h))
+    # inside the domain but 60x the luma range (FP16 path, large activations)
+    close(*_fused_vs_oracle(ctx, port, params, (x * 120.0 - 60.0).astype(np.float32), w, h))
+    # the reference's own initialisation scale, N(0, 0.001) (example_config.json:12-29), and
+    # large parameters
+    for k in (1e-3 / 0.11, 30.0):
+        p2 = {name: (v * k).astype(np.float32) for name, v in params.items()}
+        got, exp = _fused_vs_oracle(ctx, port, p2, x, w, h)
+        assert np.isfinite(got).all()
+        assert float(np.abs(got - exp).max()) <= 1e-5 * float(np.abs(exp).max()) + 1e-9
+
+
 def test_full_size_4096_properties(ctx, port):
     """BASELINE config C3 (4096x4096, 9-1-5 64/32) at full size, through size-independent
     properties: (1) random 48x48 output windows equal the oracle run on just their receptive

@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "context.cuh"
 #include "fused_forward.cuh"
 #include "fused_forward_pl.cuh"
@@ -34,15 +36,6 @@
 
 namespace srcnn {
 namespace fused_hp {
-
-struct Scales {
-  float sx, sw1, sw2, sw3, s1, s2;
-  float c1s;      // s1 / (sx * sw1): D1 -> out1 * s1
-  float c2s;      // s2 / (s1 * sw2): D2 -> out2 * s2
-  float c3;       // 1 / (s2 * sw3):  D3 -> Q
-  float inv_s1, inv_s2;
-  int ok;         // 1: the input is inside the FP16 domain, this kernel runs; 0: the TF32 one
-};
 
 struct Cfg {
   static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
@@ -85,6 +78,25 @@ struct Cfg {
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr int BAR_E3 = 1;
 };
+
+struct ScaleVals {
+  float sx, sw1, sw2, sw3, s1, s2;
+  float c1s;      // s1 / (sx * sw1): D1 -> out1 * s1
+  float c2s;      // s2 / (s1 * sw2): D2 -> out2 * s2
+  float c3;       // 1 / (s2 * sw3):  D3 -> Q
+  float inv_s1, inv_s2;
+  int ok;         // 1: the input is inside the FP16 domain, this kernel runs; 0: the TF32 one
+};
+// what hp_prepare_kernel leaves for the main kernel: the scales and the ready-made shared-memory
+// image of the B operands (scaled, split, in the canonical K-major layout) and scaled biases, so
+// that a CTA's prologue is a 37 KB copy instead of 24 576 scattered conversions -- the CTAs of a
+// training chunk or of a multi-GPU row band only live for 25..130 tiles
+struct Scales {
+  ScaleVals v;
+  int pad_[4 - (sizeof(ScaleVals) / 4) % 4];
+  unsigned char wimg[Cfg::oQs - Cfg::oW1];
+};
+static_assert(offsetof(Scales, wimg) % 16 == 0 && sizeof(Scales) % 16 == 0, "uint4 copies");
 
 // K-major canonical layout for 16-bit elements: core matrix = 8 rows x 16 bytes (8 halves);
 // returns the offset in halves of (row r, element k) of a [rows][K] operand
@@ -156,7 +168,8 @@ using fused_ws::mbar_arrive;
 using fused_ws::named_bar_sync;
 
 // ---------------------------------------------------------------------------- prepare --------
-// Derives the scales from the parameters (one CTA).  The domain check of the INPUT is done by
+// Derives the scales from the parameters (every CTA of a small grid, redundantly) and packs the
+// operand image.  The domain check of the INPUT is done by
 // the plane producers of the main kernel, which see every pixel anyway: the first |x| >= 64 (or
 // NaN) clears `ok`, and the TF32 kernel launched behind redoes the launch.
 constexpr float kInMax = 64.f;
@@ -222,8 +235,9 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
     v = (s0 + s1) * bound1 + b2v;
   }
   const float bound2 = block_max(v);
+  __shared__ ScaleVals sv;
   if (tid == 0) {
-    Scales s;
+    ScaleVals s;
     s.sx = 512.f;   // 64 * 512 = 2^15
     s.sw1 = pow2_scale(m1);
     s.sw2 = pow2_scale(m2);
@@ -237,8 +251,40 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
     s.inv_s2 = 1.f / s.s2;
     // non-finite parameters: leave the launch to the TF32 kernel
     s.ok = (bound2 < 1e30f && m3 < 1e30f) ? 1 : 0;
-    *sc = s;
+    sv = s;
+    if (blockIdx.x == 0) sc->v = s;
   }
+  __syncthreads();
+  // ---- the shared-memory image of the B operands: every CTA of the grid packs its share ----
+  using C = Cfg;
+  __half* gW1 = reinterpret_cast<__half*>(sc->wimg);
+  __half* gW2 = reinterpret_cast<__half*>(sc->wimg + (C::oW2 - C::oW1));
+  __half* gW3 = reinterpret_cast<__half*>(sc->wimg + (C::oW3 - C::oW1));
+  float* gB1 = reinterpret_cast<float*>(sc->wimg + (C::oB1 - C::oW1));
+  float* gB2 = reinterpret_cast<float*>(sc->wimg + (C::oB2 - C::oW1));
+  const int gtid = blockIdx.x * 256 + tid, gn = gridDim.x * 256;
+  for (int i = gtid; i < 2 * C::N1 * C::K1; i += gn) {
+    const int n = i / C::K1, k = i % C::K1;
+    const int t = tap16(k >> 4, (k >> 3) & 1, k & 7);
+    unsigned short hi, lo;
+    split_h(t >= 0 ? __ldg(a.pw1 + t * C::N1 + (n & (C::N1 - 1))) * sv.sw1 : 0.f, hi, lo);
+    gW1[kmajor16(n, k, C::K1)] = __ushort_as_half(n < C::N1 ? hi : lo);
+  }
+  for (int i = gtid; i < 2 * C::N2 * C::K2; i += gn) {
+    const int n = i / C::K2, k = i % C::K2;
+    unsigned short hi, lo;
+    split_h(__ldg(a.pw2 + k * C::N2 + (n & (C::N2 - 1))) * sv.sw2, hi, lo);
+    gW2[kmajor16(n, k, C::K2)] = __ushort_as_half(n < C::N2 ? hi : lo);
+  }
+  for (int i = gtid; i < 2 * C::NT3 * C::K3; i += gn) {
+    const int n = i / C::K3, k = i % C::K3;   // n & 31 = tap dy*5+dx, k = channel
+    const int tap = n & (C::NT3 - 1);
+    unsigned short hi, lo;
+    split_h(tap < C::QP ? __ldg(a.pw3 + tap * C::N2 + k) * sv.sw3 : 0.f, hi, lo);
+    gW3[kmajor16(n, k, C::K3)] = __ushort_as_half(n < C::NT3 ? hi : lo);
+  }
+  for (int i = gtid; i < C::N1; i += gn) gB1[i] = __ldg(a.pb1 + i) * sv.s1;
+  for (int i = gtid; i < C::N2; i += gn) gB2[i] = __ldg(a.pb2 + i) * sv.s2;
 }
 
 // ---------------------------------------------------------------------------- main kernel ----
@@ -249,7 +295,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   using C = Cfg;
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const Scales sc = *scales;
+  const ScaleVals sc = scales->v;
   if (!sc.ok) return;   // non-finite parameters: the TF32 kernel behind us runs instead
   __half* sW1 = reinterpret_cast<__half*>(smem_raw + C::oW1);
   __half* sW2 = reinterpret_cast<__half*>(smem_raw + C::oW2);
@@ -267,29 +313,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   const float* img = BATCH ? a.in : a.in + (size_t)blockIdx.z * a.w * a.h;
   float* dst = BATCH ? a.out : a.out + (size_t)blockIdx.z * a.w3 * a.h3;
 
-  // ---- stage parameters: B operands [n][k] canonical (16-bit), hi rows then lo rows ----------
-  for (int i = tid; i < 2 * C::N1 * C::K1; i += C::NT) {
-    const int n = i / C::K1, k = i % C::K1;
-    const int t = tap16(k >> 4, (k >> 3) & 1, k & 7);
-    unsigned short hi, lo;
-    split_h(t >= 0 ? __ldg(a.pw1 + t * C::N1 + (n & (C::N1 - 1))) * sc.sw1 : 0.f, hi, lo);
-    sW1[kmajor16(n, k, C::K1)] = __ushort_as_half(n < C::N1 ? hi : lo);
+  // ---- B operands and scaled biases: the image hp_prepare_kernel packed ---------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(scales->wimg);
+    uint4* dstw = reinterpret_cast<uint4*>(smem_raw + C::oW1);
+    for (int i = tid; i < (C::oQs - C::oW1) / 16; i += C::NT) dstw[i] = __ldg(src + i);
   }
-  for (int i = tid; i < 2 * C::N2 * C::K2; i += C::NT) {
-    const int n = i / C::K2, k = i % C::K2;
-    unsigned short hi, lo;
-    split_h(__ldg(a.pw2 + k * C::N2 + (n & (C::N2 - 1))) * sc.sw2, hi, lo);
-    sW2[kmajor16(n, k, C::K2)] = __ushort_as_half(n < C::N2 ? hi : lo);
-  }
-  for (int i = tid; i < 2 * C::NT3 * C::K3; i += C::NT) {
-    const int n = i / C::K3, k = i % C::K3;   // n & 31 = tap dy*5+dx, k = channel
-    const int tap = n & (C::NT3 - 1);
-    unsigned short hi, lo;
-    split_h(tap < C::QP ? __ldg(a.pw3 + tap * C::N2 + k) * sc.sw3 : 0.f, hi, lo);
-    sW3[kmajor16(n, k, C::K3)] = __ushort_as_half(n < C::NT3 ? hi : lo);
-  }
-  for (int i = tid; i < C::N1; i += C::NT) sB1[i] = __ldg(a.pb1 + i) * sc.s1;
-  for (int i = tid; i < C::N2; i += C::NT) sB2[i] = __ldg(a.pb2 + i) * sc.s2;
   // pad entries of the planes are read by the tensor core (times a zero weight): keep them finite
   for (int i = tid; i < 2 * (C::RO + C::RH) * C::PB / 4; i += C::NT)
     reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
@@ -353,7 +382,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     // the domain check happens where a value is consumed, never where it is loaded: the loads
     // of the next two rows stay in flight across a tile (HBM latency > one tile period)
     auto in_domain = [&](float x) {
-      if (!(fabsf(x) < kInMax * 0.999f)) scales->ok = 0;   // outside the FP16 domain (or NaN)
+      if (!(fabsf(x) < kInMax * 0.999f)) scales->v.ok = 0;   // outside the FP16 domain (or NaN)
     };
     unsigned short hh[7], hl[7];   // rows r-7 .. r-1 of this column
     {
@@ -710,7 +739,7 @@ inline int scale_slot(srcnn_ctx* ctx, Scales** sc, unsigned** ws) {
 inline int prepare(srcnn_ctx* ctx, const fused::Args& a, Scales** out) {
   unsigned* ws;
   SRCNN_TRY(scale_slot(ctx, out, &ws));
-  hp_prepare_kernel<<<1, 256, 0, ctx->stream>>>(a, *out);
+  hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, *out);
   return SRCNN_OK;
 }
 
@@ -723,7 +752,7 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
   if (!sc) SRCNN_TRY(prepare(ctx, a, &sc));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   BatchExt bx{};
-  bx.gate = &sc->ok;
+  bx.gate = &sc->v.ok;
   if (batch) {
     fused::Args v = a;
     const int pad = Cfg::F1 + Cfg::F3 - 2;

@@ -79,6 +79,7 @@ struct srcnn_ctx {
   // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
   // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes (3xTF32), 4 planes (FP16 split)
   int fused_impl = 4;
+  bool deltas_tc = true;              // f=1 deltas on the tensor cores (deltas_tc.cuh)
   void* hp_scales = nullptr;          // ring of fused_hp::Scales blocks + their work words
   unsigned long long hp_next = 0;
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging

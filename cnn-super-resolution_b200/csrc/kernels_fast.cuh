@@ -12,6 +12,7 @@
 #include "fused_forward_pl.cuh"
 #include "fused_forward_hp.cuh"
 #include "train_kernels.cuh"
+#include "deltas_tc.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,8 @@ inline int configure(srcnn_ctx* ctx) {
   if (impl && std::strcmp(impl, "simt") == 0) ctx->fused_impl = 0;
   if (impl && std::strcmp(impl, "tc") == 0) ctx->fused_impl = 1;  // lockstep tcgen05
   if (impl && std::strcmp(impl, "ws") == 0) ctx->fused_impl = 2;  // warp-specialised, im2col
+  const char* d1 = std::getenv("SRCNN_D1_IMPL");   // "simt": FP32 kernel for the f=1 deltas
+  ctx->deltas_tc = !(d1 && std::strcmp(d1, "simt") == 0);
   return SRCNN_OK;
 }
 
@@ -84,6 +87,9 @@ inline bool forward_layer(srcnn_ctx* ctx, const float* in, float* out, const flo
 
 inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
                    const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
+  if (ctx->deltas_tc &&
+      d1tc::f1_deltas_tc(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S))
+    return true;
   if (train::f1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S)) return true;
   return train::n1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S);
 }

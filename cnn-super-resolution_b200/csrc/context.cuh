@@ -82,6 +82,13 @@ struct srcnn_ctx {
   bool deltas_tc = true;              // f=1 deltas on the tensor cores (deltas_tc.cuh)
   void* hp_scales = nullptr;          // ring of fused_hp::Scales blocks + their work words
   unsigned long long hp_next = 0;
+  // cache of the prepared operand image: valid while the six parameter buffers are the same
+  // owned allocations and no device-layer call has written device memory since (write_gen)
+  void* hp_cache = nullptr;
+  bool hp_cache_valid = false;
+  const void* hp_cache_key[6] = {};
+  unsigned long long hp_cache_gen = 0;
+  unsigned long long write_gen = 0;   // bumped by every entry point that writes device memory
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand

@@ -15,8 +15,8 @@
 //     H8(r)[c] = in[r][c..c+7]: one O and one H8 plane per tile;
 //   * A2/A3 are packed half pairs: half the TMEM store traffic of the epilogues.
 //
-// Range.  The scales depend on the WEIGHTS only (computed on the device by hp_prepare_kernel
-// before every launch; data-independent, so a row-band partition of an image reproduces the
+// Range.  The scales depend on the WEIGHTS only (computed on the device by hp_prepare_kernel;
+// cached per context until a device-layer call writes device memory; data-independent, so a row-band partition of an image reproduces the
 // single-launch result bit for bit) and assume |input| < 64, 64x the luma range:
 //     sx = 2^9;  sw_l = 2^14 / pow2ceil(max|W_l|);  s_l = 2^14 / pow2ceil(bound on out_l)
 // with bound(out1) = max_n(|b1| + sum|W1|) * 64 and bound(out2) likewise from bound(out1).
@@ -291,12 +291,16 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
 template <bool BATCH>
 __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Args a, int rpc,
                                                                       BatchExt bx,
-                                                                      Scales* scales) {
+                                                                      const Scales* scales,
+                                                                      int* fallback) {
   using C = Cfg;
   using namespace tc;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ScaleVals sc = scales->v;
-  if (!sc.ok) return;   // non-finite parameters: the TF32 kernel behind us runs instead
+  if (!sc.ok) {         // non-finite parameters: the TF32 kernel behind us runs instead
+    if (threadIdx.x == 0) *fallback = 1;
+    return;
+  }
   __half* sW1 = reinterpret_cast<__half*>(smem_raw + C::oW1);
   __half* sW2 = reinterpret_cast<__half*>(smem_raw + C::oW2);
   __half* sW3 = reinterpret_cast<__half*>(smem_raw + C::oW3);
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     // the domain check happens where a value is consumed, never where it is loaded: the loads
     // of the next two rows stay in flight across a tile (HBM latency > one tile period)
     auto in_domain = [&](float x) {
-      if (!(fabsf(x) < kInMax * 0.999f)) scales->v.ok = 0;   // outside the FP16 domain (or NaN)
+      if (!(fabsf(x) < kInMax * 0.999f)) *fallback = 1;   // outside the FP16 domain (or NaN)
     };
     unsigned short hh[7], hl[7];   // rows r-7 .. r-1 of this column
     {
@@ -735,24 +739,33 @@ inline int scale_slot(srcnn_ctx* ctx, Scales** sc, unsigned** ws) {
   return SRCNN_OK;
 }
 
-// the scales of a network, computed on the context stream into a fresh block of the ring
-inline int prepare(srcnn_ctx* ctx, const fused::Args& a, Scales** out) {
-  unsigned* ws;
-  SRCNN_TRY(scale_slot(ctx, out, &ws));
-  hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, *out);
+// the scales of a network, computed on the context stream into the context's cache block
+inline int prepare_cached(srcnn_ctx* ctx, const fused::Args& a, const Scales** out) {
+  if (!ctx->hp_cache) SRCNN_CUDA(cudaMalloc(&ctx->hp_cache, sizeof(Scales)));
+  hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, reinterpret_cast<Scales*>(ctx->hp_cache));
+  *out = reinterpret_cast<const Scales*>(ctx->hp_cache);
   return SRCNN_OK;
 }
 
 // [prepare +] FP16 kernel + (gated) TF32 kernel; `S` images, or a batch as one virtual image.
-// `shared` = scales already prepared by the caller for a series of launches with the same
-// parameters (the sub-bands of srcnn_infer_rows_host); null = prepare here.
+// `shared` = scales already prepared for these parameters (the sub-bands of
+// srcnn_infer_rows_host, or the context's cache); null = prepare here.  The scales are read-only
+// for the kernels; "leave this launch to the TF32 kernel" is a per-launch word of the ring.
 inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float* out1,
-                  float* out2, Scales* shared = nullptr) {
-  Scales* sc = shared;
-  if (!sc) SRCNN_TRY(prepare(ctx, a, &sc));
+                  float* out2, const Scales* shared = nullptr) {
+  const Scales* sc = shared;
+  Scales* slot;
+  unsigned* ws;
+  SRCNN_TRY(scale_slot(ctx, &slot, &ws));
+  if (!sc) {
+    hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, slot);
+    sc = slot;
+  }
+  int* fallback = reinterpret_cast<int*>(ws);
+  SRCNN_CUDA(cudaMemsetAsync(fallback, 0, sizeof(int), ctx->stream));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   BatchExt bx{};
-  bx.gate = &sc->v.ok;
+  bx.gate = fallback;
   if (batch) {
     fused::Args v = a;
     const int pad = Cfg::F1 + Cfg::F3 - 2;
@@ -765,13 +778,15 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
     bx.S = S;
     bx.pw = a.w;
     bx.ph = a.h;
-    forward_fused_hp_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx, sc);
+    forward_fused_hp_kernel<true>
+        <<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx, sc, fallback);
     fused_pl::forward_fused_pl_kernel<true>
         <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx);
   } else {
     const int rpc = fused_pl::rows_per_cta(a.w3, a.h3, S, sms);
     dim3 grid((a.w3 + Cfg::OW3 - 1) / Cfg::OW3, (a.h3 + rpc - 1) / rpc, S);
-    forward_fused_hp_kernel<false><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx, sc);
+    forward_fused_hp_kernel<false>
+        <<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx, sc, fallback);
     fused_pl::forward_fused_pl_kernel<false>
         <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx);
   }

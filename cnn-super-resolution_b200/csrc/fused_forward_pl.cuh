@@ -160,7 +160,7 @@ struct BatchExt {
   float* out1;   // may be null
   float* out2;   // may be null
   int S, pw, ph;
-  // when set: run only if *gate == 0 (the FP16-split kernel of fused_forward_hp.cuh found the
+  // when set: run only if *gate != 0 (the FP16-split kernel of fused_forward_hp.cuh found the
   // input outside its domain and left the launch to this kernel)
   const int* gate;
 };
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   using C = Cfg;
   using namespace tc;
   extern __shared__ __align__(128) float smem[];
-  if (bx.gate != nullptr && *bx.gate != 0) return;
+  if (bx.gate != nullptr && *bx.gate == 0) return;
   float* sW1 = smem + C::oW1;
   float* sW2 = smem + C::oW2;
   float* sW3 = smem + C::oW3;

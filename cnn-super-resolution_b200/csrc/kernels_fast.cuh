@@ -109,7 +109,7 @@ inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {
 inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* in,
                          float* out, const float* w1, const float* b1, const float* w2,
                          const float* b2, const float* w3, const float* b3, int in_w, int in_h,
-                         int S, fused_hp::Scales* scales = nullptr) {
+                         int S, const fused_hp::Scales* scales = nullptr) {
   if (!fused::supported(n1, n2, f1, f2, f3))
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
@@ -131,15 +131,26 @@ inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3
   return ctx->fused_impl == 4 && fused_hp::supported(n1, n2, f1, f2, f3) ? 3 : 1;
 }
 
-// scales for a series of forward_fused launches with the same parameters (null when the
-// selected kernel needs none)
+// prepared operand image for forward_fused launches with these parameters (null when the
+// selected kernel needs none).  `cacheable`: the six buffers are context-owned allocations, so
+// nothing outside the device layer can have changed them since ctx->write_gen was recorded.
 inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* w1,
                          const float* b1, const float* w2, const float* b2, const float* w3,
-                         const float* b3, fused_hp::Scales** out) {
+                         const float* b3, bool cacheable, const fused_hp::Scales** out) {
   *out = nullptr;
   if (ctx->fused_impl != 4 || !fused_hp::supported(n1, n2, f1, f2, f3)) return SRCNN_OK;
+  const void* key[6] = {w1, b1, w2, b2, w3, b3};
+  if (cacheable && ctx->hp_cache_valid && ctx->hp_cache_gen == ctx->write_gen &&
+      std::memcmp(key, ctx->hp_cache_key, sizeof(key)) == 0) {
+    *out = reinterpret_cast<const fused_hp::Scales*>(ctx->hp_cache);
+    return SRCNN_OK;
+  }
   fused::Args a{nullptr, nullptr, w1, b1, w2, b2, w3, b3, 0, 0, 0, 0};
-  return fused_hp::prepare(ctx, a, out);
+  SRCNN_TRY(fused_hp::prepare_cached(ctx, a, out));
+  ctx->hp_cache_valid = cacheable;
+  ctx->hp_cache_gen = ctx->write_gen;
+  std::memcpy(ctx->hp_cache_key, key, sizeof(key));
+  return SRCNN_OK;
 }
 
 inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {

@@ -119,6 +119,7 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->band_out) cudaFree(ctx->band_out);
   if (ctx->packed_params) cudaFree(ctx->packed_params);
   if (ctx->hp_scales) cudaFree(ctx->hp_scales);
+  if (ctx->hp_cache) cudaFree(ctx->hp_cache);
   if (ctx->copy_in) {
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
@@ -194,6 +195,7 @@ int srcnn_alloc(srcnn_ctx* ctx, size_t bytes, srcnn_mem* out) {
 }
 
 int srcnn_wrap(srcnn_ctx* ctx, void* device_ptr, size_t bytes, srcnn_mem* out) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && out && device_ptr, "null argument");
   SRCNN_REQUIRE(bytes > 0, "cannot wrap 0 bytes");
   Allocation a;
@@ -206,6 +208,7 @@ int srcnn_wrap(srcnn_ctx* ctx, void* device_ptr, size_t bytes, srcnn_mem* out) {
 }
 
 int srcnn_release(srcnn_ctx* ctx, srcnn_mem mem) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   if (mem >= ctx->allocs.size()) return fail(SRCNN_EHANDLE, "invalid memory handle");
   Allocation& a = ctx->allocs[mem];
@@ -245,6 +248,7 @@ int srcnn_mem_usage(srcnn_ctx* ctx, size_t* buffer_bytes) {
 
 int srcnn_write(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, const void* src,
                 int block) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && src, "null argument");
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in write");
@@ -273,6 +277,7 @@ int srcnn_read(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, void*
 
 int srcnn_copy_region(srcnn_ctx* ctx, srcnn_mem src, size_t src_offset, srcnn_mem dst,
                       size_t dst_offset, size_t bytes) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   Allocation* s = ctx->get(src);
   Allocation* d = ctx->get(dst);
@@ -294,6 +299,7 @@ int srcnn_copy(srcnn_ctx* ctx, srcnn_mem src, srcnn_mem dst, size_t dst_offset) 
 }
 
 int srcnn_fill_float(srcnn_ctx* ctx, srcnn_mem mem, float value) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in fill");
@@ -324,6 +330,7 @@ int srcnn_host_free(void* host_ptr) {
 
 int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W, srcnn_mem B,
                         int k, int n, int f, int skip_relu, int in_w, int in_h, int S) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(k > 0 && n > 0 && f > 0 && S > 0, "bad layer shape k=%d n=%d f=%d S=%d", k, n, f, S);
   SRCNN_REQUIRE(in_w >= f && in_h >= f, "input %dx%d smaller than filter %d", in_w, in_h, f);
@@ -346,6 +353,7 @@ int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W
 
 int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
                         int gt_w, int gt_h, int algo_w, int algo_h, int S) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
                 "bad squared_error dimensions");
@@ -366,6 +374,7 @@ int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem 
 
 int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
                            int gt_w, int gt_h, int algo_w, int algo_h, int S) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
                 "bad last_layer_delta dimensions");
@@ -384,6 +393,7 @@ int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_m
 int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
                  srcnn_mem target, srcnn_mem W, int n_curr, int f_next, int n_next, int out_w,
                  int out_h, int S) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(n_curr > 0 && f_next > 0 && n_next > 0 && S > 0, "bad deltas shape");
   SRCNN_REQUIRE(out_w >= f_next && out_h >= f_next, "layer output smaller than next filter");
@@ -408,6 +418,7 @@ int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
 int srcnn_backpropagate(srcnn_ctx* ctx, srcnn_mem deltas, srcnn_mem layer_input,
                         srcnn_mem grad_w, srcnn_mem grad_b, int n, int k, int f, int out_w,
                         int out_h, int S) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(n > 0 && k > 0 && f > 0 && S > 0 && out_w > 0 && out_h > 0, "bad backpropagate shape");
   const int iw = out_w + f - 1, ih = out_h + f - 1;
@@ -445,6 +456,7 @@ int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad
                         srcnn_mem grad_b, srcnn_mem prev_dw, srcnn_mem prev_db, float momentum,
                         float weight_decay, float learning_rate, unsigned batch_size,
                         unsigned weights_size, unsigned bias_size) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
   float *pw, *pb, *ppw, *ppb;
@@ -465,6 +477,7 @@ int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad
 }
 
 int srcnn_sum(srcnn_ctx* ctx, srcnn_mem data, unsigned len, int squared, srcnn_mem target) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   const float* pd;
   float* pt;
@@ -480,6 +493,7 @@ int srcnn_sum(srcnn_ctx* ctx, srcnn_mem data, unsigned len, int squared, srcnn_m
 }
 
 int srcnn_sub_from_all(srcnn_ctx* ctx, srcnn_mem data, float value, unsigned len) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   float* pd;
   SRCNN_TRY(resolve(ctx, data, sizeof(float) * (size_t)len, &pd, "sub_from_all data"));
@@ -492,6 +506,7 @@ int srcnn_sub_from_all(srcnn_ctx* ctx, srcnn_mem data, float value, unsigned len
 
 int srcnn_extract_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem target, int w, int h,
                        int normalize) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(w > 0 && h > 0, "bad image size");
   const uchar4* pi;
@@ -506,6 +521,7 @@ int srcnn_extract_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem target, int w, 
 
 int srcnn_swap_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem new_luma, srcnn_mem target,
                     int gt_w, int gt_h, int luma_w, int luma_h) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_REQUIRE(gt_w > 0 && gt_h > 0 && luma_w > 0 && luma_h > 0 && luma_w <= gt_w && luma_h <= gt_h,
                 "bad swap_luma dimensions");
@@ -522,6 +538,19 @@ int srcnn_swap_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem new_luma, srcnn_me
 }
 
 // ======================================================================= fused hot path
+
+namespace {
+// true when the six parameter buffers are context-owned allocations (nothing outside this
+// library can write them, so ctx->write_gen tells whether they may have changed)
+bool params_owned(srcnn_ctx* ctx, const srcnn_net* net) {
+  for (int l = 0; l < 3; l++) {
+    const Allocation* w = ctx->get(net->w[l]);
+    const Allocation* b = ctx->get(net->b[l]);
+    if (!w || !b || !w->owned || !b->owned) return false;
+  }
+  return true;
+}
+}  // namespace
 
 int srcnn_forward_fused_supported(const srcnn_net* net) {
   if (!net) return 0;
@@ -545,9 +574,14 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
     SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
     SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
     SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
+    for (int l = 0; l < 3; l++)   // writing the result into a parameter buffer?  (nobody does)
+      if (out == net->w[l] || out == net->b[l]) ctx->write_gen++;
+    const fused_hp::Scales* scales = nullptr;
+    SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2,
+                                  w3, b3, params_owned(ctx, net), &scales));
     LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
     SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin, pout, w1,
-                                  b1, w2, b2, w3, b3, in_w, in_h, S));
+                                  b1, w2, b2, w3, b3, in_w, in_h, S, scales));
     return check_launch("forward_fused");
   }
   SRCNN_REQUIRE(scratch1 != SRCNN_NULL_MEM && scratch2 != SRCNN_NULL_MEM,
@@ -626,24 +660,24 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   }
   float* din = (float*)ctx->band_in;
   float* dout = (float*)ctx->band_out;
+  // one set of operand scales for all sub-bands (computed on the context stream, before the
+  // event the side streams wait for)
+  const fused_hp::Scales* scales = nullptr;
+  SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
+                                b3, params_owned(ctx, net), &scales));
   if (n_sub == 1) {
     SRCNN_CUDA(cudaMemcpyAsync(din, host_in + (size_t)out_row0 * in_w, in_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
     {
       LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
       SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, din, dout,
-                                    w1, b1, w2, b2, w3, b3, in_w, band_in_h, 1));
+                                    w1, b1, w2, b2, w3, b3, in_w, band_in_h, 1, scales));
       SRCNN_TRY(check_launch("forward_fused"));
     }
     SRCNN_CUDA(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     return SRCNN_OK;
   }
-  // one set of operand scales for all sub-bands (computed on the context stream, before the
-  // event the side streams wait for)
-  fused_hp::Scales* scales = nullptr;
-  SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
-                                b3, &scales));
   // order the side streams after whatever the context stream was doing with the buffers
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
@@ -803,6 +837,7 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
 
 int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
                       int h, int S, srcnn_mem work) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
@@ -817,6 +852,7 @@ int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_
 int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                               int w, int h, int S, srcnn_mem out1, srcnn_mem out2,
                               srcnn_mem out3, srcnn_mem d1, srcnn_mem d2, srcnn_mem d3) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
@@ -827,6 +863,7 @@ int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
 
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,
                      float weight_decay, const float lr[3]) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && lr, "null argument");
   SRCNN_TRY(check_net(net));
   SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
@@ -857,6 +894,7 @@ int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, 
 
 int srcnn_validate_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                          int w, int h, int S, srcnn_mem work, srcnn_mem target) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx, "ctx is null");
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);

@@ -493,6 +493,52 @@ def test_fused_fp16_domain_fallback(ctx, port):
         assert float(np.abs(got - exp).max()) <= 1e-5 * float(np.abs(exp).max()) + 1e-9
 
 
+def test_fused_operand_cache_follows_the_parameters(ctx, port):
+    """The fused kernel's packed operand image is cached per context; every way the
+    parameters can change on the device must invalidate it: a host write, a device copy, a
+    fill, and the training update."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    w, h = 150, 40
+    rng = np.random.default_rng(77)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x = luma_image(rng, h, w)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    mi, mo = ctx.upload(x), ctx.alloc(4 * w3 * h3)
+
+    def check(p):
+        on = NetState(n1, n2, f1, f2, f3, p)
+        _, _, e3 = port.net_forward(on, x, w, h, 1)
+        for _ in range(2):   # second call: served from the cache
+            net.forward_fused(mi, mo, w, h, 1)
+            got = ctx.read(mo, (1, h3, w3))
+            assert float(np.abs(got - e3).max()) <= 1e-4
+
+    check(params)
+    # host write into one layer
+    p2 = dict(params)
+    p2["w2"] = (params["w2"] * 1.5).astype(np.float32)
+    ctx.write(net.c.w[1], p2["w2"])
+    check(p2)
+    # device-to-device copy into another
+    p3 = dict(p2)
+    p3["b1"] = (params["b1"] + 0.05).astype(np.float32)
+    tmp = ctx.upload(p3["b1"])
+    ctx.copy(tmp, net.c.b[0])
+    check(p3)
+    # fill
+    p4 = dict(p3)
+    p4["b2"] = np.full_like(params["b2"], 0.02)
+    ctx.fill_float(net.c.b[1], 0.02)
+    check(p4)
+    # one training step changes all six buffers
+    px, pgt = patches(rng, 3, 33, 33)
+    work = ctx.alloc(net.train_workspace_bytes(33, 33, 3))
+    net.train_chunk(ctx.upload(px), ctx.upload(pgt), 33, 33, 3, work)
+    net.update_all(3, 0.9, 0.001, np.array([1e-2, 1e-2, 1e-3], np.float32))
+    check(net.params())
+
+
 def test_full_size_4096_properties(ctx, port):
     """BASELINE config C3 (4096x4096, 9-1-5 64/32) at full size, through size-independent
     properties: (1) random 48x48 output windows equal the oracle run on just their receptive

@@ -566,8 +566,17 @@ __global__ void __launch_bounds__(NT) grad_stream_kernel(const float* __restrict
       for (int i = tid; i < npx * F; i += NT) {
         const int px = i / F, dy = i % F;
         const long long p = p0 + px;
-        const long long s = p / ((long long)ow * oh);
-        const int rem = (int)(p - s * ow * oh);
+        long long s;
+        int rem;
+        if (P <= 0x7fffffffLL) {   // 32-bit divisions: the 64-bit ones cost ~100 instructions
+          const unsigned pu = (unsigned)p, per = (unsigned)(ow * oh);
+          const unsigned su = pu / per;
+          s = su;
+          rem = (int)(pu - su * per);
+        } else {
+          s = p / ((long long)ow * oh);
+          rem = (int)(p - s * ow * oh);
+        }
         const int row = rem / ow, col = rem - row * ow;
         const float* src = in + (s * ih + row + dy) * (long long)iw + col;
         float* dst = sA + px * G::AP + dy * F;

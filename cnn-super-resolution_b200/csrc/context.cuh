@@ -80,6 +80,7 @@ struct srcnn_ctx {
   // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes (3xTF32), 4 planes (FP16 split)
   int fused_impl = 4;
   bool deltas_tc = true;              // f=1 deltas on the tensor cores (deltas_tc.cuh)
+  bool wgrad_tc = true;               // layer-1 weight gradient on the tensor cores (wgrad_tc.cuh)
   void* hp_scales = nullptr;          // ring of fused_hp::Scales blocks + their work words
   unsigned long long hp_next = 0;
   // cache of the prepared operand image: valid while the six parameter buffers are the same

@@ -13,6 +13,7 @@
 #include "fused_forward_hp.cuh"
 #include "train_kernels.cuh"
 #include "deltas_tc.cuh"
+#include "wgrad_tc.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -72,6 +73,8 @@ inline int configure(srcnn_ctx* ctx) {
   if (impl && std::strcmp(impl, "ws") == 0) ctx->fused_impl = 2;  // warp-specialised, im2col
   const char* d1 = std::getenv("SRCNN_D1_IMPL");   // "simt": FP32 kernel for the f=1 deltas
   ctx->deltas_tc = !(d1 && std::strcmp(d1, "simt") == 0);
+  const char* gw = std::getenv("SRCNN_GW_IMPL");   // "simt": FP32 kernel for the layer-1 gradient
+  ctx->wgrad_tc = !(gw && std::strcmp(gw, "simt") == 0);
   return SRCNN_OK;
 }
 
@@ -98,6 +101,18 @@ inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* targ
 inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float* gw, float* gb,
                          int n, int k, int f, int ow, int oh, int S) {
   if (!aligned16(d) || !aligned16(in)) return 0;   // the register-tiled kernels use LDG.128
+  if (ctx->wgrad_tc) {   // layer-1 gradient on the tensor cores
+    int count = 0;
+    const int rc = wgtc::wgrad1_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      const int Mw = f * f * k, total = (Mw + 1) * n;
+      train::partial_reduce_kernel<<<(total + train::RED_OUT - 1) / train::RED_OUT,
+                                     train::RED_OUT * train::RED_WARPS, 0, ctx->stream>>>(
+          (const float*)ctx->splitk_scratch, gw, gb, Mw, n, count);
+      return 1;
+    }
+  }
   return train::gradw(ctx, d, in, gw, gb, n, k, f, ow, oh, S);
 }
 

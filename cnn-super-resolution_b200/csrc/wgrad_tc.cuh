@@ -1,0 +1,244 @@
+// Weight / bias gradient of layer 1 (k = 1, f = 9, n = 64) on the tensor cores:
+//     gW[dy][dx][n] += sum_{s,row,col} in[s][row+dy][col+dx] * d[s][row][col][n],  gB[n] += sum d
+// reference: src/kernel/backpropagate.cl:56-114 (one work-item per weight, serial over all
+// pixels, racy `+=` across samples; here deterministic).
+//
+// The contraction index is the PIXEL -- the slow index of both operands -- and tcgen05 has no
+// MN-major TF32 operands (probe/mn_probe.cu: the MMA is a no-op), so the producers transpose on
+// the way into shared memory: a thread owns one operand ROW (a filter tap / an output channel)
+// for four consecutive pixels, its four loads are coalesced across the warp (consecutive rows
+// are consecutive addresses in the pixel-major tensors), and its one STS.128 lands in the
+// canonical K-major layout without bank conflicts.  Per tile of 64 pixels:
+//     A_hi, A_lo [88 taps][64 px]   im2col of the input patches, TF32 hi / lo
+//     B          [64 ch hi; 64 ch lo][64 px]   the deltas
+//     D_hi[tap][0..127] += A_hi x B (N = 128),  D_lo[tap][0..63] += A_lo x B_hi (N = 64)
+// 16 MMAs, accumulators stay in tensor memory for ALL tiles of the (persistent) CTA; one
+// partial [81*64 + 64] per CTA goes to the fixed-order partial_reduce_kernel.
+//
+//   PA (4 warps)  im2col gather -> split -> A tiles                      -> full[i&1]
+//   PB (4 warps)  delta tile -> split -> B tile, bias sums               -> full[i&1]
+//   I  (1 warp)   8 K-steps x 2 MMAs                                     -> empty[i&1]
+#pragma once
+#include <cuda_runtime.h>
+
+#include "context.cuh"
+#include "fused_forward_pl.cuh"
+#include "tc_common.cuh"
+
+namespace srcnn {
+namespace wgtc {
+
+struct Cfg {
+  static constexpr int F = 9, T = F * F, TP = 88, N = 64;   // taps, padded taps, channels
+  static constexpr int PX = 64;                             // pixels per tile (K of the GEMM)
+  static constexpr int NT = 9 * 32, W_PB = 4, W_I = 8;
+  static constexpr int SBO = 128 * (PX / 4);                // bytes between 8-row groups
+  // shared memory per stage (floats): A_hi, A_lo (TP rows), B (2N rows)
+  static constexpr int A_FLOATS = TP * PX, B_FLOATS = 2 * N * PX;
+  static constexpr int STAGE = 2 * A_FLOATS + B_FLOATS;
+  static constexpr int oBase = 2 * STAGE;                   // per-pixel input offsets [2][PX]
+  static constexpr int TOTAL = oBase + 2 * PX;
+  // the M = 128 MMA also reads rows TP..127 of an A tile: they must lie inside the allocation
+  // (their products land in accumulator rows nobody reads)
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(TOTAL + (128 - TP) * PX);
+  static constexpr uint32_t cDhi = 0, cDlo = 128, TMEM_COLS = 256;
+};
+
+__global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __restrict__ d,
+                                                               const float* __restrict__ in,
+                                                               float* __restrict__ partial, int ow,
+                                                               int oh, long long P,
+                                                               int n_tiles_total) {
+  using C = Cfg;
+  using namespace tc;
+  using fused_pl::elect_one;
+  using fused_pl::tmem_ld16_nowait;
+  using fused_pl::tmem_ld_wait;
+  using fused_ws::mbar_arrive;
+  using fused_ws::named_bar_sync;
+  extern __shared__ __align__(128) float wg_smem[];
+  int* sBase = reinterpret_cast<int*>(wg_smem + C::oBase);
+  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ float gb_part[2][C::N];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int iw = ow + C::F - 1, ih = oh + C::F - 1;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&full[i], 256);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&done, 1);
+  }
+  // the zero rows of the im2col tiles (taps 81..87) are written once
+  for (int i = tid; i < 2 * 2 * (C::TP - C::T) * C::PX; i += C::NT) {
+    const int tile = i / ((C::TP - C::T) * C::PX), r = i % ((C::TP - C::T) * C::PX);
+    const int t = C::T + r / C::PX, k = r % C::PX;
+    wg_smem[(tile >> 1) * C::STAGE + (tile & 1) * C::A_FLOATS + kmajor_offset(t, k, C::PX)] = 0.f;
+  }
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = (n_tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long per = (long long)ow * oh;
+
+  if (warp < C::W_PB) {
+    // ============================ PA: im2col tiles ========================================
+    for (int i = 0; i < my_tiles; i++) {
+      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+      // input offset of the window origin of each pixel of the tile (-1: past the end)
+      int* base = sBase + (i & 1) * C::PX;
+      if (tid < C::PX) {
+        const long long p = p0 + tid;
+        int b = -1;
+        if (p < P) {
+          const long long s = p / per;
+          const int rem = (int)(p - s * per), row = rem / ow, col = rem - row * ow;
+          b = (int)((s * ih + row) * iw + col);
+        }
+        base[tid] = b;
+      }
+      named_bar_sync(1, 128);
+      float* sAh = wg_smem + (i & 1) * C::STAGE;
+      float* sAl = sAh + C::A_FLOATS;
+      // item = (tap t, pixel quad q); consecutive lanes take consecutive taps
+      for (int it = tid; it < C::T * (C::PX / 4); it += 128) {
+        const int t = it % C::T, q = it / C::T;
+        const int toff = (t / C::F) * iw + (t % C::F);
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int b = base[4 * q + j];
+          split_tf32(b >= 0 ? __ldg(in + b + toff) : 0.f, hi[j], lo[j]);
+        }
+        const int off = kmajor_offset(t, 4 * q, C::PX);
+        *reinterpret_cast<float4*>(sAh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sAl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[i & 1]);   // (base[] of this stage is rewritten two tiles later, behind
+                                   // the next tile's barrier)
+    }
+  } else if (warp < C::W_I) {
+    // ============================ PB: delta tiles + bias sums ==============================
+    const int pw = warp - C::W_PB;                 // 0..3
+    const int c = (pw & 1) * 32 + lane;            // output channel of this thread
+    float gb = 0.f;
+    for (int i = 0; i < my_tiles; i++) {
+      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+      float* sB = wg_smem + (i & 1) * C::STAGE + 2 * C::A_FLOATS;
+#pragma unroll 2
+      for (int q = (pw >> 1); q < C::PX / 4; q += 2) {
+        float v[4], hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const long long p = p0 + 4 * q + j;
+          v[j] = p < P ? __ldg(d + p * C::N + c) : 0.f;
+        }
+        gb += (v[0] + v[1]) + (v[2] + v[3]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) split_tf32(v[j], hi[j], lo[j]);
+        *reinterpret_cast<float4*>(sB + kmajor_offset(c, 4 * q, C::PX)) =
+            make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sB + kmajor_offset(C::N + c, 4 * q, C::PX)) =
+            make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[i & 1]);
+    }
+    gb_part[pw >> 1][c] = gb;
+  } else {
+    // ============================ I: MMA issuer ============================================
+    const uint32_t idesc_hi = make_idesc_tf32(128, 2 * C::N);   // A_hi x [B_hi; B_lo]
+    const uint32_t idesc_lo = make_idesc_tf32(128, C::N);       // A_lo x B_hi
+    for (int i = 0; i < my_tiles; i++) {
+      mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
+      tcgen05_fence_after();
+      const float* st = wg_smem + (i & 1) * C::STAGE;
+      const uint64_t ah = make_desc_kmajor(st, 0, 128, C::SBO);
+      const uint64_t al = make_desc_kmajor(st + C::A_FLOATS, 0, 128, C::SBO);
+      const uint64_t bd = make_desc_kmajor(st + 2 * C::A_FLOATS, 0, 128, C::SBO);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::PX / 8; ks++) {
+          mma_tf32(tmem + C::cDhi, ah + 16 * ks, bd + 16 * ks, idesc_hi, (i | ks) > 0);
+          mma_tf32(tmem + C::cDlo, al + 16 * ks, bd + 16 * ks, idesc_lo, (i | ks) > 0);
+        }
+        mma_commit(&empty[i & 1]);
+        if (i == my_tiles - 1) mma_commit(&done);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- epilogue: one partial [T*N + N] per CTA; thread = filter tap (TMEM lane)
+  __syncthreads();   // gb_part complete, all producers done
+  float* dst = partial + (long long)blockIdx.x * (C::T * C::N + C::N);
+  if (warp < 3) {
+    if (my_tiles > 0) {
+      mbar_wait(&done, 0);
+      tcgen05_fence_after();
+    }
+    const int t = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+    for (int g = 0; g < C::N / 16; g++) {
+      float a[16], b[16], l[16];
+      if (my_tiles > 0) {
+        tmem_ld16_nowait(tmem + lane_base + C::cDhi + g * 16, a);
+        tmem_ld16_nowait(tmem + lane_base + C::cDhi + C::N + g * 16, b);
+        tmem_ld16_nowait(tmem + lane_base + C::cDlo + g * 16, l);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = b[j] = l[j] = 0.f;
+      }
+      if (t < C::T) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + t * C::N + g * 16 + j) =
+              make_float4((a[j] + b[j]) + l[j], (a[j + 1] + b[j + 1]) + l[j + 1],
+                          (a[j + 2] + b[j + 2]) + l[j + 2], (a[j + 3] + b[j + 3]) + l[j + 3]);
+      }
+    }
+  }
+  if (tid < C::N) dst[C::T * C::N + tid] = gb_part[0][tid] + gb_part[1][tid];
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// returns 1 when it launched (partials in ctx->splitk_scratch, *count of them), 0 when not
+// handled, < 0 on error
+inline int wgrad1_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int k, int f, int ow,
+                     int oh, int S, int* count) {
+  if (k != 1 || f != Cfg::F || n != Cfg::N) return 0;
+  const long long P = (long long)S * ow * oh;
+  const long long in_elems = (long long)S * (ow + f - 1) * (oh + f - 1);
+  if (in_elems > 0x7fffffffLL) return 0;   // 32-bit input offsets
+  const long long tiles = (P + Cfg::PX - 1) / Cfg::PX;
+  if (tiles > 0x7fffffffLL) return 0;
+  static bool configured = false;
+  if (!configured) {
+    SRCNN_CUDA(cudaFuncSetAttribute(wgrad1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  *count = grid;
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
+                           sizeof(float) * (size_t)grid * (Cfg::T * Cfg::N + Cfg::N)));
+  wgrad1_tc_kernel<<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
+      d, in, (float*)ctx->splitk_scratch, ow, oh, P, (int)tiles);
+  return 1;
+}
+
+}  // namespace wgtc
+}  // namespace srcnn

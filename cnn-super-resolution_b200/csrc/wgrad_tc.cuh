@@ -15,7 +15,7 @@
 // 16 MMAs, accumulators stay in tensor memory for ALL tiles of the (persistent) CTA; one
 // partial [81*64 + 64] per CTA goes to the fixed-order partial_reduce_kernel.
 //
-//   PA (4 warps)  im2col gather -> split -> A tiles                      -> full[i&1]
+//   PA (8 warps)  im2col gather -> split -> A tiles                      -> full[i&1]
 //   PB (4 warps)  delta tile -> split -> B tile, bias sums               -> full[i&1]
 //   I  (1 warp)   8 K-steps x 2 MMAs                                     -> empty[i&1]
 #pragma once
@@ -31,7 +31,9 @@ namespace wgtc {
 struct Cfg {
   static constexpr int F = 9, T = F * F, TP = 88, N = 64;   // taps, padded taps, channels
   static constexpr int PX = 64;                             // pixels per tile (K of the GEMM)
-  static constexpr int NT = 9 * 32, W_PB = 4, W_I = 8;
+  static constexpr int N_PA = 8, W_PB = N_PA, W_I = W_PB + 4;   // warps: PA 0..7, PB 8..11, I 12
+  static constexpr int NT = (W_I + 1) * 32;
+  static constexpr int PA_ITEMS = (T * (PX / 4) + N_PA * 32 - 1) / (N_PA * 32);   // per thread
   static constexpr int SBO = 128 * (PX / 4);                // bytes between 8-row groups
   // shared memory per stage (floats): A_hi, A_lo (TP rows), B (2N rows)
   static constexpr int A_FLOATS = TP * PX, B_FLOATS = 2 * N * PX;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
   if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
   if (tid == 0) {
     for (int i = 0; i < 2; i++) {
-      mbar_init(&full[i], 256);
+      mbar_init(&full[i], C::N_PA * 32 + 128);
       mbar_init(&empty[i], 1);
     }
     mbar_init(&done, 1);
@@ -103,22 +105,36 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
         }
         base[tid] = b;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, C::N_PA * 32);
       float* sAh = wg_smem + (i & 1) * C::STAGE;
       float* sAl = sAh + C::A_FLOATS;
-      // item = (tap t, pixel quad q); consecutive lanes take consecutive taps
-      for (int it = tid; it < C::T * (C::PX / 4); it += 128) {
+      // item = (tap t, pixel quad q); consecutive lanes take consecutive taps.  All loads of a
+      // thread are issued before the first is used: the gather is latency-bound otherwise
+      // (one item at a time: 6 000 cycles per tile against 900 of MMA work)
+      float v[C::PA_ITEMS][4];
+#pragma unroll
+      for (int u = 0; u < C::PA_ITEMS; u++) {
+        const int it = tid + C::N_PA * 32 * u;
         const int t = it % C::T, q = it / C::T;
         const int toff = (t / C::F) * iw + (t % C::F);
-        float hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const int b = base[4 * q + j];
-          split_tf32(b >= 0 ? __ldg(in + b + toff) : 0.f, hi[j], lo[j]);
+          const int b = it < C::T * (C::PX / 4) ? base[4 * q + j] : -1;
+          v[u][j] = b >= 0 ? __ldg(in + b + toff) : 0.f;
         }
-        const int off = kmajor_offset(t, 4 * q, C::PX);
-        *reinterpret_cast<float4*>(sAh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sAl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < C::PA_ITEMS; u++) {
+        const int it = tid + C::N_PA * 32 * u;
+        if (it < C::T * (C::PX / 4)) {
+          const int t = it % C::T, q = it / C::T;
+          float hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
+          const int off = kmajor_offset(t, 4 * q, C::PX);
+          *reinterpret_cast<float4*>(sAh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(sAl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
       fence_proxy_async();
       mbar_arrive(&full[i & 1]);   // (base[] of this stage is rewritten two tiles later, behind
@@ -133,17 +149,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
       const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
       if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
       float* sB = wg_smem + (i & 1) * C::STAGE + 2 * C::A_FLOATS;
-#pragma unroll 2
-      for (int q = (pw >> 1); q < C::PX / 4; q += 2) {
-        float v[4], hi[4], lo[4];
+      float v[C::PX / 8][4];   // this thread's 8 pixel quads, all loads in flight together
+#pragma unroll
+      for (int u = 0; u < C::PX / 8; u++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const long long p = p0 + 4 * q + j;
-          v[j] = p < P ? __ldg(d + p * C::N + c) : 0.f;
+          const long long p = p0 + 4 * ((pw >> 1) + 2 * u) + j;
+          v[u][j] = p < P ? __ldg(d + p * C::N + c) : 0.f;
         }
-        gb += (v[0] + v[1]) + (v[2] + v[3]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) split_tf32(v[j], hi[j], lo[j]);
+      for (int u = 0; u < C::PX / 8; u++) {
+        const int q = (pw >> 1) + 2 * u;
+        float hi[4], lo[4];
+        gb += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
         *reinterpret_cast<float4*>(sB + kmajor_offset(c, 4 * q, C::PX)) =
             make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(sB + kmajor_offset(C::N + c, 4 * q, C::PX)) =

@@ -101,9 +101,10 @@ inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* targ
 inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float* gw, float* gb,
                          int n, int k, int f, int ow, int oh, int S) {
   if (!aligned16(d) || !aligned16(in)) return 0;   // the register-tiled kernels use LDG.128
-  if (ctx->wgrad_tc) {   // layer-1 gradient on the tensor cores
+  if (ctx->wgrad_tc) {   // layer-1 / layer-2 gradients on the tensor cores
     int count = 0;
-    const int rc = wgtc::wgrad1_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
+    int rc = wgtc::wgrad1_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
+    if (rc == 0) rc = wgtc::wgrad2_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
     if (rc < 0) return rc;
     if (rc == 1) {
       const int Mw = f * f * k, total = (Mw + 1) * n;

@@ -234,6 +234,194 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight / bias gradient of an f = 1 layer (layer 2 of 9-1-5, k = 64 -> n = 32):
+//     gW[m][n] += sum_p in[p][m] * d[p][n],   gB[n] += sum_p d[p][n]
+// Same scheme; both operands are plain transposes, and with 64 + 64 rows of A (hi, lo) and
+// 32 + 32 rows of B all four partial products come out of ONE M = 128, N = 64 MMA per K-step:
+//     D[m][n] = hi.hi   D[m][32+n] = hi.lo   D[64+m][n] = lo.hi   (D[64+m][32+n] = lo.lo, unused)
+struct Cfg2 {
+  static constexpr int K = 64, N = 32, PX = 64;
+  static constexpr int N_PA = 8, W_PB = N_PA, W_I = W_PB + 4;
+  static constexpr int NT = (W_I + 1) * 32;
+  static constexpr int SBO = 128 * (PX / 4);
+  static constexpr int A_FLOATS = 2 * K * PX, B_FLOATS = 2 * N * PX;
+  static constexpr int STAGE = A_FLOATS + B_FLOATS;
+  static constexpr int oX = 2 * STAGE;                       // epilogue exchange [K][N]
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(oX + K * N);
+  static constexpr uint32_t TMEM_COLS = 64;
+};
+
+__global__ void __launch_bounds__(Cfg2::NT, 1) wgrad2_tc_kernel(const float* __restrict__ d,
+                                                                const float* __restrict__ in,
+                                                                float* __restrict__ partial,
+                                                                long long P, int n_tiles_total) {
+  using C = Cfg2;
+  using namespace tc;
+  using fused_pl::elect_one;
+  using fused_pl::tmem_ld16_nowait;
+  using fused_pl::tmem_ld_wait;
+  using fused_ws::mbar_arrive;
+  extern __shared__ __align__(128) float wg_smem[];
+  float* sX = wg_smem + C::oX;
+  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ float gb_part[4][C::N];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&full[i], C::N_PA * 32 + 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&done, 1);
+  }
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = (n_tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < C::W_PB) {
+    // ============================ PA: layer input, transposed ==============================
+    const int c = (warp & 1) * 32 + lane;          // input channel (row of A)
+    for (int i = 0; i < my_tiles; i++) {
+      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+      float* sA = wg_smem + (i & 1) * C::STAGE;
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const long long p = p0 + 4 * ((warp >> 1) + 4 * u) + j;
+          v[u][j] = p < P ? __ldg(in + p * C::K + c) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = (warp >> 1) + 4 * u;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
+        *reinterpret_cast<float4*>(sA + kmajor_offset(c, 4 * q, C::PX)) =
+            make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sA + kmajor_offset(C::K + c, 4 * q, C::PX)) =
+            make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[i & 1]);
+    }
+  } else if (warp < C::W_I) {
+    // ============================ PB: deltas, transposed + bias sums =======================
+    const int pw = warp - C::W_PB;                 // 0..3: pixel quads pw, pw+4, ..
+    float gb = 0.f;
+    for (int i = 0; i < my_tiles; i++) {
+      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+      float* sB = wg_smem + (i & 1) * C::STAGE + C::A_FLOATS;
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const long long p = p0 + 4 * (pw + 4 * u) + j;
+          v[u][j] = p < P ? __ldg(d + p * C::N + lane) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = pw + 4 * u;
+        float hi[4], lo[4];
+        gb += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
+        *reinterpret_cast<float4*>(sB + kmajor_offset(lane, 4 * q, C::PX)) =
+            make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sB + kmajor_offset(C::N + lane, 4 * q, C::PX)) =
+            make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[i & 1]);
+    }
+    gb_part[pw][lane] = gb;
+  } else {
+    // ============================ I: MMA issuer ============================================
+    const uint32_t idesc = make_idesc_tf32(128, 2 * C::N);
+    for (int i = 0; i < my_tiles; i++) {
+      mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
+      tcgen05_fence_after();
+      const float* st = wg_smem + (i & 1) * C::STAGE;
+      const uint64_t ad = make_desc_kmajor(st, 0, 128, C::SBO);
+      const uint64_t bd = make_desc_kmajor(st + C::A_FLOATS, 0, 128, C::SBO);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C::PX / 8; ks++)
+          mma_tf32(tmem, ad + 16 * ks, bd + 16 * ks, idesc, (i | ks) > 0);
+        mma_commit(&empty[i & 1]);
+        if (i == my_tiles - 1) mma_commit(&done);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- epilogue: gW[m][n] = D[m][n] + D[m][32+n] + D[64+m][n]; thread = TMEM lane
+  __syncthreads();
+  float* dst = partial + (long long)blockIdx.x * (C::K * C::N + C::N);
+  if (warp < 4) {
+    mbar_wait(&done, 0);
+    tcgen05_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int r = warp * 32 + lane;   // accumulator row
+    float a[32], b[32];
+    tmem_ld16_nowait(tmem + lane_base, a);
+    tmem_ld16_nowait(tmem + lane_base + 16, a + 16);
+    tmem_ld16_nowait(tmem + lane_base + 32, b);
+    tmem_ld16_nowait(tmem + lane_base + 48, b + 16);
+    tmem_ld_wait();
+    if (r >= C::K) {   // lo.hi rows -> exchange buffer
+#pragma unroll
+      for (int j = 0; j < C::N; j++) sX[(r - C::K) * C::N + j] = a[j];
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (r < C::K) {
+#pragma unroll
+      for (int j = 0; j < C::N; j += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(sX + r * C::N + j);
+        *reinterpret_cast<float4*>(dst + r * C::N + j) =
+            make_float4((a[j] + b[j]) + x.x, (a[j + 1] + b[j + 1]) + x.y,
+                        (a[j + 2] + b[j + 2]) + x.z, (a[j + 3] + b[j + 3]) + x.w);
+      }
+    }
+  }
+  if (tid < C::N)
+    dst[C::K * C::N + tid] = (gb_part[0][tid] + gb_part[1][tid]) + (gb_part[2][tid] + gb_part[3][tid]);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+inline int wgrad2_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int k, int f, int ow,
+                     int oh, int S, int* count) {
+  if (f != 1 || k != Cfg2::K || n != Cfg2::N) return 0;
+  const long long P = (long long)S * ow * oh;
+  const long long tiles = (P + Cfg2::PX - 1) / Cfg2::PX;
+  if (tiles > 0x7fffffffLL) return 0;
+  static bool configured = false;
+  if (!configured) {
+    SRCNN_CUDA(cudaFuncSetAttribute(wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg2::SMEM_BYTES));
+    configured = true;
+  }
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  *count = grid;
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
+                           sizeof(float) * (size_t)grid * (Cfg2::K * Cfg2::N + Cfg2::N)));
+  wgrad2_tc_kernel<<<grid, Cfg2::NT, Cfg2::SMEM_BYTES, ctx->stream>>>(
+      d, in, (float*)ctx->splitk_scratch, P, (int)tiles);
+  return 1;
+}
+
 // returns 1 when it launched (partials in ctx->splitk_scratch, *count of them), 0 when not
 // handled, < 0 on error
 inline int wgrad1_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int k, int f, int ow,

@@ -294,9 +294,11 @@ def run_ours(args, rank, world, local_rank):
             net.update_all(n_loc * world, MOMENTUM, DECAY, LR)
 
         def train_e2e_step(i):
-            ctx.L.srcnn_write(ctx.h, d_in, 0, px.nbytes, px.ptr, 0)
-            ctx.L.srcnn_write(ctx.h, d_gt, 0, pg.nbytes, pg.ptr, 0)
-            train_step(i)
+            # HOST samples in (pinned), upload of chunk i+1 overlapping the training of chunk i
+            net.train_chunks_host(px.array, pg.array, PATCH, PATCH, chunk, work)
+            if world > 1:
+                dist.all_reduce(grad)
+            net.update_all(n_loc * world, MOMENTUM, DECAY, LR)
             off = 0
             for l in range(3):     # read the updated parameters back (the step's result)
                 for hnd, cnt in ((net.c.w[l], net.sizes[l][0]), (net.c.b[l], net.sizes[l][1])):

@@ -101,6 +101,7 @@ _SIGS = {
     "srcnn_forward_fused": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
     "srcnn_infer_rows_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _i, _vp]),
     "srcnn_train_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64]),
+    "srcnn_train_chunks_host": (_i, [_vp, C.POINTER(CNet), _vp, _vp, _i, _i, _i, _i, _u64]),
     "srcnn_train_chunk_buffers": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i,
                                        _u64, _u64, _u64, _u64, _u64, _u64]),
     "srcnn_train_workspace_bytes": (_sz, [C.POINTER(CNet), _i, _i, _i]),
@@ -378,6 +379,15 @@ class Net:
 
     def train_chunk(self, inp, gt, w, h, S, work):
         _check(self.ctx.L.srcnn_train_chunk(self.ctx.h, C.byref(self.c), inp, gt, w, h, S, work))
+
+    def train_chunks_host(self, host_in, host_gt, w, h, chunk, work):
+        """Forward + backward over HOST sample arrays [n][h][w] (pinned for overlap), uploads
+        pipelined with the training of the previous chunk; gradients accumulate."""
+        assert host_in.dtype == np.float32 and host_gt.dtype == np.float32
+        assert host_in.shape == host_gt.shape and host_in.flags.c_contiguous
+        _check(self.ctx.L.srcnn_train_chunks_host(self.ctx.h, C.byref(self.c), _np_ptr(host_in),
+                                                  _np_ptr(host_gt), w, h, int(host_in.shape[0]),
+                                                  chunk, work))
 
     def update_all(self, batch_size, momentum, decay, lr3):
         lr = (C.c_float * 3)(*[float(v) for v in lr3])

@@ -97,6 +97,9 @@ struct srcnn_ctx {
   void* band_in = nullptr;          // srcnn_infer_rows_host staging (device)
   void* band_out = nullptr;
   size_t band_in_bytes = 0, band_out_bytes = 0;
+  void* stage_in[2] = {nullptr, nullptr};   // srcnn_train_chunks_host staging (device)
+  void* stage_gt[2] = {nullptr, nullptr};
+  size_t stage_in_bytes[2] = {0, 0}, stage_gt_bytes[2] = {0, 0};
   // side streams + events of the pipelined host-buffer inference (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr, compute2 = nullptr;
   cudaEvent_t ev_in[16] = {}, ev_k[16] = {};

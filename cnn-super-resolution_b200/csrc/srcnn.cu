@@ -117,6 +117,10 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->splitk_scratch) cudaFree(ctx->splitk_scratch);
   if (ctx->band_in) cudaFree(ctx->band_in);
   if (ctx->band_out) cudaFree(ctx->band_out);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+    if (ctx->stage_gt[i]) cudaFree(ctx->stage_gt[i]);
+  }
   if (ctx->packed_params) cudaFree(ctx->packed_params);
   if (ctx->hp_scales) cudaFree(ctx->hp_scales);
   if (ctx->hp_cache) cudaFree(ctx->hp_cache);
@@ -859,6 +863,60 @@ int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
   SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
   Work wk{out1, out2, out3, d1, d2, d3};
   return train_chunk_on(ctx, net, in, gt, w, h, S, wk);
+}
+
+int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in,
+                            const float* host_gt, int w, int h, int n_samples, int chunk,
+                            srcnn_mem work) {
+  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
+  SRCNN_REQUIRE(ctx && host_in && host_gt, "null argument");
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(n_samples > 0 && chunk > 0 && d.w3 > 0 && d.h3 > 0,
+                "bad sample set: %d samples of %dx%d, chunk %d", n_samples, w, h, chunk);
+  const size_t per = sizeof(float) * (size_t)w * h;
+  const size_t need = per * (size_t)std::min(chunk, n_samples);
+  for (int b = 0; b < 2; b++) {
+    SRCNN_TRY(ensure_scratch(ctx, &ctx->stage_in[b], &ctx->stage_in_bytes[b], need));
+    SRCNN_TRY(ensure_scratch(ctx, &ctx->stage_gt[b], &ctx->stage_gt_bytes[b], need));
+  }
+  if (!ctx->copy_in) {
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  // the copy stream starts behind whatever the context stream was doing with the staging
+  SRCNN_CUDA(cudaEventRecord(ctx->ev_k[2], ctx->stream));
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[2], 0));
+  int rc = SRCNN_OK;
+  for (int i = 0, s0 = 0; s0 < n_samples && rc == SRCNN_OK; i++, s0 += chunk) {
+    const int S = std::min(chunk, n_samples - s0), b = i & 1;
+    // staging b was last read by the training of chunk i-2
+    if (i >= 2) SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[b], 0));
+    SRCNN_CUDA(cudaMemcpyAsync(ctx->stage_in[b], host_in + (size_t)s0 * w * h, per * S,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
+    SRCNN_CUDA(cudaMemcpyAsync(ctx->stage_gt[b], host_gt + (size_t)s0 * w * h, per * S,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->copy_in));
+    SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+    srcnn_mem mi, mg;
+    SRCNN_TRY(srcnn_wrap(ctx, ctx->stage_in[b], per * S, &mi));
+    SRCNN_TRY(srcnn_wrap(ctx, ctx->stage_gt[b], per * S, &mg));
+    Work wk;
+    rc = carve(ctx, net, work, w, h, S, &wk);
+    if (rc == SRCNN_OK) {
+      rc = train_chunk_on(ctx, net, mi, mg, w, h, S, wk);
+      uncarve(ctx);
+    }
+    ctx->allocs.resize(ctx->allocs.size() - 2);   // the two staging handles
+    if (rc == SRCNN_OK) SRCNN_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+  }
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_in));   // the host buffers may be reused
+  return rc;
 }
 
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,

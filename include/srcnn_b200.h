@@ -225,6 +225,18 @@ int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
                               int w, int h, int S, srcnn_mem out1, srcnn_mem out2,
                               srcnn_mem out3, srcnn_mem d1, srcnn_mem d2, srcnn_mem d3);
 
+/* ConfigBasedDataPipeline::execute_batch(backpropagate = true, ...)
+ * (src/ConfigBasedDataPipeline.cpp:128-195) on HOST-resident samples: `n_samples` inputs and
+ * ground truths of w x h floats each are cut into chunks of at most `chunk` samples; the upload
+ * of chunk i+1 (copy stream, double-buffered staging owned by the context) overlaps the
+ * forward + backward of chunk i (srcnn_train_chunk).  Gradients accumulate in net->grad_*;
+ * the caller all-reduces them (multi-GPU) and calls srcnn_update_all.  `work` must hold
+ * srcnn_train_workspace_bytes(net, w, h, chunk).  Returns once the host buffers may be reused;
+ * the last chunk may still be training on the context stream. */
+int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in,
+                            const float* host_gt, int w, int h, int n_samples, int chunk,
+                            srcnn_mem work);
+
 /* ConfigBasedDataPipeline::update_parameters (src/ConfigBasedDataPipeline.cpp:325-361) in
  * ONE launch: the three layers with lr[0..2], then the six accumulators are zeroed. */
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,

@@ -372,6 +372,29 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
         np.testing.assert_allclose(g["b%d" % (l + 1)], on.gb[l], rtol=RTOL, atol=1e-4, err_msg="gb%d" % l)
 
 
+def test_train_chunks_from_host_buffers(ctx, port):
+    """execute_batch(backpropagate=true) on host-resident samples (uploads pipelined with the
+    training of the previous chunk, ragged last chunk): gradients equal those of one device-
+    resident chunk over the same samples."""
+    n1, n2, f1, f2, f3, w, h, n = 64, 32, 9, 1, 5, 33, 33, 7
+    rng = np.random.default_rng(707)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x, gt = patches(rng, n, w, h)
+    net_a = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    work = ctx.alloc(net_a.train_workspace_bytes(w, h, n))
+    net_a.train_chunk(ctx.upload(x), ctx.upload(gt), w, h, n, work)
+    ga = net_a.grads()
+    net_b = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    hx, hg = pkg.PinnedBuffer(x.shape), pkg.PinnedBuffer(gt.shape)
+    hx.array[:], hg.array[:] = x, gt
+    net_b.train_chunks_host(hx.array, hg.array, w, h, 3, work)
+    ctx.block()
+    gb = net_b.grads()
+    for k in ga:
+        np.testing.assert_allclose(gb[k], ga[k], rtol=RTOL, atol=1e-5, err_msg=k)
+        assert np.abs(ga[k]).max() > 0
+
+
 @pytest.mark.parametrize("name", ["ref_train_chain.npz", "ref_train_915.npz"])
 def test_training_epochs_vs_committed_reference(ctx, name):
     """2 epochs x 2 chunks, momentum + weight decay: per-epoch parameters within 1e-4 relative

@@ -562,6 +562,30 @@ def test_fused_operand_cache_follows_the_parameters(ctx, port):
     check(net.params())
 
 
+def test_inference_random_shapes(ctx, port):
+    """Seeded sweep over ragged shapes of the fused 9-1-5 64/32 path: strip / band / batch
+    boundaries at arbitrary positions (1x1 outputs, one-column strips, S > 1 both as virtual
+    image and as separate images)."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    rng = np.random.default_rng(20261018)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    on = NetState(n1, n2, f1, f2, f3, params)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    shapes = [(13, 13, 1), (137, 13, 1), (13, 137, 2), (136, 40, 1), (261, 30, 1), (260, 31, 3)]
+    for _ in range(14):
+        shapes.append((int(rng.integers(13, 700)), int(rng.integers(13, 160)), int(rng.integers(1, 4))))
+    for (w, h, S) in shapes:
+        x = np.stack([luma_image(rng, h, w) for _ in range(S)])
+        _, _, e3 = port.net_forward(on, x, w, h, S)
+        (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+        mi, mo = ctx.upload(x), ctx.alloc(4 * S * w3 * h3)
+        net.forward_fused(mi, mo, w, h, S)
+        got = ctx.read(mo, (S, h3, w3))
+        assert float(np.abs(got - e3).max()) <= 1e-4, (w, h, S)
+        ctx.release(mi)
+        ctx.release(mo)
+
+
 def test_full_size_4096_properties(ctx, port):
     """BASELINE config C3 (4096x4096, 9-1-5 64/32) at full size, through size-independent
     properties: (1) random 48x48 output windows equal the oracle run on just their receptive

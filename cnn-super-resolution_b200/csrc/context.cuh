@@ -89,6 +89,7 @@ struct srcnn_ctx {
   bool hp_cache_valid = false;
   const void* hp_cache_key[6] = {};
   unsigned long long hp_cache_gen = 0;
+  int hp_cache_n1 = 0;
   unsigned long long write_gen = 0;   // bumped by every entry point that writes device memory
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes

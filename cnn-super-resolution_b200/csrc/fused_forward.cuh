@@ -66,6 +66,7 @@ struct Args {
   float* out;        // [S][h3][w3]
   const float *pw1, *pb1, *pw2, *pb2, *pw3, *pb3;
   int w, h, w3, h3;
+  const int* gate = nullptr;   // device word: run only if *gate != 0 (null: always run)
 };
 
 template <class C>
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256, 1) forward_fused_kernel(Args a) {
   float* sIn = smem + C::oIn;
   float* sO1 = smem + C::oO1;
   float* sO2 = smem + C::oO2;
+  if (a.gate && *a.gate == 0) return;   // a tensor-core launch ahead of us did the work
 
   const int tid = threadIdx.x;
   const int X0 = blockIdx.x * C::OW3;   // first output column == first input column

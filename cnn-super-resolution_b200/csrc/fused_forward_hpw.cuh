@@ -1,28 +1,13 @@
-// Fused SRCNN inference, FP16-split tensor-core version (9-1-5, n1=64, n2=32).
-//
-// Same structure as fused_forward_pl.cuh (plane operands, one MMA issuer per layer, in-place
-// TMEM operands, every buffer double) but every operand is split into two HALVES instead of two
-// TF32 terms:
-//     x * s = hi + lo / 2048        hi = half(x*s), lo = half((x*s - hi) * 2048)
-// with s a power of two that keeps both halves in the normal range.  x.w is evaluated as
-// hi.w_hi + (hi.w_lo + lo.w_hi) / 2048: the first product accumulates in one half of the
-// (stacked) accumulator, the two correction products -- which carry the extra factor 2048 -- in
-// the other, and the epilogue recombines them.  Accuracy is that of the 3xTF32 scheme (22
-// mantissa bits per operand; probe/f16_probe.cu: 2.5e-7 max error on a 9x9x64 tile), but
-//   * kind::f16 MMAs take K = 16 per instruction: 6 + 4 + 2 K-steps per tile instead of
-//     11 + 8 + 4, i.e. 24 instructions instead of 46, ~1 050 pipe cycles instead of ~2 050;
-//   * layer 1 reads "oct planes" O(s)[c] = rows s..s+7 of column c (8 halves = 16 bytes) and
-//     H8(r)[c] = in[r][c..c+7]: one O and one H8 plane per tile;
-//   * A2/A3 are packed half pairs: half the TMEM store traffic of the epilogues.
-//
-// Range.  The scales depend on the WEIGHTS only (computed on the device by hp_prepare_kernel;
-// cached per context until a device-layer call writes device memory; data-independent, so a row-band partition of an image reproduces the
-// single-launch result bit for bit) and assume |input| < 64, 64x the luma range:
-//     sx = 2^9;  sw_l = 2^14 / pow2ceil(max|W_l|);  s_l = 2^14 / pow2ceil(bound on out_l)
-// with bound(out1) = max_n(|b1| + sum|W1|) * 64 and bound(out2) likewise from bound(out1).
-// The plane producers check every input pixel they load: the first |x| >= 64 (or NaN) clears the
-// `ok` flag, and the TF32 kernel -- launched right behind this one with the flag as its gate --
-// redoes the whole launch.  No result ever depends on an FP16 overflow.
+// Fused SRCNN inference, FP16-split tensor-core version for the WIDE network of BASELINE config
+// C5 (9-1-5, n1=128, n2=64).  Same scheme as fused_forward_hp.cuh (oct planes, K = 16 MMAs,
+// scaled hi/lo halves, stacked weights, in-place TMEM operands, one issuer warp per layer,
+// prepacked operand image, device-side domain check) -- read that file first.  What differs:
+//   * the stacked layer-1 accumulator is 2*n1 = 256 TMEM columns, layer 2's 128, layer 3's 64:
+//     448 of 512 columns with ONE buffer each, so tiles overlap only across layers: MMA-1(b+1)
+//     waits until MMA-2(b) has read A2(b) out of the D1 columns, MMA-2(b+1) until MMA-3(b) has
+//     read A3(b), MMA-3(b+1) until E3(b) has drained D3;
+//   * E1 / E2 convert their 64 channels per thread in two rounds (register budget);
+//   * the fallback behind the device-side gate is the FP32 SIMT fused kernel (fused_forward.cuh).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -35,10 +20,10 @@
 #include "tc_common.cuh"
 
 namespace srcnn {
-namespace fused_hp {
+namespace fused_hpw {
 
 struct Cfg {
-  static constexpr int N1 = 64, N2 = 32, F1 = 9, F3 = 5;
+  static constexpr int N1 = 128, N2 = 64, F1 = 9, F3 = 5;
   static constexpr int M = 128;
   static constexpr int OW3 = M - (F3 - 1);
   static constexpr int KS1 = 6, K1 = KS1 * 16;   // halves: 81 taps + 15 zero weights
@@ -46,10 +31,7 @@ struct Cfg {
   static constexpr int PW = 144;                 // plane entries (16 bytes = 8 halves each)
   static constexpr int PB = PW * 16;             // bytes per plane
   static constexpr int RO = 4, RH = 4;           // ring slots: oct planes, H8 planes
-#ifndef HP_N_E1
-#define HP_N_E1 8
-#endif
-  static constexpr int W_E1 = 0, N_E1 = HP_N_E1, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4,
+  static constexpr int W_E1 = 0, N_E1 = 8, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4,
                        N_IM = 5, W_I1 = W_IM + N_IM, W_I2 = W_I1 + 1, W_I3 = W_I2 + 1;
   static constexpr int NT = (W_I3 + 1) * 32;
   static constexpr int E1_CHUNKS = (N1 / 16) / (N_E1 / 4);   // 16-channel chunks per E1 warp
@@ -68,11 +50,11 @@ struct Cfg {
   static constexpr int oQs = oB2 + N2 * 4;           // 2 staged Q rows [M][QP] floats
   static constexpr int TOTAL = oQs + 2 * M * QP * 4;
   static constexpr size_t SMEM_BYTES = (size_t)TOTAL;
-  // tensor memory columns (+ size * (b & 1)):
-  //   D1: [0,64) hi.w_hi, [64,128) corrections  ->  A2: hi pairs of channels 16g..16g+15 at
-  //       a2col(g) = 32*(g/2) + 8*(g%2), lo pairs at 64 + a2col(g): inside the columns the SAME
-  //       E1 warp has already read, whether 4 or 8 warps share the 64 channels
-  //   D2: [0,32), [32,64)                       ->  A3: [0,16) hi pairs, [32,48) lo pairs
+  // tensor memory columns, ONE buffer each:
+  //   D1: [0,128) hi.w_hi, [128,256) corrections -> A2: hi pairs of channels 16g..16g+15 at
+  //       a2col(g) = 64*(g/4) + 8*(g%4), lo pairs at 128 + a2col(g) (columns the same E1 warp
+  //       has already read)
+  //   D2: [0,64), [64,128)   ->  A3: hi pairs at 8g, lo pairs at 64 + 8g
   //   D3: [0,32), [32,64) (25 taps of 32 used)
   static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
   static constexpr uint32_t TMEM_COLS = 512;
@@ -87,7 +69,7 @@ struct ScaleVals {
   float inv_s1, inv_s2;
   int ok;         // 1: the input is inside the FP16 domain, this kernel runs; 0: the TF32 one
 };
-// what hp_prepare_kernel leaves for the main kernel: the scales and the ready-made shared-memory
+// what hpw_prepare_kernel leaves for the main kernel: the scales and the ready-made shared-memory
 // image of the B operands (scaled, split, in the canonical K-major layout) and scaled biases, so
 // that a CTA's prologue is a 37 KB copy instead of 24 576 scattered conversions -- the CTAs of a
 // training chunk or of a multi-GPU row band only live for 25..130 tiles
@@ -179,11 +161,7 @@ __device__ __forceinline__ float pow2_scale(float bound) {   // 2^14 / pow2ceil(
   frexpf(bound, &e);                 // bound = f * 2^e, f in [0.5, 1)
   return ldexpf(1.f, 14 - e);
 }
-__global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* sc) {
-  // the parameters are staged in shared memory with coalesced loads first: the column sums
-  // below would otherwise be chains of dependent global loads (13 us instead of ~3)
-  __shared__ float sw1[Cfg::F1 * Cfg::F1 * Cfg::N1];   // |W1| [tap][n]
-  __shared__ float sw2[Cfg::N1 * Cfg::N2];             // |W2| [k][n]
+__global__ void __launch_bounds__(256) hpw_prepare_kernel(fused::Args a, Scales* sc) {
   __shared__ float red_f[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto block_max = [&](float v) -> float {
@@ -197,16 +175,8 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
     return r;
   };
   float v1 = 0.f, v2 = 0.f, v3 = 0.f;
-  for (int i = tid; i < Cfg::F1 * Cfg::F1 * Cfg::N1; i += 256) {
-    const float w = fabsf(__ldg(a.pw1 + i));
-    sw1[i] = w;
-    v1 = fmaxf(v1, w);
-  }
-  for (int i = tid; i < Cfg::N1 * Cfg::N2; i += 256) {
-    const float w = fabsf(__ldg(a.pw2 + i));
-    sw2[i] = w;
-    v2 = fmaxf(v2, w);
-  }
+  for (int i = tid; i < Cfg::F1 * Cfg::F1 * Cfg::N1; i += 256) v1 = fmaxf(v1, fabsf(__ldg(a.pw1 + i)));
+  for (int i = tid; i < Cfg::N1 * Cfg::N2; i += 256) v2 = fmaxf(v2, fabsf(__ldg(a.pw2 + i)));
   for (int i = tid; i < Cfg::QP * Cfg::N2; i += 256) v3 = fmaxf(v3, fabsf(__ldg(a.pw3 + i)));
   const float b1v = tid < Cfg::N1 ? fabsf(__ldg(a.pb1 + tid)) : 0.f;
   const float b2v = tid < Cfg::N2 ? fabsf(__ldg(a.pb2 + tid)) : 0.f;
@@ -216,11 +186,12 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
   // bound on |out1[n]| and, from it, on |out2[n]|
   float v = 0.f;
   if (tid < Cfg::N1) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;   // coalesced across the threads (n fastest)
+#pragma unroll 9
     for (int t = 0; t < Cfg::F1 * Cfg::F1; t += 3) {
-      s0 += sw1[t * Cfg::N1 + tid];
-      s1 += sw1[(t + 1) * Cfg::N1 + tid];
-      s2 += sw1[(t + 2) * Cfg::N1 + tid];
+      s0 += fabsf(__ldg(a.pw1 + t * Cfg::N1 + tid));
+      s1 += fabsf(__ldg(a.pw1 + (t + 1) * Cfg::N1 + tid));
+      s2 += fabsf(__ldg(a.pw1 + (t + 2) * Cfg::N1 + tid));
     }
     v = (s0 + s1 + s2) * kInMax + b1v;
   }
@@ -228,9 +199,10 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
   v = 0.f;
   if (tid < Cfg::N2) {
     float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
     for (int k = 0; k < Cfg::N1; k += 2) {
-      s0 += sw2[k * Cfg::N2 + tid];
-      s1 += sw2[(k + 1) * Cfg::N2 + tid];
+      s0 += fabsf(__ldg(a.pw2 + k * Cfg::N2 + tid));
+      s1 += fabsf(__ldg(a.pw2 + (k + 1) * Cfg::N2 + tid));
     }
     v = (s0 + s1) * bound1 + b2v;
   }
@@ -289,7 +261,7 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
 
 // ---------------------------------------------------------------------------- main kernel ----
 template <bool BATCH>
-__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Args a, int rpc,
+__global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Args a, int rpc,
                                                                       BatchExt bx,
                                                                       const Scales* scales,
                                                                       int* fallback) {
@@ -307,8 +279,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   float* sB1 = reinterpret_cast<float*>(smem_raw + C::oB1);
   float* sB2 = reinterpret_cast<float*>(smem_raw + C::oB2);
   float* sQs = reinterpret_cast<float*>(smem_raw + C::oQs);
-  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2],
-      a3_full[2], bar3[2], d3_free[2];
+  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1, a2_full, bar2, a3_full, bar3,
+      d3_free;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,7 +289,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   const float* img = BATCH ? a.in : a.in + (size_t)blockIdx.z * a.w * a.h;
   float* dst = BATCH ? a.out : a.out + (size_t)blockIdx.z * a.w3 * a.h3;
 
-  // ---- B operands and scaled biases: the image hp_prepare_kernel packed ---------------------
+  // ---- B operands and scaled biases: the image hpw_prepare_kernel packed ---------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(scales->wimg);
     uint4* dstw = reinterpret_cast<uint4*>(smem_raw + C::oW1);
@@ -335,14 +307,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       mbar_init(&p_full[i], C::IM_THREADS);
       mbar_init(&p_free[i], 1);
     }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&bar1[i], 1);
-      mbar_init(&a2_full[i], C::N_E1 * 32);
-      mbar_init(&bar2[i], 1);
-      mbar_init(&a3_full[i], 128);
-      mbar_init(&bar3[i], 1);
-      mbar_init(&d3_free[i], 128);
-    }
+    mbar_init(&bar1, 1);
+    mbar_init(&a2_full, C::N_E1 * 32);
+    mbar_init(&bar2, 1);
+    mbar_init(&a3_full, 128);
+    mbar_init(&bar3, 1);
+    mbar_init(&d3_free, 128);
   }
   fence_proxy_async();
   tcgen05_fence_before();
@@ -460,10 +430,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     };
     for (int t = 0; t < n_tiles; t++) {
       mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1));
-      // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
-      if (t >= 2) mbar_wait(&bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      // D1 still holds A2(t-1) until MMA-2(t-1) has read it
+      if (t >= 1) mbar_wait(&bar2, (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
-      const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
+      const uint32_t d1 = tmem + C::cD1;
       const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
       const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * C::PB;
       PL_EV(t, 0)
@@ -480,7 +450,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
           mma_f16_ss(d1, adesc(ah, lbo_h), wdesc + 16 * s, idesc_hi, s > 0);
           mma_f16_ss(d1 + C::N1, adesc(al, lbo_l), wdesc + 16 * s, idesc_lo, 1);
         }
-        mma_commit(&bar1[t & 1]);
+        mma_commit(&bar1);
         mma_commit(&p_free[t & 3]);
       }
       __syncwarp();
@@ -492,21 +462,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::N2);
     const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1));
-      // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
-      if (t >= 2) mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      mbar_wait(&a2_full, (uint32_t)(t & 1));
+      // D2 still holds A3(t-1) until MMA-3(t-1) has read it
+      if (t >= 1) mbar_wait(&bar3, (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
-      const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
-      const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      const uint32_t a2 = tmem + C::cD1;
+      const uint32_t d2 = tmem + C::cD2;
       PL_EV(t, 4)
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K2 / 16; ks++) {
-          const uint32_t col = 32u * (ks >> 1) + 8u * (ks & 1);   // a2col(ks)
+          const uint32_t col = 64u * (ks >> 2) + 8u * (ks & 3);   // a2col(ks)
           mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_hi, ks > 0);
           mma_f16_ts(d2 + C::N2, a2 + C::N1 + col, wdesc + 16 * ks, idesc_lo, 1);
         }
-        mma_commit(&bar2[t & 1]);
+        mma_commit(&bar2);
       }
       __syncwarp();
       PL_EV(t, 5)
@@ -517,11 +487,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::NT3);
     const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::K3 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1));
-      if (t >= 2) mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      mbar_wait(&a3_full, (uint32_t)(t & 1));
+      if (t >= 1) mbar_wait(&d3_free, (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
-      const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
-      const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+      const uint32_t a3 = tmem + C::cD2;
+      const uint32_t d3 = tmem + C::cD3;
       PL_EV(t, 8)
       if (elect_one()) {
 #pragma unroll
@@ -529,7 +499,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
           mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
           mma_f16_ts(d3 + C::NT3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
         }
-        mma_commit(&bar3[t & 1]);
+        mma_commit(&bar3);
       }
       __syncwarp();
       PL_EV(t, 9)
@@ -537,8 +507,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   } else if (warp < C::W_E1 + C::N_E1) {
     // ============================ E1: A2 = split(relu(out1) * s1), in place ================
     // warp w: TMEM lane quarter w&3, chunks g0 .. g0+E1_CHUNKS-1 of 16 channels.  Chunk g reads
-    // D1 columns [16g,16g+16) and [64+16g, ..), then writes its hi pairs to a2col(g) and its lo
-    // pairs to 64 + a2col(g): columns this warp has consumed
+    // D1 columns [16g,16g+16) and [128+16g, ..), then writes its hi pairs to a2col(g) and its lo
+    // pairs to 128 + a2col(g): columns this warp has consumed
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int g0 = (warp >> 2) * C::E1_CHUNKS;
     float* o1 = nullptr;
@@ -550,42 +520,46 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
+      mbar_wait(&bar1, (uint32_t)(b & 1));                     // MMA-1(b) done
       if (warp == 0) PL_EV(b, 2)
       tcgen05_fence_after();
-      const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
-      // all loads of this warp's chunks first (one TMEM round trip), then the conversions
-      float va[C::E1_CHUNKS][16], vb[C::E1_CHUNKS][16];
+      const uint32_t d1 = tmem + lane_base + C::cD1;
+      // two rounds of two chunks: the loads of a round first (one TMEM round trip), then the
+      // conversions.  Round 1 writes into columns round 0 has read
 #pragma unroll
-      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
-        tmem_ld16_nowait(d1 + (g0 + gl) * 16, va[gl]);
-        tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
-      }
-      tmem_ld_wait();
+      for (int rd = 0; rd < C::E1_CHUNKS / 2; rd++) {
+        float va[2][16], vb[2][16];
 #pragma unroll
-      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
-        const int g = g0 + gl;
-        uint32_t hi[8], lo[8];
-        float act[16];
+        for (int gl = 0; gl < 2; gl++) {
+          tmem_ld16_nowait(d1 + (g0 + 2 * rd + gl) * 16, va[gl]);
+          tmem_ld16_nowait(d1 + C::N1 + (g0 + 2 * rd + gl) * 16, vb[gl]);
+        }
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c1s, sB1[g * 16 + j]), 0.f);
+        for (int gl = 0; gl < 2; gl++) {
+          const int g = g0 + 2 * rd + gl;
+          uint32_t hi[8], lo[8];
+          float act[16];
 #pragma unroll
-        for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-        const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
-        tmem_st8u(d1 + col, hi);
-        tmem_st8u(d1 + C::N1 + col, lo);
-        if (BATCH && o1) {
-          float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
+          for (int j = 0; j < 16; j++)
+            act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c1s, sB1[g * 16 + j]), 0.f);
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            q[j] = make_float4(act[4 * j] * sc.inv_s1, act[4 * j + 1] * sc.inv_s1,
-                               act[4 * j + 2] * sc.inv_s1, act[4 * j + 3] * sc.inv_s1);
+          for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
+          const uint32_t col = 64u * (uint32_t)(g >> 2) + 8u * (uint32_t)(g & 3);   // a2col(g)
+          tmem_st8u(d1 + col, hi);
+          tmem_st8u(d1 + C::N1 + col, lo);
+          if (BATCH && o1) {
+            float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              q[j] = make_float4(act[4 * j] * sc.inv_s1, act[4 * j + 1] * sc.inv_s1,
+                                 act[4 * j + 2] * sc.inv_s1, act[4 * j + 3] * sc.inv_s1);
+          }
         }
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&a2_full[b & 1]);
+      mbar_arrive(&a2_full);
       if (warp == 0) PL_EV(b, 3)
     }
   } else if (warp < C::W_E3) {
@@ -600,40 +574,45 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
+      mbar_wait(&bar2, (uint32_t)(b & 1));                     // MMA-2(b) done
       if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
-      const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
-      // all loads first (one TMEM round trip), then the conversions
-      float va[2][16], vb[2][16];
+      const uint32_t d2 = tmem + lane_base + C::cD2;
+      // two rounds of two chunks, as in E1; hi pairs of chunk g land on [8g, 8g+8): columns of
+      // chunks <= g/2, read in this round or an earlier one
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        tmem_ld16_nowait(d2 + g * 16, va[g]);
-        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb[g]);
-      }
-      tmem_ld_wait();
+      for (int rd = 0; rd < C::N2 / 32; rd++) {
+        float va[2][16], vb[2][16];
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        uint32_t hi[8], lo[8];
-        float act[16];
+        for (int gl = 0; gl < 2; gl++) {
+          tmem_ld16_nowait(d2 + (2 * rd + gl) * 16, va[gl]);
+          tmem_ld16_nowait(d2 + C::N2 + (2 * rd + gl) * 16, vb[gl]);
+        }
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[g][j], 1.f / 2048.f, va[g][j]), sc.c2s, sB2[g * 16 + j]), 0.f);
+        for (int gl = 0; gl < 2; gl++) {
+          const int g = 2 * rd + gl;
+          uint32_t hi[8], lo[8];
+          float act[16];
 #pragma unroll
-        for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-        tmem_st8u(d2 + g * 8, hi);
-        tmem_st8u(d2 + C::N2 + g * 8, lo);
-        if (BATCH && o2) {
-          float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16);
+          for (int j = 0; j < 16; j++)
+            act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c2s, sB2[g * 16 + j]), 0.f);
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            q[j] = make_float4(act[4 * j] * sc.inv_s2, act[4 * j + 1] * sc.inv_s2,
-                               act[4 * j + 2] * sc.inv_s2, act[4 * j + 3] * sc.inv_s2);
+          for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
+          tmem_st8u(d2 + g * 8, hi);
+          tmem_st8u(d2 + C::N2 + g * 8, lo);
+          if (BATCH && o2) {
+            float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              q[j] = make_float4(act[4 * j] * sc.inv_s2, act[4 * j + 1] * sc.inv_s2,
+                                 act[4 * j + 2] * sc.inv_s2, act[4 * j + 3] * sc.inv_s2);
+          }
         }
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&a3_full[b & 1]);
+      mbar_arrive(&a3_full);
       if (warp == C::W_E2) PL_EV(b, 7)
     }
   } else if (warp < C::W_IM) {
@@ -652,10 +631,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-3(b) done
+      mbar_wait(&bar3, (uint32_t)(b & 1));                     // MMA-3(b) done
       if (warp == C::W_E3) PL_EV(b, 10)
       tcgen05_fence_after();
-      const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
+      const uint32_t d3 = tmem + lane_base + C::cD3;
       float v[32], w[32];
       tmem_ld16_nowait(d3, v);
       tmem_ld16_nowait(d3 + 16, v + 16);
@@ -663,7 +642,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tmem_ld16_nowait(d3 + 48, w + 16);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
+      mbar_arrive(&d3_free);                                   // D3 may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
       for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]);
@@ -712,57 +691,32 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
 }
 
 inline int configure() {
-  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<false>,
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hpw_kernel<false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::SMEM_BYTES));
-  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<true>,
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hpw_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::SMEM_BYTES));
   return SRCNN_OK;
 }
 
 inline bool supported(int n1, int n2, int f1, int f2, int f3) {
-  return n1 == 64 && n2 == 32 && f1 == 9 && f2 == 1 && f3 == 5;
+  return n1 == Cfg::N1 && n2 == Cfg::N2 && f1 == 9 && f2 == 1 && f3 == 5;
 }
 
-// the per-context ring of scale blocks: launches on different streams (the pipelined
-// host-buffer inference) must not share one
-inline int scale_slot(srcnn_ctx* ctx, Scales** sc, unsigned** ws) {
-  constexpr int kSlots = 32;
-  if (!ctx->hp_scales) {
-    SRCNN_CUDA(cudaMalloc(&ctx->hp_scales, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));
-    SRCNN_CUDA(cudaMemset(ctx->hp_scales, 0, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));
-  }
-  const int i = (int)(ctx->hp_next++ % kSlots);
-  *sc = reinterpret_cast<Scales*>(ctx->hp_scales) + i;
-  *ws = reinterpret_cast<unsigned*>(reinterpret_cast<Scales*>(ctx->hp_scales) + kSlots) + 2 * i;
-  return SRCNN_OK;
+// the operand image of a network, packed on the context stream into `block`
+inline void prepare(srcnn_ctx* ctx, const fused::Args& a, void* block) {
+  hpw_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, reinterpret_cast<Scales*>(block));
 }
 
-// the scales and operand image of a network, computed on the context stream into `block`
-inline void prepare_into(srcnn_ctx* ctx, const fused::Args& a, void* block) {
-  hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, reinterpret_cast<Scales*>(block));
-}
-
-// [prepare +] FP16 kernel + (gated) TF32 kernel; `S` images, or a batch as one virtual image.
-// `shared` = scales already prepared for these parameters (the sub-bands of
-// srcnn_infer_rows_host, or the context's cache); null = prepare here.  The scales are read-only
-// for the kernels; "leave this launch to the TF32 kernel" is a per-launch word of the ring.
-inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float* out1,
-                  float* out2, const Scales* shared = nullptr) {
-  const Scales* sc = shared;
-  Scales* slot;
-  unsigned* ws;
-  SRCNN_TRY(scale_slot(ctx, &slot, &ws));
-  if (!sc) {
-    hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(a, slot);
-    sc = slot;
-  }
-  int* fallback = reinterpret_cast<int*>(ws);
+// FP16 kernel + (gated) FP32 SIMT kernel; `S` images, or a batch as one virtual image.
+// `sc` = the operand image prepared for these parameters; `fallback` = this launch's
+// "leave it to the FP32 kernel" word.
+inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, const Scales* sc,
+                  int* fallback) {
   SRCNN_CUDA(cudaMemsetAsync(fallback, 0, sizeof(int), ctx->stream));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   BatchExt bx{};
-  bx.gate = fallback;
   if (batch) {
     fused::Args v = a;
     const int pad = Cfg::F1 + Cfg::F3 - 2;
@@ -770,25 +724,21 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
     v.w3 = S * a.w - pad;
     const int rpc = fused_pl::rows_per_cta(v.w3, v.h3, 1, sms);
     dim3 grid((v.w3 + Cfg::OW3 - 1) / Cfg::OW3, (v.h3 + rpc - 1) / rpc, 1);
-    bx.out1 = out1;
-    bx.out2 = out2;
     bx.S = S;
     bx.pw = a.w;
     bx.ph = a.h;
-    forward_fused_hp_kernel<true>
+    forward_fused_hpw_kernel<true>
         <<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx, sc, fallback);
-    fused_pl::forward_fused_pl_kernel<true>
-        <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx);
   } else {
     const int rpc = fused_pl::rows_per_cta(a.w3, a.h3, S, sms);
     dim3 grid((a.w3 + Cfg::OW3 - 1) / Cfg::OW3, (a.h3 + rpc - 1) / rpc, S);
-    forward_fused_hp_kernel<false>
+    forward_fused_hpw_kernel<false>
         <<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx, sc, fallback);
-    fused_pl::forward_fused_pl_kernel<false>
-        <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx);
   }
-  return SRCNN_OK;
+  fused::Args g = a;
+  g.gate = fallback;
+  return fused::launch(ctx, Cfg::N1, Cfg::N2, g, S);
 }
 
-}  // namespace fused_hp
+}  // namespace fused_hpw
 }  // namespace srcnn

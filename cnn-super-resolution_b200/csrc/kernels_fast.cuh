@@ -11,6 +11,7 @@
 #include "fused_forward_ws.cuh"
 #include "fused_forward_pl.cuh"
 #include "fused_forward_hp.cuh"
+#include "fused_forward_hpw.cuh"
 #include "train_kernels.cuh"
 #include "deltas_tc.cuh"
 #include "wgrad_tc.cuh"
@@ -64,6 +65,7 @@ inline int configure(srcnn_ctx* ctx) {
   SRCNN_TRY(fused_ws::configure());
   SRCNN_TRY(fused_pl::configure());
   SRCNN_TRY(fused_hp::configure());
+  SRCNN_TRY(fused_hpw::configure());
   // A/B switch between the generations of the fused kernel (default: the newest)
   const char* impl = std::getenv("SRCNN_FUSED_IMPL");
   ctx->fused_impl = 4;                                           // "hp": planes, FP16 split
@@ -121,20 +123,65 @@ inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {
   return fused::supported(n1, n2, f1, f2, f3);
 }
 
-// `scales`: fused_hp::Scales block shared by a series of launches (or null)
+// prepared operand image for forward_fused launches with these parameters (null when the
+// selected kernel needs none).  `cacheable`: the six buffers are context-owned allocations, so
+// nothing outside the device layer can have changed them since ctx->write_gen was recorded.
+inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* w1,
+                         const float* b1, const float* w2, const float* b2, const float* w3,
+                         const float* b3, bool cacheable, const void** out) {
+  *out = nullptr;
+  const bool wide = fused_hpw::supported(n1, n2, f1, f2, f3);
+  if (ctx->fused_impl != 4 || !(wide || fused_hp::supported(n1, n2, f1, f2, f3))) return SRCNN_OK;
+  const void* key[6] = {w1, b1, w2, b2, w3, b3};
+  if (cacheable && ctx->hp_cache_valid && ctx->hp_cache_gen == ctx->write_gen &&
+      ctx->hp_cache_n1 == n1 && std::memcmp(key, ctx->hp_cache_key, sizeof(key)) == 0) {
+    *out = ctx->hp_cache;
+    return SRCNN_OK;
+  }
+  if (!ctx->hp_cache) {
+    constexpr size_t bytes = sizeof(fused_hpw::Scales) > sizeof(fused_hp::Scales)
+                                 ? sizeof(fused_hpw::Scales) : sizeof(fused_hp::Scales);
+    SRCNN_CUDA(cudaMalloc(&ctx->hp_cache, bytes));
+  }
+  fused::Args a{nullptr, nullptr, w1, b1, w2, b2, w3, b3, 0, 0, 0, 0};
+  if (wide)
+    fused_hpw::prepare(ctx, a, ctx->hp_cache);
+  else
+    fused_hp::prepare_into(ctx, a, ctx->hp_cache);
+  *out = ctx->hp_cache;
+  ctx->hp_cache_valid = cacheable;
+  ctx->hp_cache_gen = ctx->write_gen;
+  ctx->hp_cache_n1 = n1;
+  std::memcpy(ctx->hp_cache_key, key, sizeof(key));
+  return SRCNN_OK;
+}
+
+// `scales`: the operand image fused_prepare returned for these parameters, shared by a series of
+// launches (or null)
 inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* in,
                          float* out, const float* w1, const float* b1, const float* w2,
                          const float* b2, const float* w3, const float* b3, int in_w, int in_h,
-                         int S, const fused_hp::Scales* scales = nullptr) {
+                         int S, const void* scales = nullptr) {
   if (!fused::supported(n1, n2, f1, f2, f3))
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
+  if (ctx->fused_impl == 4 && fused_hpw::supported(n1, n2, f1, f2, f3)) {
+    // the wide network (n1 = 128, n2 = 64)
+    const bool as_batch = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30);
+    if (!scales) SRCNN_TRY(fused_prepare(ctx, n1, n2, f1, f2, f3, w1, b1, w2, b2, w3, b3, false, &scales));
+    fused_hp::Scales* unused;
+    unsigned* ws;
+    SRCNN_TRY(fused_hp::scale_slot(ctx, &unused, &ws));
+    return fused_hpw::launch(ctx, a, S, as_batch, static_cast<const fused_hpw::Scales*>(scales),
+                             reinterpret_cast<int*>(ws));
+  }
   if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
     // batches of small samples (validation patches) go through the virtual-image variant
     const bool as_batch = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30);
     if (ctx->fused_impl == 4)
-      return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr, scales);
+      return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr,
+                              static_cast<const fused_hp::Scales*>(scales));
     if (ctx->fused_impl == 3 && as_batch) return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
     if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
     return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
@@ -144,29 +191,10 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
 
 // kernels one fused forward call launches: the FP16-split path is prepare + main + gated TF32
 inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
-  return ctx->fused_impl == 4 && fused_hp::supported(n1, n2, f1, f2, f3) ? 3 : 1;
-}
-
-// prepared operand image for forward_fused launches with these parameters (null when the
-// selected kernel needs none).  `cacheable`: the six buffers are context-owned allocations, so
-// nothing outside the device layer can have changed them since ctx->write_gen was recorded.
-inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3, const float* w1,
-                         const float* b1, const float* w2, const float* b2, const float* w3,
-                         const float* b3, bool cacheable, const fused_hp::Scales** out) {
-  *out = nullptr;
-  if (ctx->fused_impl != 4 || !fused_hp::supported(n1, n2, f1, f2, f3)) return SRCNN_OK;
-  const void* key[6] = {w1, b1, w2, b2, w3, b3};
-  if (cacheable && ctx->hp_cache_valid && ctx->hp_cache_gen == ctx->write_gen &&
-      std::memcmp(key, ctx->hp_cache_key, sizeof(key)) == 0) {
-    *out = reinterpret_cast<const fused_hp::Scales*>(ctx->hp_cache);
-    return SRCNN_OK;
-  }
-  fused::Args a{nullptr, nullptr, w1, b1, w2, b2, w3, b3, 0, 0, 0, 0};
-  SRCNN_TRY(fused_hp::prepare_cached(ctx, a, out));
-  ctx->hp_cache_valid = cacheable;
-  ctx->hp_cache_gen = ctx->write_gen;
-  std::memcpy(ctx->hp_cache_key, key, sizeof(key));
-  return SRCNN_OK;
+  if (ctx->fused_impl != 4) return 1;
+  if (fused_hp::supported(n1, n2, f1, f2, f3)) return 3;    // prepare + FP16 + gated TF32
+  if (fused_hpw::supported(n1, n2, f1, f2, f3)) return 3;   // prepare + FP16 + gated FP32
+  return 1;
 }
 
 inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {

@@ -580,7 +580,7 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
     SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
     for (int l = 0; l < 3; l++)   // writing the result into a parameter buffer?  (nobody does)
       if (out == net->w[l] || out == net->b[l]) ctx->write_gen++;
-    const fused_hp::Scales* scales = nullptr;
+    const void* scales = nullptr;
     SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2,
                                   w3, b3, params_owned(ctx, net), &scales));
     LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
@@ -666,7 +666,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   float* dout = (float*)ctx->band_out;
   // one set of operand scales for all sub-bands (computed on the context stream, before the
   // event the side streams wait for)
-  const fused_hp::Scales* scales = nullptr;
+  const void* scales = nullptr;
   SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
                                 b3, params_owned(ctx, net), &scales));
   if (n_sub == 1) {

@@ -435,7 +435,10 @@ INFER = [
     (64, 32, 9, 1, 5, 500, 40, 3),      # wide and flat, S>1
     (64, 32, 9, 1, 5, 600, 30, 2),      # S>1 but too wide for the virtual-image variant
     (64, 32, 9, 5, 5, 96, 80, 1),       # 9-5-5
-    (128, 64, 9, 1, 5, 120, 67, 1),     # C5's network
+    (128, 64, 9, 1, 5, 120, 67, 1),     # C5's network (the wide tensor-core kernel)
+    (128, 64, 9, 1, 5, 300, 150, 2),    # ... more strips than one, S>1
+    (128, 64, 9, 1, 5, 33, 33, 11),     # ... validation patches as a virtual wide image
+    (128, 64, 9, 1, 5, 13, 14, 1),      # ... 1x2 output
     (32, 16, 9, 1, 5, 64, 64, 1),       # example_config.json
     (4, 3, 3, 1, 3, 20, 11, 2),         # no fused instantiation -> three-launch path
 ]
@@ -469,8 +472,8 @@ def test_inference_vs_oracle(ctx, port, cfg):
         ctx.release(m)
 
 
-def _fused_vs_oracle(ctx, port, params, x, w, h):
-    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+def _fused_vs_oracle(ctx, port, params, x, w, h, n1=64, n2=32):
+    f1, f2, f3 = 9, 1, 5
     on = NetState(n1, n2, f1, f2, f3, params)
     _, _, e3 = port.net_forward(on, x, w, h, 1)
     net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
@@ -483,15 +486,17 @@ def _fused_vs_oracle(ctx, port, params, x, w, h):
     return got, e3
 
 
-def test_fused_fp16_domain_fallback(ctx, port):
+@pytest.mark.parametrize("n1,n2", [(64, 32), (128, 64)])
+def test_fused_fp16_domain_fallback(ctx, port, n1, n2):
     """The default fused kernel splits operands into FP16 halves with scales that assume
     |input| < 64.  Inputs outside that domain must still give the reference's result: the
-    kernel flags them on the device and the 3xTF32 kernel launched behind it redoes the launch.
+    kernel flags them on the device and the kernel launched behind it (3xTF32 for 64/32, FP32
+    SIMT for the wide network) redoes the launch.
     Also: inputs near the domain edge, and parameters far from O(1), stay within a RELATIVE
     1e-5 of the oracle (the absolute 1e-4 of north_star is for luma-range data)."""
     w, h = 200, 90
     rng = np.random.default_rng(64)
-    params = make_params(rng, 64, 32, 9, 1, 5)
+    params = make_params(rng, n1, n2, 9, 1, 5)
     x = luma_image(rng, h, w)
 
     def close(got, exp):
@@ -502,25 +507,26 @@ def test_fused_fp16_domain_fallback(ctx, port):
     # one pixel far outside the domain, in the last strip / last rows
     x1 = x.copy()
     x1[h - 1, w - 1] = 1000.0
-    close(*_fused_vs_oracle(ctx, port, params, x1, w, h))
+    close(*_fused_vs_oracle(ctx, port, params, x1, w, h, n1, n2))
     # everything outside the domain
-    close(*_fused_vs_oracle(ctx, port, params, (x * 400.0 - 100.0).astype(np.float32), w, h))
+    close(*_fused_vs_oracle(ctx, port, params, (x * 400.0 - 100.0).astype(np.float32), w, h, n1, n2))
     # inside the domain but 60x the luma range (FP16 path, large activations)
-    close(*_fused_vs_oracle(ctx, port, params, (x * 120.0 - 60.0).astype(np.float32), w, h))
+    close(*_fused_vs_oracle(ctx, port, params, (x * 120.0 - 60.0).astype(np.float32), w, h, n1, n2))
     # the reference's own initialisation scale, N(0, 0.001) (example_config.json:12-29), and
     # large parameters
     for k in (1e-3 / 0.11, 30.0):
         p2 = {name: (v * k).astype(np.float32) for name, v in params.items()}
-        got, exp = _fused_vs_oracle(ctx, port, p2, x, w, h)
+        got, exp = _fused_vs_oracle(ctx, port, p2, x, w, h, n1, n2)
         assert np.isfinite(got).all()
         assert float(np.abs(got - exp).max()) <= 1e-5 * float(np.abs(exp).max()) + 1e-9
 
 
-def test_fused_operand_cache_follows_the_parameters(ctx, port):
+@pytest.mark.parametrize("n1,n2", [(64, 32), (128, 64)])
+def test_fused_operand_cache_follows_the_parameters(ctx, port, n1, n2):
     """The fused kernel's packed operand image is cached per context; every way the
     parameters can change on the device must invalidate it: a host write, a device copy, a
     fill, and the training update."""
-    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    f1, f2, f3 = 9, 1, 5
     w, h = 150, 40
     rng = np.random.default_rng(77)
     params = make_params(rng, n1, n2, f1, f2, f3)

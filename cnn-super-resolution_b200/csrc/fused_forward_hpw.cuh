@@ -1,12 +1,20 @@
 // Fused SRCNN inference, FP16-split tensor-core version for the WIDE network of BASELINE config
 // C5 (9-1-5, n1=128, n2=64).  Same scheme as fused_forward_hp.cuh (oct planes, K = 16 MMAs,
-// scaled hi/lo halves, stacked weights, in-place TMEM operands, one issuer warp per layer,
-// prepacked operand image, device-side domain check) -- read that file first.  What differs:
-//   * the stacked layer-1 accumulator is 2*n1 = 256 TMEM columns, layer 2's 128, layer 3's 64:
-//     448 of 512 columns with ONE buffer each, so tiles overlap only across layers: MMA-1(b+1)
-//     waits until MMA-2(b) has read A2(b) out of the D1 columns, MMA-2(b+1) until MMA-3(b) has
-//     read A3(b), MMA-3(b+1) until E3(b) has drained D3;
-//   * E1 / E2 convert their 64 channels per thread in two rounds (register budget);
+// scaled hi/lo halves, in-place TMEM operands, one issuer warp per layer, prepacked operand
+// image, device-side domain check) -- read that file first.  What differs:
+//   * ONE accumulator per layer-1 / layer-2 tile instead of the stacked pair: with twice the
+//     channels the stacked D1 would take 2 x 256 of the 512 TMEM columns.  The low halves are
+//     kept UNSCALED (lo = fp16(x*s - hi), no factor 2048), so that the three products
+//     A_hi.W_hi + A_hi.W_lo + A_lo.W_hi accumulate into the same FP32 columns: three N = n MMAs
+//     per K-step cost the tensor pipe what the stacked pair (2n + n) did.  Values are scaled to
+//     ~2^14, so a low half only becomes an FP16 subnormal below 2^-25 of the operand range --
+//     the absolute error stays under 2^-38 of it.  D1 2 x 128 + D2 2 x 64 + D3 2 x 64 columns:
+//     everything double-buffered as in the 64/32 kernel;
+//   * A2 / A3 are written in place chunk by chunk: the 16 columns of a 16-channel chunk become
+//     8 columns of hi pairs + 8 columns of lo pairs, so no column another thread still needs is
+//     ever touched and E1 / E2 can work in two rounds (register budget);
+//   * E1 / E2 read half as many TMEM columns per channel (no correction accumulator);
+//   * layer 3 (tap GEMM, N = 32) keeps the stacked pair: there it is the cheaper form;
 //   * the fallback behind the device-side gate is the FP32 SIMT fused kernel (fused_forward.cuh).
 #pragma once
 #include <cuda_fp16.h>
@@ -50,12 +58,10 @@ struct Cfg {
   static constexpr int oQs = oB2 + N2 * 4;           // 2 staged Q rows [M][QP] floats
   static constexpr int TOTAL = oQs + 2 * M * QP * 4;
   static constexpr size_t SMEM_BYTES = (size_t)TOTAL;
-  // tensor memory columns, ONE buffer each:
-  //   D1: [0,128) hi.w_hi, [128,256) corrections -> A2: hi pairs of channels 16g..16g+15 at
-  //       a2col(g) = 64*(g/4) + 8*(g%4), lo pairs at 128 + a2col(g) (columns the same E1 warp
-  //       has already read)
-  //   D2: [0,64), [64,128)   ->  A3: hi pairs at 8g, lo pairs at 64 + 8g
-  //   D3: [0,32), [32,64) (25 taps of 32 used)
+  // tensor memory columns (+ size * (b & 1)):
+  //   D1[2]: 128 columns  ->  A2: chunk g (channels 16g..16g+15): hi pairs at 16g, lo at 16g+8
+  //   D2[2]: 64 columns   ->  A3: the same
+  //   D3[2]: [0,32) hi.w_hi, [32,64) corrections (25 taps of 32 used)
   static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr int BAR_E3 = 1;
@@ -115,17 +121,17 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, u
       "r"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-// xs = hi + lo / 2048 (raw half bits)
+// xs = hi + lo (raw half bits)
 __device__ __forceinline__ void split_h(float xs, unsigned short& hi, unsigned short& lo) {
   const __half h = __float2half_rn(xs);
   hi = __half_as_ushort(h);
-  lo = __half_as_ushort(__float2half_rn((xs - __half2float(h)) * 2048.f));
+  lo = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
 }
 // two values -> packed pairs (element 0 in the low half: K index order)
 __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -279,8 +285,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
   float* sB1 = reinterpret_cast<float*>(smem_raw + C::oB1);
   float* sB2 = reinterpret_cast<float*>(smem_raw + C::oB2);
   float* sQs = reinterpret_cast<float*>(smem_raw + C::oQs);
-  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1, a2_full, bar2, a3_full, bar3,
-      d3_free;
+  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2],
+      a3_full[2], bar3[2], d3_free[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -307,12 +313,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
       mbar_init(&p_full[i], C::IM_THREADS);
       mbar_init(&p_free[i], 1);
     }
-    mbar_init(&bar1, 1);
-    mbar_init(&a2_full, C::N_E1 * 32);
-    mbar_init(&bar2, 1);
-    mbar_init(&a3_full, 128);
-    mbar_init(&bar3, 1);
-    mbar_init(&d3_free, 128);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&bar1[i], 1);
+      mbar_init(&a2_full[i], C::N_E1 * 32);
+      mbar_init(&bar2[i], 1);
+      mbar_init(&a3_full[i], 128);
+      mbar_init(&bar3[i], 1);
+      mbar_init(&d3_free[i], 128);
+    }
   }
   fence_proxy_async();
   tcgen05_fence_before();
@@ -419,9 +427,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     }
   } else if (warp == C::W_I1) {
     // ============================ I1: layer-1 MMA issuer ===================================
-    const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::N1);   // A_hi x [W_hi; W_lo]
-    const uint32_t idesc_lo = make_idesc_f16(C::M, C::N1);       // A_lo x W_hi
-    const uint64_t wdesc = make_desc_kmajor(sW1, 0, 128, 128 * (C::K1 / 8));
+    const uint32_t idesc = make_idesc_f16(C::M, C::N1);
+    const uint64_t wd_hi = make_desc_kmajor(sW1, 0, 128, 128 * (C::K1 / 8));
+    const uint64_t wd_lo = wd_hi + ((C::N1 * C::K1 * 2) >> 4);   // rows N1.. of the image
     const uint32_t aOh = smem_u32(smem_raw + C::oOh), aOl = smem_u32(smem_raw + C::oOl);
     const uint32_t aHh = smem_u32(smem_raw + C::oHh), aHl = smem_u32(smem_raw + C::oHl);
     auto adesc = [](uint32_t addr, uint32_t lbo) -> uint64_t {
@@ -430,10 +438,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     };
     for (int t = 0; t < n_tiles; t++) {
       mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1));
-      // D1 still holds A2(t-1) until MMA-2(t-1) has read it
-      if (t >= 1) mbar_wait(&bar2, (uint32_t)((t - 1) & 1));
+      // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
+      if (t >= 2) mbar_wait(&bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
       tcgen05_fence_after();
-      const uint32_t d1 = tmem + C::cD1;
+      const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
       const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
       const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * C::PB;
       PL_EV(t, 0)
@@ -447,10 +455,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
             lbo_h = (aHh + sh) - ah; lbo_l = (aHl + sh) - al;
           }
           else { ah = aHh + sh + 128; al = aHl + sh + 128; lbo_h = lbo_l = 16; }
-          mma_f16_ss(d1, adesc(ah, lbo_h), wdesc + 16 * s, idesc_hi, s > 0);
-          mma_f16_ss(d1 + C::N1, adesc(al, lbo_l), wdesc + 16 * s, idesc_lo, 1);
+          mma_f16_ss(d1, adesc(ah, lbo_h), wd_hi + 16 * s, idesc, s > 0);
+          mma_f16_ss(d1, adesc(ah, lbo_h), wd_lo + 16 * s, idesc, 1);
+          mma_f16_ss(d1, adesc(al, lbo_l), wd_hi + 16 * s, idesc, 1);
         }
-        mma_commit(&bar1);
+        mma_commit(&bar1[t & 1]);
         mma_commit(&p_free[t & 3]);
       }
       __syncwarp();
@@ -458,25 +467,25 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     }
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
-    const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::N2);
-    const uint32_t idesc_lo = make_idesc_f16(C::M, C::N2);
-    const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
+    const uint32_t idesc = make_idesc_f16(C::M, C::N2);
+    const uint64_t wd_hi = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
+    const uint64_t wd_lo = wd_hi + ((C::N2 * C::K2 * 2) >> 4);
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a2_full, (uint32_t)(t & 1));
-      // D2 still holds A3(t-1) until MMA-3(t-1) has read it
-      if (t >= 1) mbar_wait(&bar3, (uint32_t)((t - 1) & 1));
+      mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1));
+      // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
+      if (t >= 2) mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
       tcgen05_fence_after();
-      const uint32_t a2 = tmem + C::cD1;
-      const uint32_t d2 = tmem + C::cD2;
+      const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
+      const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
       PL_EV(t, 4)
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K2 / 16; ks++) {
-          const uint32_t col = 64u * (ks >> 2) + 8u * (ks & 3);   // a2col(ks)
-          mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_f16_ts(d2 + C::N2, a2 + C::N1 + col, wdesc + 16 * ks, idesc_lo, 1);
+          mma_f16_ts(d2, a2 + 16 * ks, wd_hi + 16 * ks, idesc, ks > 0);
+          mma_f16_ts(d2, a2 + 16 * ks, wd_lo + 16 * ks, idesc, 1);
+          mma_f16_ts(d2, a2 + 16 * ks + 8, wd_hi + 16 * ks, idesc, 1);
         }
-        mma_commit(&bar2);
+        mma_commit(&bar2[t & 1]);
       }
       __syncwarp();
       PL_EV(t, 5)
@@ -487,19 +496,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::NT3);
     const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::K3 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a3_full, (uint32_t)(t & 1));
-      if (t >= 1) mbar_wait(&d3_free, (uint32_t)((t - 1) & 1));
+      mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1));
+      if (t >= 2) mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
       tcgen05_fence_after();
-      const uint32_t a3 = tmem + C::cD2;
-      const uint32_t d3 = tmem + C::cD3;
+      const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
       PL_EV(t, 8)
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K3 / 16; ks++) {
-          mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_f16_ts(d3 + C::NT3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          mma_f16_ts(d3, a3 + 16 * ks, wdesc + 16 * ks, idesc_hi, ks > 0);
+          mma_f16_ts(d3 + C::NT3, a3 + 16 * ks + 8, wdesc + 16 * ks, idesc_lo, 1);
         }
-        mma_commit(&bar3);
+        mma_commit(&bar3[t & 1]);
       }
       __syncwarp();
       PL_EV(t, 9)
@@ -507,8 +516,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
   } else if (warp < C::W_E1 + C::N_E1) {
     // ============================ E1: A2 = split(relu(out1) * s1), in place ================
     // warp w: TMEM lane quarter w&3, chunks g0 .. g0+E1_CHUNKS-1 of 16 channels.  Chunk g reads
-    // D1 columns [16g,16g+16) and [128+16g, ..), then writes its hi pairs to a2col(g) and its lo
-    // pairs to 128 + a2col(g): columns this warp has consumed
+    // D1 columns [16g,16g+16) and writes its hi pairs to [16g,16g+8), its lo pairs behind them
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int g0 = (warp >> 2) * C::E1_CHUNKS;
     float* o1 = nullptr;
@@ -520,20 +528,17 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     }
     const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar1, (uint32_t)(b & 1));                     // MMA-1(b) done
+      mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
       if (warp == 0) PL_EV(b, 2)
       tcgen05_fence_after();
-      const uint32_t d1 = tmem + lane_base + C::cD1;
+      const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
       // two rounds of two chunks: the loads of a round first (one TMEM round trip), then the
-      // conversions.  Round 1 writes into columns round 0 has read
+      // conversions
 #pragma unroll
       for (int rd = 0; rd < C::E1_CHUNKS / 2; rd++) {
-        float va[2][16], vb[2][16];
+        float va[2][16];
 #pragma unroll
-        for (int gl = 0; gl < 2; gl++) {
-          tmem_ld16_nowait(d1 + (g0 + 2 * rd + gl) * 16, va[gl]);
-          tmem_ld16_nowait(d1 + C::N1 + (g0 + 2 * rd + gl) * 16, vb[gl]);
-        }
+        for (int gl = 0; gl < 2; gl++) tmem_ld16_nowait(d1 + (g0 + 2 * rd + gl) * 16, va[gl]);
         tmem_ld_wait();
 #pragma unroll
         for (int gl = 0; gl < 2; gl++) {
@@ -541,13 +546,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
           uint32_t hi[8], lo[8];
           float act[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++)
-            act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c1s, sB1[g * 16 + j]), 0.f);
+          for (int j = 0; j < 16; j++) act[j] = fmaxf(fmaf(va[gl][j], sc.c1s, sB1[g * 16 + j]), 0.f);
 #pragma unroll
           for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-          const uint32_t col = 64u * (uint32_t)(g >> 2) + 8u * (uint32_t)(g & 3);   // a2col(g)
-          tmem_st8u(d1 + col, hi);
-          tmem_st8u(d1 + C::N1 + col, lo);
+          tmem_st8u(d1 + g * 16, hi);
+          tmem_st8u(d1 + g * 16 + 8, lo);
           if (BATCH && o1) {
             float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
 #pragma unroll
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&a2_full);
+      mbar_arrive(&a2_full[b & 1]);
       if (warp == 0) PL_EV(b, 3)
     }
   } else if (warp < C::W_E3) {
@@ -574,20 +577,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     }
     const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar2, (uint32_t)(b & 1));                     // MMA-2(b) done
+      mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
       if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
-      const uint32_t d2 = tmem + lane_base + C::cD2;
-      // two rounds of two chunks, as in E1; hi pairs of chunk g land on [8g, 8g+8): columns of
-      // chunks <= g/2, read in this round or an earlier one
+      const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
+      // two rounds of two chunks, as in E1
 #pragma unroll
       for (int rd = 0; rd < C::N2 / 32; rd++) {
-        float va[2][16], vb[2][16];
+        float va[2][16];
 #pragma unroll
-        for (int gl = 0; gl < 2; gl++) {
-          tmem_ld16_nowait(d2 + (2 * rd + gl) * 16, va[gl]);
-          tmem_ld16_nowait(d2 + C::N2 + (2 * rd + gl) * 16, vb[gl]);
-        }
+        for (int gl = 0; gl < 2; gl++) tmem_ld16_nowait(d2 + (2 * rd + gl) * 16, va[gl]);
         tmem_ld_wait();
 #pragma unroll
         for (int gl = 0; gl < 2; gl++) {
@@ -595,12 +594,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
           uint32_t hi[8], lo[8];
           float act[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++)
-            act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c2s, sB2[g * 16 + j]), 0.f);
+          for (int j = 0; j < 16; j++) act[j] = fmaxf(fmaf(va[gl][j], sc.c2s, sB2[g * 16 + j]), 0.f);
 #pragma unroll
           for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-          tmem_st8u(d2 + g * 8, hi);
-          tmem_st8u(d2 + C::N2 + g * 8, lo);
+          tmem_st8u(d2 + g * 16, hi);
+          tmem_st8u(d2 + g * 16 + 8, lo);
           if (BATCH && o2) {
             float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16);
 #pragma unroll
@@ -612,7 +610,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive(&a3_full);
+      mbar_arrive(&a3_full[b & 1]);
       if (warp == C::W_E2) PL_EV(b, 7)
     }
   } else if (warp < C::W_IM) {
@@ -631,10 +629,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
     }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar3, (uint32_t)(b & 1));                     // MMA-3(b) done
+      mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-3(b) done
       if (warp == C::W_E3) PL_EV(b, 10)
       tcgen05_fence_after();
-      const uint32_t d3 = tmem + lane_base + C::cD3;
+      const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
       float v[32], w[32];
       tmem_ld16_nowait(d3, v);
       tmem_ld16_nowait(d3 + 16, v + 16);
@@ -642,10 +640,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hpw_kernel(fused::Ar
       tmem_ld16_nowait(d3 + 48, w + 16);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&d3_free);                                   // D3 may be overwritten
+      mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
-      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]);
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j] + w[j];
       named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
       float r[C::F3];
       if (x < C::OW3) {

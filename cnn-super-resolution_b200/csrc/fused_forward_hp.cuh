@@ -3,11 +3,14 @@
 // Same structure as fused_forward_pl.cuh (plane operands, one MMA issuer per layer, in-place
 // TMEM operands, every buffer double) but every operand is split into two HALVES instead of two
 // TF32 terms:
-//     x * s = hi + lo / 2048        hi = half(x*s), lo = half((x*s - hi) * 2048)
-// with s a power of two that keeps both halves in the normal range.  x.w is evaluated as
-// hi.w_hi + (hi.w_lo + lo.w_hi) / 2048: the first product accumulates in one half of the
-// (stacked) accumulator, the two correction products -- which carry the extra factor 2048 -- in
-// the other, and the epilogue recombines them.  Accuracy is that of the 3xTF32 scheme (22
+//     x * s = hi + lo               hi = half(x*s), lo = half(x*s - hi)
+// with s a power of two that puts the operand range at ~2^14: lo only becomes an FP16 subnormal
+// for values below 2^-25 of that range, where its absolute error (2^-25) is 2^-39 of the range.
+// (An earlier version kept lo * 2048 to stay clear of subnormals; the multiply and the
+// rescaling FMA in the epilogues cost 7 % of the kernel: 0.982 -> 0.914 ms on C3.)  x.w is
+// evaluated as hi.w_hi + (hi.w_lo + lo.w_hi): the first product accumulates in one half of the
+// (stacked) accumulator, the two correction products in the other (one N = 2n MMA + one N = n
+// MMA per K-step), and the epilogue adds them.  Accuracy is that of the 3xTF32 scheme (22
 // mantissa bits per operand; probe/f16_probe.cu: 2.5e-7 max error on a 9x9x64 tile), but
 //   * kind::f16 MMAs take K = 16 per instruction: 6 + 4 + 2 K-steps per tile instead of
 //     11 + 8 + 4, i.e. 24 instructions instead of 46, ~1 050 pipe cycles instead of ~2 050;
@@ -133,17 +136,17 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, u
       "r"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-// xs = hi + lo / 2048 (raw half bits)
+// xs = hi + lo (raw half bits)
 __device__ __forceinline__ void split_h(float xs, unsigned short& hi, unsigned short& lo) {
   const __half h = __float2half_rn(xs);
   hi = __half_as_ushort(h);
-  lo = __half_as_ushort(__float2half_rn((xs - __half2float(h)) * 2048.f));
+  lo = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
 }
 // two values -> packed pairs (element 0 in the low half: K index order)
 __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         float act[16];
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[gl][j], 1.f / 2048.f, va[gl][j]), sc.c1s, sB1[g * 16 + j]), 0.f);
+          act[j] = fmaxf(fmaf(va[gl][j] + vb[gl][j], sc.c1s, sB1[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         float act[16];
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(fmaf(vb[g][j], 1.f / 2048.f, va[g][j]), sc.c2s, sB2[g * 16 + j]), 0.f);
+          act[j] = fmaxf(fmaf(va[g][j] + vb[g][j], sc.c2s, sB2[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         tmem_st8u(d2 + g * 8, hi);
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
-      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = fmaf(w[j], 1.f / 2048.f, v[j]);
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j] + w[j];
       named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
       float r[C::F3];
       if (x < C::OW3) {

@@ -512,6 +512,9 @@ def test_fused_fp16_domain_fallback(ctx, port, n1, n2):
     close(*_fused_vs_oracle(ctx, port, params, (x * 400.0 - 100.0).astype(np.float32), w, h, n1, n2))
     # inside the domain but 60x the luma range (FP16 path, large activations)
     close(*_fused_vs_oracle(ctx, port, params, (x * 120.0 - 60.0).astype(np.float32), w, h, n1, n2))
+    # tiny inputs: the low halves of the split are FP16 subnormals (absolute error 2^-25 of the
+    # scaled operand), the result is bias-dominated and must still match
+    close(*_fused_vs_oracle(ctx, port, params, (x * 1e-4).astype(np.float32), w, h, n1, n2))
     # the reference's own initialisation scale, N(0, 0.001) (example_config.json:12-29), and
     # large parameters
     for k in (1e-3 / 0.11, 30.0):

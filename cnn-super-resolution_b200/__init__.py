@@ -105,6 +105,7 @@ _SIGS = {
     "srcnn_train_chunk_buffers": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i,
                                        _u64, _u64, _u64, _u64, _u64, _u64]),
     "srcnn_train_workspace_bytes": (_sz, [C.POINTER(CNet), _i, _i, _i]),
+    "srcnn_train_materializes_d1": (_i, [_vp, C.POINTER(CNet)]),
     "srcnn_update_all": (_i, [_vp, C.POINTER(CNet), _u, _f, _f, C.POINTER(_f)]),
     "srcnn_validate_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
 }
@@ -376,6 +377,10 @@ class Net:
 
     def train_workspace_bytes(self, w, h, S):
         return self.ctx.L.srcnn_train_workspace_bytes(C.byref(self.c), w, h, S)
+
+    def train_materializes_d1(self):
+        """False when the chunk entries keep the layer-1 deltas inside the gradient kernel."""
+        return bool(self.ctx.L.srcnn_train_materializes_d1(self.ctx.h, C.byref(self.c)))
 
     def train_chunk(self, inp, gt, w, h, S, work):
         _check(self.ctx.L.srcnn_train_chunk(self.ctx.h, C.byref(self.c), inp, gt, w, h, S, work))

@@ -81,6 +81,7 @@ struct srcnn_ctx {
   int fused_impl = 4;
   bool deltas_tc = true;              // f=1 deltas on the tensor cores (deltas_tc.cuh)
   bool wgrad_tc = true;               // layer-1 weight gradient on the tensor cores (wgrad_tc.cuh)
+  bool d1_fused = true;               // layer-1 deltas inside the layer-1 gradient kernel
   void* hp_scales = nullptr;          // ring of fused_hp::Scales blocks + their work words
   unsigned long long hp_next = 0;
   // cache of the prepared operand image: valid while the six parameter buffers are the same

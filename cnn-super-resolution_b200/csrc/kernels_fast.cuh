@@ -15,6 +15,7 @@
 #include "train_kernels.cuh"
 #include "deltas_tc.cuh"
 #include "wgrad_tc.cuh"
+#include "wgrad1_fused_tc.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +78,9 @@ inline int configure(srcnn_ctx* ctx) {
   ctx->deltas_tc = !(d1 && std::strcmp(d1, "simt") == 0);
   const char* gw = std::getenv("SRCNN_GW_IMPL");   // "simt": FP32 kernel for the layer-1 gradient
   ctx->wgrad_tc = !(gw && std::strcmp(gw, "simt") == 0);
+  // "separate" (or "simt"): the layer-1 deltas are materialised by their own launch; default:
+  // they only exist inside the layer-1 gradient kernel (wgrad1_fused_tc.cuh)
+  ctx->d1_fused = ctx->deltas_tc && ctx->wgrad_tc && !(d1 && std::strcmp(d1, "separate") == 0);
   return SRCNN_OK;
 }
 
@@ -117,6 +121,26 @@ inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float*
     }
   }
   return train::gradw(ctx, d, in, gw, gb, n, k, f, ow, oh, S);
+}
+
+// layer-1 deltas + layer-1 gradients in one launch (+ the fixed-order reduce of the per-CTA
+// partials).  returns 1 when it launched, 0 when not handled, <0 on error
+inline bool backward1_fused_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2) {
+  return ctx->d1_fused && f1 == wgf::Cfg::F && f2 == 1 && n1 == wgf::Cfg::N && n2 == wgf::Cfg::K2;
+}
+inline int backward1_fused(srcnn_ctx* ctx, const float* d2, const float* out1, const float* W2,
+                           const float* in, float* gw, float* gb, int n1, int n2, int f1, int f2,
+                           int ow, int oh, int S) {
+  if (!backward1_fused_supported(ctx, n1, n2, f1, f2)) return 0;
+  if (!aligned16(d2) || !aligned16(out1)) return 0;
+  int count = 0;
+  const int rc = wgf::wgrad1_fused_tc(ctx, d2, out1, W2, in, n1, n2, f1, f2, ow, oh, S, &count);
+  if (rc != 1) return rc;
+  const int Mw = f1 * f1, total = (Mw + 1) * n1;
+  train::partial_reduce_kernel<<<(total + train::RED_OUT - 1) / train::RED_OUT,
+                                 train::RED_OUT * train::RED_WARPS, 0, ctx->stream>>>(
+      (const float*)ctx->splitk_scratch, gw, gb, Mw, n1, count);
+  return 1;
 }
 
 inline bool fused_supported(int n1, int n2, int f1, int f2, int f3) {

@@ -781,6 +781,28 @@ int backward3_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem gt, co
   return rc ? check_launch("bwd3_fused") : SRCNN_OK;
 }
 
+// layer-1 deltas + layer-1 gradients in one launch: d1 is never materialised
+// (replaces `deltas` + `backpropagate` of ConfigBasedDataPipeline.cpp:265-270, 300-320)
+int backward1_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, const Work& wk,
+                          int w, int h, int S, int* launched) {
+  const Dims d = net_dims(net, w, h);
+  const float *pin, *o1, *pd2, *w2;
+  float *gw, *gb;
+  SRCNN_TRY(resolve(ctx, in, sizeof(float) * (size_t)S * w * h, &pin, "input luma"));
+  SRCNN_TRY(resolve(ctx, wk.out1, sizeof(float) * (size_t)S * d.w1 * d.h1 * net->n1, &o1, "out1"));
+  SRCNN_TRY(resolve(ctx, wk.d2, sizeof(float) * (size_t)S * d.w2 * d.h2 * net->n2, &pd2, "d2"));
+  SRCNN_TRY(resolve(ctx, net->w[1], sizeof(float) * (size_t)net->n1 * net->n2, &w2, "w2"));
+  SRCNN_TRY(resolve(ctx, net->grad_w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &gw, "grad_w1"));
+  SRCNN_TRY(resolve(ctx, net->grad_b[0], sizeof(float) * (size_t)net->n1, &gb, "grad_b1"));
+  LaunchScope scope(ctx, SRCNN_K_TRAIN_FUSED, 2);
+  const int rc = fast::backward1_fused(ctx, pd2, o1, w2, pin, gw, gb, net->n1, net->n2, net->f1,
+                                       net->f2, d.w1, d.h1, S);
+  if (rc < 0) return rc;
+  *launched = rc;
+  if (!rc) scope.n_launches = 0;
+  return rc ? check_launch("backward1_fused") : SRCNN_OK;
+}
+
 // forward of a training chunk through the fused tensor-core kernel, activations kept
 // (replaces the three execute_layer calls of ConfigBasedDataPipeline.cpp:200-241)
 int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, const Work& wk,
@@ -830,14 +852,22 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
     if (rc == SRCNN_OK) rc = srcnn_last_layer_delta(ctx, gt, wk.out3, wk.d3, w, h, d.w3, d.h3, S);
     if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d3, wk.out2, wk.d2, net->w[2], net->n2, net->f3, 1, d.w2, d.h2, S);
   }
-  if (rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d2, wk.out1, wk.d1, net->w[1], net->n1, net->f2, net->n2, d.w1, d.h1, S);
+  // layer-1 deltas and gradients in one launch where instantiated: d1 is then NOT written
+  int fused_b1 = 0;
+  if (rc == SRCNN_OK) rc = backward1_fused_entry(ctx, net, in, wk, w, h, S, &fused_b1);
+  if (!fused_b1 && rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d2, wk.out1, wk.d1, net->w[1], net->n1, net->f2, net->n2, d.w1, d.h1, S);
   // gradients (ConfigBasedDataPipeline.cpp:287-320)
   if (!fused_b3 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d2, wk.out1, net->grad_w[1], net->grad_b[1], net->n2, net->n1, net->f2, d.w2, d.h2, S);
-  if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
+  if (!fused_b1 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
   return rc;
 }
 }  // namespace
+
+int srcnn_train_materializes_d1(srcnn_ctx* ctx, const srcnn_net* net) {
+  if (!ctx || !net) return 1;
+  return fast::backward1_fused_supported(ctx, net->n1, net->n2, net->f1, net->f2) ? 0 : 1;
+}
 
 int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
                       int h, int S, srcnn_mem work) {

@@ -216,6 +216,13 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
 int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                       int w, int h, int S, srcnn_mem work);
 size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S);
+/* The layer-1 deltas are an intermediate of the layer-1 gradients only
+ * (ConfigBasedDataPipeline.cpp:265-270 -> 300-320).  For f2 = 1, n1 = 64, n2 = 32 networks the
+ * training-chunk entries compute them inside the layer-1 gradient kernel and leave the d1
+ * buffer untouched; returns 1 when the chunk entries write d1 for this network on this
+ * context, 0 when they do not (SRCNN_D1_IMPL=separate in the environment restores the
+ * separate launch; srcnn_deltas itself always materialises its target). */
+int srcnn_train_materializes_d1(srcnn_ctx* ctx, const srcnn_net* net);
 
 /* Same chunk, with the six activation / delta buffers owned by the caller -- the buffers
  * ConfigBasedDataPipeline allocates itself (_out_1.._out_3, _delta_1.._delta_3,

@@ -365,11 +365,42 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
                                    np.ascontiguousarray(got["out2"]),
                                    np.ascontiguousarray(got["out3"]))
     for name, exp in (("d1", d1), ("d2", d2), ("d3", d3)):
+        if name == "d1" and not net.train_materializes_d1():
+            continue   # lives inside the layer-1 gradient kernel: checked through gw1 / gb1 below
         np.testing.assert_allclose(got[name], exp, rtol=RTOL, atol=ATOL, err_msg=name)
     g = net.grads()
     for l in range(3):
         np.testing.assert_allclose(g["w%d" % (l + 1)], on.gw[l], rtol=RTOL, atol=1e-4, err_msg="gw%d" % l)
         np.testing.assert_allclose(g["b%d" % (l + 1)], on.gb[l], rtol=RTOL, atol=1e-4, err_msg="gb%d" % l)
+
+
+def test_layer1_deltas_fused_and_separate_agree(ctx, port):
+    """The layer-1 deltas normally live inside the layer-1 gradient kernel; with
+    SRCNN_D1_IMPL=separate they are materialised by their own launch.  Same gradients either
+    way, several tiles per CTA with a ragged last tile, and d1 against the oracle where it is
+    written."""
+    n1, n2, f1, f2, f3, w, h, S = 64, 32, 9, 1, 5, 33, 33, 301
+    rng = np.random.default_rng(301)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x, gt = patches(rng, S, w, h)
+    os.environ["SRCNN_D1_IMPL"] = "separate"
+    try:
+        ctx2 = pkg.Context(0)
+    finally:
+        del os.environ["SRCNN_D1_IMPL"]
+    grads = []
+    for c in (ctx, ctx2):
+        net = pkg.Net(c, n1, n2, f1, f2, f3, params)
+        assert net.train_materializes_d1() == (c is ctx2)
+        work = c.alloc(net.train_workspace_bytes(w, h, S))
+        net.train_chunk(c.upload(x), c.upload(gt), w, h, S, work)
+        grads.append(net.grads())
+        c.release(work)
+    for k in grads[0]:
+        scale = float(np.abs(grads[1][k]).max())
+        assert scale > 0
+        assert float(np.abs(grads[0][k] - grads[1][k]).max()) <= 2e-5 * scale, k
+    ctx2.close()
 
 
 def test_train_chunks_from_host_buffers(ctx, port):

@@ -71,6 +71,13 @@ struct Cfg {
   static constexpr int oQs = oB2 + N2 * 4;           // 2 staged Q rows [M][QP] floats
   static constexpr int TOTAL = oQs + 2 * M * QP * 4;
   static constexpr size_t SMEM_BYTES = (size_t)TOTAL;
+  // training forward (out1 / out2 kept): each E1 / E2 warp stages its 32 pixels x 32 channels
+  // of a tile in shared memory and writes them out as full 128-byte lines
+  static constexpr int SP = 36;                        // floats per staged pixel (128 B + pad)
+  static constexpr int oS1 = TOTAL;                    // E1: N_E1 warps x 32 px x SP
+  static constexpr int oS2 = oS1 + N_E1 * 32 * SP * 4; // E2: 4 warps
+  static constexpr size_t SMEM_BYTES_KEEP = (size_t)(oS2 + 4 * 32 * SP * 4);
+  static_assert(E1_CHUNKS == 2 && N2 == 32, "staging assumes 32 channels per warp");
   // tensor memory columns (+ size * (b & 1)):
   //   D1: [0,64) hi.w_hi, [64,128) corrections  ->  A2: hi pairs of channels 16g..16g+15 at
   //       a2col(g) = 32*(g/2) + 8*(g%2), lo pairs at 64 + a2col(g): inside the columns the SAME
@@ -544,14 +551,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     // pairs to 64 + a2col(g): columns this warp has consumed
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int g0 = (warp >> 2) * C::E1_CHUNKS;
-    float* o1 = nullptr;
-    if (BATCH && bx.out1) {
+    // out1 (training): pixel index of this lane's pixel in tile 0, -1 = not an out1 pixel
+    int pix1 = -1;
+    const bool keep1 = BATCH && bx.out1 != nullptr;
+    if (keep1) {
       const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
       const int w1 = bx.pw - (C::F1 - 1), h1 = bx.ph - (C::F1 - 1);
-      if (m < C::OW3 && vx < a.w && px < w1)
-        o1 = bx.out1 + (((size_t)smp * h1 + R0) * w1 + px) * C::N1;
+      if (m < C::OW3 && vx < a.w && px < w1) pix1 = (smp * h1 + R0) * w1 + px;
     }
-    const size_t o1_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N1;
+    const int w1_row = bx.pw - (C::F1 - 1);
+    float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + warp * (32 * C::SP);
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
       if (warp == 0) PL_EV(b, 2)
@@ -578,8 +587,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
         tmem_st8u(d1 + col, hi);
         tmem_st8u(d1 + C::N1 + col, lo);
-        if (BATCH && o1) {
-          float4* q = reinterpret_cast<float4*>(o1 + (size_t)b * o1_row + g * 16);
+        if (keep1) {
+          float4* q = reinterpret_cast<float4*>(st1 + lane * C::SP + gl * 16);
 #pragma unroll
           for (int j = 0; j < 4; j++)
             q[j] = make_float4(act[4 * j] * sc.inv_s1, act[4 * j + 1] * sc.inv_s1,
@@ -589,19 +598,35 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a2_full[b & 1]);
+      if (keep1) {
+        // 8 lanes per pixel: every store instruction writes four full 128-byte lines (one
+        // 64-byte run per thread touched 32 lines per instruction and bound the whole kernel)
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+          const int pp = it * 4 + (lane >> 3), ck = lane & 7;
+          const int pidx = __shfl_sync(0xffffffffu, pix1, pp);
+          const float4 v = *reinterpret_cast<const float4*>(st1 + pp * C::SP + ck * 4);
+          if (pidx >= 0)
+            *reinterpret_cast<float4*>(bx.out1 + ((size_t)pidx + (size_t)b * w1_row) * C::N1 +
+                                       g0 * 16 + ck * 4) = v;
+        }
+        __syncwarp();
+      }
       if (warp == 0) PL_EV(b, 3)
     }
   } else if (warp < C::W_E3) {
     // ============================ E2: A3 = split(relu(out2) * s2), in place ================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    float* o2 = nullptr;
-    if (BATCH && bx.out2) {
+    int pix2 = -1;
+    const bool keep2 = BATCH && bx.out2 != nullptr;
+    if (keep2) {
       const int m = (warp & 3) * 32 + lane, vx = X0 + m, smp = vx / bx.pw, px = vx - smp * bx.pw;
       const int w2 = bx.pw - (C::F1 - 1), h2 = bx.ph - (C::F1 - 1);
-      if (m < C::OW3 && vx < a.w && px < w2)
-        o2 = bx.out2 + (((size_t)smp * h2 + R0) * w2 + px) * C::N2;
+      if (m < C::OW3 && vx < a.w && px < w2) pix2 = (smp * h2 + R0) * w2 + px;
     }
-    const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
+    const int w2_row = bx.pw - (C::F1 - 1);
+    float* st2 = reinterpret_cast<float*>(smem_raw + C::oS2) + (warp - C::W_E2) * (32 * C::SP);
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
       if (warp == C::W_E2) PL_EV(b, 6)
@@ -626,8 +651,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         tmem_st8u(d2 + g * 8, hi);
         tmem_st8u(d2 + C::N2 + g * 8, lo);
-        if (BATCH && o2) {
-          float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16);
+        if (keep2) {
+          float4* q = reinterpret_cast<float4*>(st2 + lane * C::SP + g * 16);
 #pragma unroll
           for (int j = 0; j < 4; j++)
             q[j] = make_float4(act[4 * j] * sc.inv_s2, act[4 * j + 1] * sc.inv_s2,
@@ -637,6 +662,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(&a3_full[b & 1]);
+      if (keep2) {
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+          const int pp = it * 4 + (lane >> 3), ck = lane & 7;
+          const int pidx = __shfl_sync(0xffffffffu, pix2, pp);
+          const float4 v = *reinterpret_cast<const float4*>(st2 + pp * C::SP + ck * 4);
+          if (pidx >= 0)
+            *reinterpret_cast<float4*>(bx.out2 + ((size_t)pidx + (size_t)b * w2_row) * C::N2 +
+                                       ck * 4) = v;
+        }
+        __syncwarp();
+      }
       if (warp == C::W_E2) PL_EV(b, 7)
     }
   } else if (warp < C::W_IM) {
@@ -720,7 +758,7 @@ inline int configure() {
                                   (int)Cfg::SMEM_BYTES));
   SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)Cfg::SMEM_BYTES));
+                                  (int)Cfg::SMEM_BYTES_KEEP));
   return SRCNN_OK;
 }
 
@@ -779,7 +817,8 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
     bx.pw = a.w;
     bx.ph = a.h;
     forward_fused_hp_kernel<true>
-        <<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx, sc, fallback);
+        <<<grid, Cfg::NT, (out1 || out2) ? Cfg::SMEM_BYTES_KEEP : Cfg::SMEM_BYTES, ctx->stream>>>(
+            v, rpc, bx, sc, fallback);
     fused_pl::forward_fused_pl_kernel<true>
         <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx);
   } else {

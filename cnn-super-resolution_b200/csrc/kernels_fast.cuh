@@ -233,6 +233,7 @@ inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, i
                                const float* w3, const float* b3, int in_w, int in_h, int S) {
   if (ctx->fused_impl < 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
   if ((long long)S * in_w >= (1LL << 30)) return 0;
+  if ((long long)S * in_w * in_h >= (1LL << 31)) return 0;   // 32-bit pixel indices of out1 / out2
   fused::Args a{in, out3, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
   const int rc = ctx->fused_impl == 4 ? fused_hp::launch(ctx, a, S, true, out1, out2)

@@ -817,17 +817,27 @@ inline int bwd3_fused(srcnn_ctx* ctx, const float* gt, const float* out3, const 
   const int pw = w3 + 2 * (f - 1), ph = h3 + 2 * (f - 1);
   const size_t smem = sizeof(float) * (((size_t)pw * ph + 3) / 4 * 4 + (size_t)B3_WARPS * f * f * k);
   if (smem > 96 * 1024) return 0;   // image-sized samples: the per-kernel path handles them
-  const int count = (int)std::min<long long>(S, 4LL * ctx->sm_count);
+  // one wave of resident CTAs, each walking S / count samples: with more CTAs than fit, the
+  // leftover ones run as a second wave at a fraction of the occupancy
+  int occ = 0;
+  if (k <= 32) {
+    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bwd3_fused_kernel<1>, B3_NT, smem));
+  } else {
+    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bwd3_fused_kernel<2>, B3_NT, smem));
+  }
+  if (occ < 1) occ = 1;
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  const int count = (int)std::min<long long>(S, (long long)occ * sms);
   const int Mw = f * f * k;
   SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
                            sizeof(float) * (size_t)count * (Mw + 1)));
   float* part = (float*)ctx->splitk_scratch;
   if (k <= 32) {
-    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd3_fused_kernel<1><<<count, B3_NT, smem, ctx->stream>>>(gt, out3, out2, W3, d3, d2, part, k,
                                                              gt_w, gt_h, w3, h3, S);
   } else {
-    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd3_fused_kernel<2><<<count, B3_NT, smem, ctx->stream>>>(gt, out3, out2, W3, d3, d2, part, k,
                                                              gt_w, gt_h, w3, h3, S);
   }

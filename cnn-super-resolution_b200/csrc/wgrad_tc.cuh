@@ -247,7 +247,8 @@ struct Cfg2 {
   static constexpr int SBO = 128 * (PX / 4);
   static constexpr int A_FLOATS = 2 * K * PX, B_FLOATS = 2 * N * PX;
   static constexpr int STAGE = A_FLOATS + B_FLOATS;
-  static constexpr int oX = 2 * STAGE;                       // epilogue exchange [K][N]
+  static constexpr int NS = 4;                               // stages (two tiles per producer step)
+  static constexpr int oX = NS * STAGE;                      // epilogue exchange [K][N]
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(oX + K * N);
   static constexpr uint32_t TMEM_COLS = 64;
 };
@@ -264,13 +265,13 @@ __global__ void __launch_bounds__(Cfg2::NT, 1) wgrad2_tc_kernel(const float* __r
   using fused_ws::mbar_arrive;
   extern __shared__ __align__(128) float wg_smem[];
   float* sX = wg_smem + C::oX;
-  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ __align__(8) uint64_t full[C::NS], empty[C::NS], done;
   __shared__ float gb_part[4][C::N];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
   if (tid == 0) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < C::NS; i++) {
       mbar_init(&full[i], C::N_PA * 32 + 128);
       mbar_init(&empty[i], 1);
     }
@@ -286,78 +287,101 @@ __global__ void __launch_bounds__(Cfg2::NT, 1) wgrad2_tc_kernel(const float* __r
   if (warp < C::W_PB) {
     // ============================ PA: layer input, transposed ==============================
     const int c = (warp & 1) * 32 + lane;          // input channel (row of A)
-    for (int i = 0; i < my_tiles; i++) {
-      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
-      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
-      float* sA = wg_smem + (i & 1) * C::STAGE;
-      float v[4][4];
+    // two tiles per step: the loads of both are in flight together (with one, the producers
+    // waited on HBM latency every tile and the kernel sat at 58 % of the HBM peak)
+    for (int i = 0; i < my_tiles; i += 2) {
+      float v[2][4][4];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int h = 0; h < 2; h++) {
+        const long long p0 = ((long long)blockIdx.x + (long long)(i + h) * gridDim.x) * C::PX;
+        const bool on = i + h < my_tiles;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const long long p = p0 + 4 * ((warp >> 1) + 4 * u) + j;
-          v[u][j] = p < P ? __ldg(in + p * C::K + c) : 0.f;
-        }
+        for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int q = (warp >> 1) + 4 * u;
-        float hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
-        *reinterpret_cast<float4*>(sA + kmajor_offset(c, 4 * q, C::PX)) =
-            make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sA + kmajor_offset(C::K + c, 4 * q, C::PX)) =
-            make_float4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 4; j++) {
+            const long long p = p0 + 4 * ((warp >> 1) + 4 * u) + j;
+            v[h][u][j] = (on && p < P) ? __ldg(in + p * C::K + c) : 0.f;
+          }
       }
-      fence_proxy_async();
-      mbar_arrive(&full[i & 1]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int t = i + h, st = t & (C::NS - 1);
+        if (t < my_tiles) {
+          if (t >= C::NS) mbar_wait(&empty[st], (uint32_t)(((t - C::NS) / C::NS) & 1));
+          float* sA = wg_smem + st * C::STAGE;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int q = (warp >> 1) + 4 * u;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) split_tf32(v[h][u][j], hi[j], lo[j]);
+            *reinterpret_cast<float4*>(sA + kmajor_offset(c, 4 * q, C::PX)) =
+                make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(sA + kmajor_offset(C::K + c, 4 * q, C::PX)) =
+                make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+          mbar_arrive(&full[st]);
+        }
+      }
     }
   } else if (warp < C::W_I) {
     // ============================ PB: deltas, transposed + bias sums =======================
     const int pw = warp - C::W_PB;                 // 0..3: pixel quads pw, pw+4, ..
     float gb = 0.f;
-    for (int i = 0; i < my_tiles; i++) {
-      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
-      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
-      float* sB = wg_smem + (i & 1) * C::STAGE + C::A_FLOATS;
-      float v[4][4];
+    for (int i = 0; i < my_tiles; i += 2) {
+      float v[2][4][4];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int h = 0; h < 2; h++) {
+        const long long p0 = ((long long)blockIdx.x + (long long)(i + h) * gridDim.x) * C::PX;
+        const bool on = i + h < my_tiles;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const long long p = p0 + 4 * (pw + 4 * u) + j;
-          v[u][j] = p < P ? __ldg(d + p * C::N + lane) : 0.f;
-        }
+        for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int q = pw + 4 * u;
-        float hi[4], lo[4];
-        gb += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
-        *reinterpret_cast<float4*>(sB + kmajor_offset(lane, 4 * q, C::PX)) =
-            make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sB + kmajor_offset(C::N + lane, 4 * q, C::PX)) =
-            make_float4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 4; j++) {
+            const long long p = p0 + 4 * (pw + 4 * u) + j;
+            v[h][u][j] = (on && p < P) ? __ldg(d + p * C::N + lane) : 0.f;
+          }
       }
-      fence_proxy_async();
-      mbar_arrive(&full[i & 1]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int t = i + h, st = t & (C::NS - 1);
+        if (t < my_tiles) {
+          if (t >= C::NS) mbar_wait(&empty[st], (uint32_t)(((t - C::NS) / C::NS) & 1));
+          float* sB = wg_smem + st * C::STAGE + C::A_FLOATS;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int q = pw + 4 * u;
+            float hi[4], lo[4];
+            gb += (v[h][u][0] + v[h][u][1]) + (v[h][u][2] + v[h][u][3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) split_tf32(v[h][u][j], hi[j], lo[j]);
+            *reinterpret_cast<float4*>(sB + kmajor_offset(lane, 4 * q, C::PX)) =
+                make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(sB + kmajor_offset(C::N + lane, 4 * q, C::PX)) =
+                make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+          mbar_arrive(&full[st]);
+        }
+      }
     }
     gb_part[pw][lane] = gb;
   } else {
     // ============================ I: MMA issuer ============================================
     const uint32_t idesc = make_idesc_tf32(128, 2 * C::N);
     for (int i = 0; i < my_tiles; i++) {
-      mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
+      const int sg = i & (C::NS - 1);
+      mbar_wait(&full[sg], (uint32_t)((i / C::NS) & 1));
       tcgen05_fence_after();
-      const float* st = wg_smem + (i & 1) * C::STAGE;
+      const float* st = wg_smem + sg * C::STAGE;
       const uint64_t ad = make_desc_kmajor(st, 0, 128, C::SBO);
       const uint64_t bd = make_desc_kmajor(st + C::A_FLOATS, 0, 128, C::SBO);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::PX / 8; ks++)
           mma_tf32(tmem, ad + 16 * ks, bd + 16 * ks, idesc, (i | ks) > 0);
-        mma_commit(&empty[i & 1]);
+        mma_commit(&empty[sg]);
         if (i == my_tiles - 1) mma_commit(&done);
       }
       __syncwarp();

@@ -670,3 +670,41 @@ def test_full_size_4096_properties(ctx, port):
     m2, o2 = ctx.upload(xs), ctx.alloc(4 * (ws_ - pad) * (hs - pad))
     net.forward_fused(m2, o2, ws_, hs, 1)
     np.testing.assert_array_equal(ctx.read(o2, (hs - pad, ws_ - pad)), full[dy:, dx:])
+
+
+def test_wide_network_1080p_properties(ctx, port):
+    """BASELINE config C5's network (9-1-5, n1=128, n2=64) on a 1920x1080 frame through the
+    wide tensor-core kernel: random 40x40 output windows equal the oracle run on their receptive
+    field; row bands through the HOST entry point (sub-bands on two streams, shared operand
+    image) are bit-identical to the single launch; so is a translated crop."""
+    n1, n2, f1, f2, f3 = 128, 64, 9, 1, 5
+    w, h = 1920, 1080
+    rng = np.random.default_rng(1080)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x = luma_image(rng, h, w)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    pad = net.padding
+    mi, mo = ctx.upload(x), ctx.alloc(4 * w3 * h3)
+    net.forward_fused(mi, mo, w, h, 1)
+    full = ctx.read(mo, (h3, w3))
+    on = NetState(n1, n2, f1, f2, f3, params)
+    spots = [(0, 0), (h3 - 40, w3 - 40), (0, w3 - 40), (h3 - 40, 0)]
+    spots += [(int(rng.integers(0, h3 - 40)), int(rng.integers(0, w3 - 40))) for _ in range(4)]
+    for (y0, x0) in spots:
+        crop = np.ascontiguousarray(x[y0:y0 + 40 + pad, x0:x0 + 40 + pad])
+        _, _, e3 = port.net_forward(on, crop, 40 + pad, 40 + pad, 1)
+        assert np.abs(full[y0:y0 + 40, x0:x0 + 40] - e3[0]).max() <= 1e-4
+    for world in (1, 3):
+        out = np.zeros((h3, w3), np.float32)
+        for (r0, r1) in pkg.row_bands(h3, world):
+            net.infer_rows_host(x, w, h, r0, r1, out[r0:r1])
+        np.testing.assert_array_equal(out, full)
+    dy, dx = 11, 29
+    xs = np.ascontiguousarray(x[dy:, dx:])
+    hs, ws_ = xs.shape
+    m2, o2 = ctx.upload(xs), ctx.alloc(4 * (ws_ - pad) * (hs - pad))
+    net.forward_fused(m2, o2, ws_, hs, 1)
+    np.testing.assert_array_equal(ctx.read(o2, (hs - pad, ws_ - pad)), full[dy:, dx:])
+    for m in (mi, mo, m2, o2):
+        ctx.release(m)

@@ -634,7 +634,9 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // SRCNN_E2E_SUBBANDS=n (2..16) overrides the default for experiments.  Measured on C3 (PCIe
   // gen5 x16, 55 GB/s each way): 4 sub-bands 2.45 ms, 6: 2.19, 8: 2.08, 10: 2.01, 12-16: 2.00.
   // A single launch that polls per-slice arrival flags (stream memory operations) was tried
-  // and is slower (2.33 ms at best): every flag write serialises the copy stream.
+  // and is slower (2.33 ms at best): every flag write serialises the copy stream.  So is
+  // storing the result straight into the pinned output buffer from the kernel (no device
+  // buffer, no D2H copies): 1.96 ms against 1.89 in the same run.
   static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 12;
   int n_sub = band_out_h >= 1024 ? std::min(std::max(kSubDefault, 2), kMaxSub) : 1;
   int sub_r0[kMaxSub + 1] = {0};

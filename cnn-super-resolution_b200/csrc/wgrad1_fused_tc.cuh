@@ -371,15 +371,23 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
     }
   } else if (warp < C::W_I2) {
     // ============================ LD: d2 tile -> TF32 hi / lo (rows = pixels) ==============
-    const int t = tid - C::W_LD * 32;   // pixel of the tile
+    // item u of a thread = (pixel px_of(u), 16-byte chunk ck_of(u)): the 8 lanes of a quarter
+    // warp take 8 consecutive pixels (conflict-free STS.128 into the K-major tile: the 16-byte
+    // slot inside a core matrix is the pixel & 7), the four quarters four consecutive chunks, so
+    // one load instruction touches 8 lines of 64 bytes (thread = pixel row: 32 lines of 16)
+    const int lw = warp - C::W_LD;
+    auto px_of = [&](int u) { return 8 * (4 * lw + (u >> 1)) + (lane & 7); };
+    auto ck_of = [&](int u) { return (lane >> 3) + 4 * (u & 1); };
     // one tile ahead in registers, for the same reason as the mask of the PB warps
     auto load_tile = [&](int i, float4 (&v)[C::K2 / 4]) {
-      const long long p = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX + t;
-      const bool ok = i < my_tiles && p < P;
+      const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
 #pragma unroll
-      for (int q = 0; q < C::K2 / 4; q++)
-        v[q] = ok ? __ldg(reinterpret_cast<const float4*>(d2 + p * C::K2) + q)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < C::K2 / 4; u++) {
+        const long long p = p0 + px_of(u);
+        v[u] = (i < my_tiles && p < P)
+                   ? __ldg(reinterpret_cast<const float4*>(d2 + p * C::K2) + ck_of(u))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     float4 v[C::K2 / 4], nv[C::K2 / 4];
     load_tile(0, v);
@@ -398,7 +406,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
         split_tf32(v[q].y, hi[1], lo[1]);
         split_tf32(v[q].z, hi[2], lo[2]);
         split_tf32(v[q].w, hi[3], lo[3]);
-        const int off = kmajor_offset(t, 4 * q, C::K2);
+        const int off = kmajor_offset(px_of(q), 4 * ck_of(q), C::K2);
         *reinterpret_cast<float4*>(sh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(sl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }

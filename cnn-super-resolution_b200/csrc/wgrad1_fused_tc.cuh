@@ -17,6 +17,14 @@
 // and the four PB warps -- one per TMEM lane quarter -- split the pixels of a tile in halves
 // without exchanging anything.
 //
+// Measured and not kept: (1) the PB warps rewriting DT in place (hi parts in lanes 0..63, lo
+// parts in the duplicate lanes 64..127) so that the gradient MMAs take their channel operand
+// from TMEM: -32 KB of STS and -32 KB of tensor-core reads per tile, but every PB thread then
+// needs the mask of all 64 pixels and the chunk went from 0.784 to 1.00 ms (a 1-bit mask written
+// by the forward kernel would remove that); (2) keeping next-tile loads in registers across a
+// tile (the compiler serialises load -> compare chains).  The im2col producers (PA) are the
+// critical path: ~3 000 cycles per tile for 400 instructions per thread in dependent chains.
+//
 //   LD (2 warps)  d2 tile -> TF32 hi / lo -> smem                               -> d2_full
 //   I2 (1 warp)   DT[i&1] = [W2;W2] x d2^T, 12 MMAs                             -> dt_full
 //   PB (2x4 warps) DT -> mask(out1) -> bias sums -> split -> B tile              -> full, dt_free

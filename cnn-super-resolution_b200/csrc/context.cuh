@@ -104,7 +104,14 @@ struct srcnn_ctx {
   size_t stage_in_bytes[2] = {0, 0}, stage_gt_bytes[2] = {0, 0};
   // side streams + events of the pipelined host-buffer inference (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr, compute2 = nullptr;
-  cudaEvent_t ev_in[16] = {}, ev_k[16] = {};
+  // the sub-band pipeline of srcnn_infer_rows_host as an instantiated CUDA graph, replayed while
+  // the call's arguments (host / device pointers, shape, band, parameters) stay the same
+  cudaGraphExec_t e2e_graph = nullptr;
+  unsigned long long e2e_key[20] = {};
+  unsigned e2e_graph_launches = 0;
+  cudaEvent_t ev_join[2] = {};
+  static constexpr int kEvents = 32;
+  cudaEvent_t ev_in[kEvents] = {}, ev_k[kEvents] = {};
   // last srcnn_net whose derived (repacked) parameters are cached; see fused kernels
   void* packed_params = nullptr;
   size_t packed_bytes = 0;

@@ -128,7 +128,10 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
-    for (int i = 0; i < 16; i++) {
+    if (ctx->e2e_graph) cudaGraphExecDestroy(ctx->e2e_graph);
+    for (int i = 0; i < 2; i++)
+      if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    for (int i = 0; i < srcnn_ctx::kEvents; i++) {
       cudaEventDestroy(ctx->ev_in[i]);
       cudaEventDestroy(ctx->ev_k[i]);
     }
@@ -630,14 +633,12 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // last sub-band are small because their upload / download is exposed.  Every sub-band is the
   // same valid-convolution problem with a halo, so the result is bit-identical to a single
   // launch.
-  constexpr int kMaxSub = 16;
-  // SRCNN_E2E_SUBBANDS=n (2..16) overrides the default for experiments.  Measured on C3 (PCIe
-  // gen5 x16, 55 GB/s each way): 4 sub-bands 2.45 ms, 6: 2.19, 8: 2.08, 10: 2.01, 12-16: 2.00.
-  // A single launch that polls per-slice arrival flags (stream memory operations) was tried
-  // and is slower (2.33 ms at best): every flag write serialises the copy stream.  So is
-  // storing the result straight into the pinned output buffer from the kernel (no device
-  // buffer, no D2H copies): 1.96 ms against 1.89 in the same run.
-  static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 12;
+  constexpr int kMaxSub = srcnn_ctx::kEvents;
+  // SRCNN_E2E_SUBBANDS=n (2..32) / SRCNN_E2E_RAMPCAP=c override the defaults for experiments.
+  // Measured on C3 (PCIe gen5 x16, 55 GB/s each way, 47.6 with both directions busy), wall
+  // clock of the call with the 0.9 ms kernel: 12 sub-bands 1.84-1.88 ms, 14: 1.78, 16: 1.73-1.78,
+  // 18: 1.78, 20 (cap 3): 1.79, 24: 1.83, 32: 1.96; ramp cap 3 / 5 / 6 at 16: 1.78 / 1.83 / 1.79.
+  static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 16;
   int n_sub = band_out_h >= 1024 ? std::min(std::max(kSubDefault, 2), kMaxSub) : 1;
   int sub_r0[kMaxSub + 1] = {0};
   {
@@ -645,7 +646,8 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     // capped at 4 units; the exposed head upload / tail download shrink with them
     float unit[kMaxSub], total = 0.f;
     for (int i = 0; i < n_sub; i++) {
-      unit[i] = (float)std::min(std::min(i + 1, n_sub - i), 4);
+      static const int kRampCap = std::getenv("SRCNN_E2E_RAMPCAP") ? std::atoi(std::getenv("SRCNN_E2E_RAMPCAP")) : 4;
+      unit[i] = (float)std::min(std::min(i + 1, n_sub - i), std::max(kRampCap, 1));
       total += unit[i];
     }
     float acc = 0.f;
@@ -684,6 +686,54 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     return SRCNN_OK;
   }
+  // The pipeline is ~10 runtime calls per sub-band; issued one by one the host only just stays
+  // ahead of the GPU (and falls behind when another thread competes for the CPU), so it is
+  // captured once into a CUDA graph and replayed with one launch while the arguments repeat
+  // (SRCNN_E2E_GRAPH=0 disables; profile mode times individual launches and never captures).
+  static const bool kGraphs = !(std::getenv("SRCNN_E2E_GRAPH") && std::atoi(std::getenv("SRCNN_E2E_GRAPH")) == 0);
+  const bool use_graph = kGraphs && !ctx->profile;
+  unsigned long long key[20] = {
+      (unsigned long long)(uintptr_t)host_in, (unsigned long long)(uintptr_t)host_out,
+      (unsigned long long)(uintptr_t)din, (unsigned long long)(uintptr_t)dout,
+      (unsigned long long)in_w, (unsigned long long)in_h, (unsigned long long)out_row0,
+      (unsigned long long)out_row1, (unsigned long long)n_sub,
+      (unsigned long long)(uintptr_t)w1, (unsigned long long)(uintptr_t)b1,
+      (unsigned long long)(uintptr_t)w2, (unsigned long long)(uintptr_t)b2,
+      (unsigned long long)(uintptr_t)w3, (unsigned long long)(uintptr_t)b3,
+      (unsigned long long)(uintptr_t)scales, (unsigned long long)ctx->fused_impl,
+      (unsigned long long)net->n1, (unsigned long long)net->n2,
+      (unsigned long long)(uintptr_t)ctx->stream};
+  if (use_graph && ctx->e2e_graph && std::memcmp(key, ctx->e2e_key, sizeof(key)) == 0) {
+    SRCNN_CUDA(cudaGraphLaunch(ctx->e2e_graph, ctx->stream));
+    ctx->launch_count += ctx->e2e_graph_launches;
+    ctx->stats[SRCNN_K_FORWARD_FUSED].launches += ctx->e2e_graph_launches;
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SRCNN_OK;
+  }
+  if (use_graph) {
+    if (ctx->e2e_graph) {
+      cudaGraphExecDestroy(ctx->e2e_graph);
+      ctx->e2e_graph = nullptr;
+    }
+    if (!ctx->ev_join[0])
+      for (int i = 0; i < 2; i++)
+        SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    {   // everything the launches allocate lazily must exist before the capture starts
+      fused_hp::Scales* s_;
+      unsigned* w_;
+      SRCNN_TRY(fused_hp::scale_slot(ctx, &s_, &w_));
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+      cudaGraph_t stale = nullptr;   // a capture an earlier failed call left open
+      cudaStreamEndCapture(ctx->stream, &stale);
+      if (stale) cudaGraphDestroy(stale);
+      cudaGetLastError();
+    }
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SRCNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  }
+  const uint64_t launches_before = ctx->launch_count;
   // order the side streams after whatever the context stream was doing with the buffers
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
@@ -718,6 +768,28 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaMemcpyAsync(host_out + (size_t)r0 * d.w3, dout + (size_t)r0 * d.w3,
                                sizeof(float) * (size_t)(r1 - r0) * d.w3, cudaMemcpyDeviceToHost,
                                ctx->copy_out));
+  }
+  if (use_graph) {
+    // join the side streams back into the capturing stream, instantiate, replay
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaEventRecord(ctx->ev_join[0], ctx->copy_out);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->ev_join[0], 0);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_join[1], ctx->compute2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->ev_join[1], 0);
+    const cudaError_t e2 = cudaStreamEndCapture(main_stream, &graph);
+    if (e == cudaSuccess) e = e2;
+    if (rc == SRCNN_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ctx->e2e_graph, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != SRCNN_OK) return rc;
+    if (e != cudaSuccess) {
+      ctx->e2e_graph = nullptr;
+      return fail(SRCNN_ECUDA, "capturing the sub-band pipeline failed: %s", cudaGetErrorString(e));
+    }
+    std::memcpy(ctx->e2e_key, key, sizeof(key));
+    ctx->e2e_graph_launches = (unsigned)(ctx->launch_count - launches_before);
+    SRCNN_CUDA(cudaGraphLaunch(ctx->e2e_graph, main_stream));
+    SRCNN_CUDA(cudaStreamSynchronize(main_stream));
+    return SRCNN_OK;
   }
   SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_out));
   SRCNN_CUDA(cudaStreamSynchronize(ctx->compute2));
@@ -916,7 +988,7 @@ int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* h
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < srcnn_ctx::kEvents; i++) {
       SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
       SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
     }

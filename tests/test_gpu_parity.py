@@ -708,3 +708,39 @@ def test_wide_network_1080p_properties(ctx, port):
     np.testing.assert_array_equal(ctx.read(o2, (hs - pad, ws_ - pad)), full[dy:, dx:])
     for m in (mi, mo, m2, o2):
         ctx.release(m)
+
+
+def test_host_row_pipeline_replay(ctx, port):
+    """srcnn_infer_rows_host replays a captured CUDA graph while its arguments repeat: the
+    replay must see new input DATA in the same host buffer, new parameter VALUES in the same
+    device buffers, and a different band must not reuse the old graph."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    w, h = 200, 1100                      # >= 1024 output rows: the multi-stream pipeline
+    rng = np.random.default_rng(1100)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    hin, hout = pkg.PinnedBuffer((h, w)), pkg.PinnedBuffer((h3, w3))
+    mi, mo = ctx.alloc(4 * w * h), ctx.alloc(4 * w3 * h3)
+
+    def single_launch(x):
+        ctx.write(mi, x)
+        net.forward_fused(mi, mo, w, h, 1)
+        return ctx.read(mo, (h3, w3))
+
+    for rep in range(3):                  # capture, then two replays with new data
+        x = luma_image(rng, h, w)
+        hin.array[:] = x
+        hout.array[:] = -1.0
+        net.infer_rows_host(hin.array, w, h, 0, h3, hout.array)
+        np.testing.assert_array_equal(hout.array, single_launch(x))
+    # new parameter values in the same buffers
+    ctx.write(net.c.w[1], (params["w2"] * 0.5).astype(np.float32))
+    net.infer_rows_host(hin.array, w, h, 0, h3, hout.array)
+    np.testing.assert_array_equal(hout.array, single_launch(x))
+    # a different band of the same image
+    out2 = np.zeros((h3 - 40, w3), np.float32)
+    net.infer_rows_host(hin.array, w, h, 40, h3, out2)
+    np.testing.assert_array_equal(out2, single_launch(x)[40:])
+    ctx.release(mi)
+    ctx.release(mo)

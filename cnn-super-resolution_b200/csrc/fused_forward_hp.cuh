@@ -740,11 +740,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
 #ifdef PL_TRACE
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles > 108) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles >= PL_TRACE_BASE + 8) {
     const long long t0 = pl_trace[0][12];
     for (int t = 0; t < 8; t++)
       printf("tile %d: IM %6lld | I1 %6lld..%6lld | E1 %6lld..%6lld | I2 %6lld..%6lld | E2 %6lld..%6lld | I3 %6lld..%6lld | E3 %6lld..%6lld\n",
-             100 + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
+             PL_TRACE_BASE + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
              pl_trace[t][3] - t0, pl_trace[t][4] - t0, pl_trace[t][5] - t0, pl_trace[t][6] - t0,
              pl_trace[t][7] - t0, pl_trace[t][8] - t0, pl_trace[t][9] - t0, pl_trace[t][10] - t0,
              pl_trace[t][11] - t0);

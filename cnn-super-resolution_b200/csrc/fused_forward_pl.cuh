@@ -99,10 +99,13 @@ __host__ __device__ __forceinline__ int tap_of(int s, int j, int e) {
 }
 
 #ifdef PL_TRACE
-// event timeline of tiles 100..103 of CTA (0,0,0): PL_EV(tile, event id)
+// event timeline of tiles PL_TRACE_BASE .. +7 of CTA (0,0,0): PL_EV(tile, event id)
+#ifndef PL_TRACE_BASE
+#define PL_TRACE_BASE 100
+#endif
 __device__ long long pl_trace[8][16];
-#define PL_EV(t, e) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) >= 100 && (t) < 108 && lane == 0) \
-    pl_trace[(t) - 100][e] = clock64();
+#define PL_EV(t, e) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) >= PL_TRACE_BASE && (t) < PL_TRACE_BASE + 8 && lane == 0) \
+    pl_trace[(t) - PL_TRACE_BASE][e] = clock64();
 #else
 #define PL_EV(t, e) {}
 #endif
@@ -607,11 +610,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
 #ifdef PL_TRACE
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles > 108) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && n_tiles >= PL_TRACE_BASE + 8) {
     const long long t0 = pl_trace[0][12];
     for (int t = 0; t < 8; t++)
       printf("tile %d: IM %6lld | I1 %6lld..%6lld | E1 %6lld..%6lld | I2 %6lld..%6lld | E2 %6lld..%6lld | I3 %6lld..%6lld | E3 %6lld..%6lld\n",
-             100 + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
+             PL_TRACE_BASE + t, pl_trace[t][12] - t0, pl_trace[t][0] - t0, pl_trace[t][1] - t0, pl_trace[t][2] - t0,
              pl_trace[t][3] - t0, pl_trace[t][4] - t0, pl_trace[t][5] - t0, pl_trace[t][6] - t0,
              pl_trace[t][7] - t0, pl_trace[t][8] - t0, pl_trace[t][9] - t0, pl_trace[t][10] - t0,
              pl_trace[t][11] - t0);

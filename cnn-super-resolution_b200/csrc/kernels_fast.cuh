@@ -172,6 +172,8 @@ inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     fused_hpw::prepare(ctx, a, ctx->hp_cache);
   else
     fused_hp::prepare_into(ctx, a, ctx->hp_cache);
+  ctx->launch_count += 1;
+  ctx->stats[SRCNN_K_FORWARD_FUSED].launches += 1;
   *out = ctx->hp_cache;
   ctx->hp_cache_valid = cacheable;
   ctx->hp_cache_gen = ctx->write_gen;
@@ -214,10 +216,13 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
 }
 
 // kernels one fused forward call launches: the FP16-split path is prepare + main + gated TF32
-inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3) {
+inline int fused_launches(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
+                          bool shared_scales = false) {
   if (ctx->fused_impl != 4) return 1;
-  if (fused_hp::supported(n1, n2, f1, f2, f3)) return 3;    // prepare + FP16 + gated TF32
-  if (fused_hpw::supported(n1, n2, f1, f2, f3)) return 3;   // prepare + FP16 + gated FP32
+  // FP16 kernel + gated fallback kernel, + the prepare kernel when the launch packs its own
+  // operand image (fused_prepare counts the ones it launches itself)
+  if (fused_hp::supported(n1, n2, f1, f2, f3) || fused_hpw::supported(n1, n2, f1, f2, f3))
+    return shared_scales ? 2 : 3;
   return 1;
 }
 

@@ -586,7 +586,7 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
     const void* scales = nullptr;
     SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2,
                                   w3, b3, params_owned(ctx, net), &scales));
-    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
+    LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
     SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin, pout, w1,
                                   b1, w2, b2, w3, b3, in_w, in_h, S, scales));
     return check_launch("forward_fused");
@@ -677,7 +677,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaMemcpyAsync(din, host_in + (size_t)out_row0 * in_w, in_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
     {
-      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
       SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, din, dout,
                                     w1, b1, w2, b2, w3, b3, in_w, band_in_h, 1, scales));
       SRCNN_TRY(check_launch("forward_fused"));
@@ -754,7 +754,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     cudaStream_t cs = (i & 1) ? ctx->compute2 : main_stream;
     SRCNN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_in[i], 0));
     {
-      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
       ctx->stream = cs;   // the launch helpers use the context stream
       rc = fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
                                din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2, b2,

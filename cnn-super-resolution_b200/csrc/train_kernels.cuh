@@ -819,14 +819,23 @@ inline int bwd3_fused(srcnn_ctx* ctx, const float* gt, const float* out3, const 
   if (smem > 96 * 1024) return 0;   // image-sized samples: the per-kernel path handles them
   // one wave of resident CTAs, each walking S / count samples: with more CTAs than fit, the
   // leftover ones run as a second wave at a fraction of the occupancy
-  int occ = 0;
-  if (k <= 32) {
-    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bwd3_fused_kernel<1>, B3_NT, smem));
-  } else {
-    SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bwd3_fused_kernel<2>, B3_NT, smem));
+  // (the attribute and the occupancy only depend on the instantiation and the smem size)
+  static size_t cached_smem[2] = {0, 0};
+  static int cached_occ[2] = {0, 0};
+  const int inst = k <= 32 ? 0 : 1;
+  if (cached_smem[inst] != smem) {
+    int q = 0;
+    if (inst == 0) {
+      SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, bwd3_fused_kernel<1>, B3_NT, smem));
+    } else {
+      SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, bwd3_fused_kernel<2>, B3_NT, smem));
+    }
+    cached_smem[inst] = smem;
+    cached_occ[inst] = q;
   }
+  int occ = cached_occ[inst];
   if (occ < 1) occ = 1;
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int count = (int)std::min<long long>(S, (long long)occ * sms);

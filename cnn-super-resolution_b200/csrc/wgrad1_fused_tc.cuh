@@ -22,8 +22,11 @@
 // from TMEM: -32 KB of STS and -32 KB of tensor-core reads per tile, but every PB thread then
 // needs the mask of all 64 pixels and the chunk went from 0.784 to 1.00 ms (a 1-bit mask written
 // by the forward kernel would remove that); (2) keeping next-tile loads in registers across a
-// tile (the compiler serialises load -> compare chains).  The im2col producers (PA) are the
-// critical path: ~3 000 cycles per tile for 400 instructions per thread in dependent chains.
+// tile (the compiler serialises load -> compare chains); (3) staging the input rows from the two
+// LD warps instead of the producers (cp.async completion on an mbarrier): 0.784 -> 0.889 ms, the
+// LD warps sit on the delta-GEMM chain and 64 threads are too few for 660 copies per tile;
+// (4) 12 producer warps + one PB group: 0.831 ms.  The im2col producers (PA) are the critical
+// path: ~3 000 cycles per tile for 400 instructions per thread in dependent chains.
 //
 //   LD (2 warps)  d2 tile -> TF32 hi / lo -> smem                               -> d2_full
 //   I2 (1 warp)   DT[i&1] = [W2;W2] x d2^T, 12 MMAs                             -> dt_full

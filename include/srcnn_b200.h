@@ -204,7 +204,12 @@ int srcnn_forward_fused_supported(const srcnn_net* net);
  * [row0 - halo .. row1 + halo) of a [h][w] luma image, runs the fused forward, downloads
  * output rows [row0,row1) of the [h3][w3] result into host_out (which points at row row0).
  * halo = f1+f2+f3-3 input rows per band.  Used by bench.py e2e and by the
- * multi-GPU row-band sharding: rank g calls it with its own [row0,row1). */
+ * multi-GPU row-band sharding: rank g calls it with its own [row0,row1).
+ * Bands of >= 1024 output rows are cut into sub-bands whose upload, compute and download
+ * overlap on separate streams; that pipeline is captured into a CUDA graph owned by the
+ * context and replayed while the call's arguments (both host pointers, shape, band, network
+ * buffers) repeat -- the buffers' CONTENTS are read afresh on every call.  Synchronous: the
+ * result is in host_out on return.  Pinned host buffers give the PCIe rate; pageable ones work. */
 int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int in_w,
                           int in_h, int out_row0, int out_row1, float* host_out);
 

@@ -997,8 +997,13 @@ int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* h
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[2], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[2], 0));
   int rc = SRCNN_OK;
-  for (int i = 0, s0 = 0; s0 < n_samples && rc == SRCNN_OK; i++, s0 += chunk) {
-    const int S = std::min(chunk, n_samples - s0), b = i & 1;
+  // The upload of the FIRST chunk is exposed (nothing to train yet): when there is more than one
+  // chunk's worth of samples it is cut to half a chunk (SRCNN_TRAIN_HEAD=0 keeps it whole)
+  static const bool kHead = !(std::getenv("SRCNN_TRAIN_HEAD") && std::atoi(std::getenv("SRCNN_TRAIN_HEAD")) == 0);
+  const int head = (kHead && n_samples > chunk && chunk >= 512) ? chunk / 2 : chunk;
+  for (int i = 0, s0 = 0, S = 0; s0 < n_samples && rc == SRCNN_OK; i++, s0 += S) {
+    S = std::min(i == 0 ? head : chunk, n_samples - s0);
+    const int b = i & 1;
     // staging b was last read by the training of chunk i-2
     if (i >= 2) SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[b], 0));
     SRCNN_CUDA(cudaMemcpyAsync(ctx->stage_in[b], host_in + (size_t)s0 * w * h, per * S,

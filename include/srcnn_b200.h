@@ -241,7 +241,8 @@ int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
  * (src/ConfigBasedDataPipeline.cpp:128-195) on HOST-resident samples: `n_samples` inputs and
  * ground truths of w x h floats each are cut into chunks of at most `chunk` samples; the upload
  * of chunk i+1 (copy stream, double-buffered staging owned by the context) overlaps the
- * forward + backward of chunk i (srcnn_train_chunk).  Gradients accumulate in net->grad_*;
+ * forward + backward of chunk i (srcnn_train_chunk); the first chunk, whose upload nothing can
+ * hide, is half a chunk when there is more than one chunk of samples.  Gradients accumulate in net->grad_*;
  * the caller all-reduces them (multi-GPU) and calls srcnn_update_all.  `work` must hold
  * srcnn_train_workspace_bytes(net, w, h, chunk).  Returns once the host buffers may be reused;
  * the last chunk may still be training on the context stream. */

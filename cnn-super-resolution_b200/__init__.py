@@ -108,6 +108,14 @@ _SIGS = {
     "srcnn_train_materializes_d1": (_i, [_vp, C.POINTER(CNet)]),
     "srcnn_update_all": (_i, [_vp, C.POINTER(CNet), _u, _f, _f, C.POINTER(_f)]),
     "srcnn_validate_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
+    "srcnn_invalidate_params": (_i, [_vp]),
+    "srcnn_comm_unique_id": (_i, [_vp]),
+    "srcnn_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "srcnn_comm_destroy": (_i, [_vp]),
+    "srcnn_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "srcnn_allreduce_sum": (_i, [_vp, _u64, _sz, _sz]),
+    "srcnn_allreduce_grads": (_i, [_vp, C.POINTER(CNet)]),
+    "srcnn_broadcast": (_i, [_vp, _u64, _sz, _i]),
 }
 
 
@@ -215,6 +223,35 @@ class Context:
         p = _vp()
         _check(self.L.srcnn_stream(self.h, C.byref(p)))
         return p.value
+
+    # -- multi-GPU (NCCL communicator owned by the context) --
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id created on rank 0; hand it to the other ranks."""
+        buf = (C.c_ubyte * 128)()
+        _check(lib().srcnn_comm_unique_id(C.cast(buf, _vp)))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.L.srcnn_comm_init(self.h, rank, world, C.cast(buf, _vp)))
+
+    def comm_destroy(self):
+        _check(self.L.srcnn_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w = _i(), _i()
+        _check(self.L.srcnn_comm_info(self.h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def allreduce_sum(self, mem, count, offset=0):
+        _check(self.L.srcnn_allreduce_sum(self.h, mem, offset, count))
+
+    def broadcast(self, mem, count, root=0):
+        _check(self.L.srcnn_broadcast(self.h, mem, count, root))
+
+    def invalidate_params(self):
+        _check(self.L.srcnn_invalidate_params(self.h))
 
     # -- memory --
     def alloc(self, nbytes):
@@ -402,6 +439,10 @@ class Net:
     def validate_chunk(self, inp, gt, w, h, S, work, target):
         _check(self.ctx.L.srcnn_validate_chunk(self.ctx.h, C.byref(self.c), inp, gt, w, h, S,
                                                work, target))
+
+    def allreduce_grads(self):
+        """Sum the six gradient accumulators over the ranks of the context's communicator."""
+        _check(self.ctx.L.srcnn_allreduce_grads(self.ctx.h, C.byref(self.c)))
 
     def params(self):
         out = {}

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/srcnn_b200.h"
@@ -55,6 +57,10 @@ struct Allocation {
   size_t bytes = 0;
   bool released = false;
   bool owned = true;  // false: wrapped caller memory (srcnn_wrap)
+  // srcnn_mem_ptr has handed the raw device pointer out: anything (an NCCL broadcast, a torch
+  // copy, a kernel on another stream) may write it behind the device layer's back, so derived
+  // data (the packed operand image of the fused kernels) is never cached for it
+  bool exposed = false;
 };
 
 struct KernelStat {
@@ -77,7 +83,7 @@ struct srcnn_ctx {
   uint64_t launch_count = 0;
   // fused inference implementation: tensor cores (tcgen05, 3xTF32) where instantiated, unless
   // SRCNN_FUSED_IMPL=simt asks for the FP32 SIMT kernel (A/B measurements)
-  // 0 simt, 1 tcgen05 lockstep, 2 warp-specialised im2col, 3 planes (3xTF32), 4 planes (FP16 split)
+  // 0 simt, 3 planes (3xTF32), 4 planes (FP16 split); earlier generations live in exp/superseded
   int fused_impl = 4;
   bool deltas_tc = true;              // f=1 deltas on the tensor cores (deltas_tc.cuh)
   bool wgrad_tc = true;               // layer-1 weight gradient on the tensor cores (wgrad_tc.cuh)
@@ -91,7 +97,14 @@ struct srcnn_ctx {
   const void* hp_cache_key[6] = {};
   unsigned long long hp_cache_gen = 0;
   int hp_cache_n1 = 0;
-  unsigned long long write_gen = 0;   // bumped by every entry point that writes device memory
+  // bumped whenever one of the six buffers the cached image was packed from is written through
+  // the device layer (note_write) or by srcnn_invalidate_params
+  unsigned long long write_gen = 0;
+  srcnn_mem hp_cache_h[6] = {};
+  // per-context (= per-device) one-time kernel setup: opt-in dynamic shared memory sizes and
+  // occupancy queries, keyed by the kernel's address.  cudaFuncSetAttribute is per DEVICE, so a
+  // process-wide flag would leave a second context on another GPU unconfigured.
+  std::unordered_map<const void*, std::pair<size_t, int>> func_setup;
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand
@@ -112,11 +125,20 @@ struct srcnn_ctx {
   cudaEvent_t ev_join[2] = {};
   static constexpr int kEvents = 32;
   cudaEvent_t ev_in[kEvents] = {}, ev_k[kEvents] = {};
+  // data-parallel communicator (NCCL, loaded at run time: comm.cuh); null = single GPU
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   // last srcnn_net whose derived (repacked) parameters are cached; see fused kernels
   void* packed_params = nullptr;
   size_t packed_bytes = 0;
 
   static constexpr size_t kRedScratchBytes = 64 * 1024;
+
+  // a device-layer call is about to write the allocation behind `h`
+  void note_write(srcnn_mem h) {
+    for (int i = 0; i < 6; i++)
+      if (hp_cache_valid && hp_cache_h[i] == h) write_gen++;
+  }
 
   srcnn::Allocation* get(srcnn_mem h) {
     if (h >= allocs.size()) return nullptr;
@@ -171,6 +193,34 @@ inline int resolve(srcnn_ctx* ctx, srcnn_mem h, size_t need, T** out, const char
   *out = reinterpret_cast<T*>(a->ptr);
   return SRCNN_OK;
 }
+
+// Opt-in dynamic shared memory of `kernel` on this context's device, once per context and size;
+// with `occ` also the resident CTAs per SM at `threads` threads.
+template <class Kernel>
+inline int ensure_func_setup(srcnn_ctx* ctx, Kernel kernel, size_t smem, int threads = 0,
+                             int* occ = nullptr) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = ctx->func_setup.find(key);
+  if (it == ctx->func_setup.end() || it->second.first != smem || (occ && it->second.second < 0)) {
+    SRCNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = -1;
+    if (occ) SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kernel, threads, smem));
+    ctx->func_setup[key] = std::make_pair(smem, q);
+    it = ctx->func_setup.find(key);
+  }
+  if (occ) *occ = it->second.second;
+  return SRCNN_OK;
+}
+
+// every C-ABI entry starts here: the context must exist and its device must be current (a
+// caller thread, or torch, may have switched devices since the context was created)
+#define SRCNN_ENTER(ctx)                                                    \
+  do {                                                                      \
+    if (!(ctx)) return ::srcnn::fail(SRCNN_EINVAL, "ctx is null");          \
+    int _dev = -1;                                                          \
+    if (cudaGetDevice(&_dev) != cudaSuccess || _dev != (ctx)->device)       \
+      SRCNN_CUDA(cudaSetDevice((ctx)->device));                             \
+  } while (0)
 
 inline int ensure_scratch(srcnn_ctx* ctx, void** ptr, size_t* have, size_t need) {
   if (*have >= need) return SRCNN_OK;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) f1_deltas_tc_kernel(const float* _
   using fused_pl::elect_one;
   using fused_pl::tmem_ld16_nowait;
   using fused_pl::tmem_ld_wait;
-  using fused_ws::mbar_arrive;
+  using tc::mbar_arrive;
   __shared__ __align__(128) float sW[2 * C::N * C::K];   // [128][K]: rows 0..63 hi, 64..127 lo
   __shared__ __align__(8) uint64_t a_full[2], mma_done[2], d_free[2];
   __shared__ uint32_t tmem_slot;

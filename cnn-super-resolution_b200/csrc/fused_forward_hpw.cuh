@@ -152,8 +152,8 @@ using fused_pl::BatchExt;
 using fused_pl::elect_one;
 using fused_pl::tmem_ld16_nowait;
 using fused_pl::tmem_ld_wait;
-using fused_ws::mbar_arrive;
-using fused_ws::named_bar_sync;
+using tc::mbar_arrive;
+using tc::named_bar_sync;
 
 // ---------------------------------------------------------------------------- prepare --------
 // Derives the scales from the parameters (every CTA of a small grid, redundantly) and packs the

@@ -36,7 +36,6 @@
 
 #include "context.cuh"
 #include "fused_forward.cuh"
-#include "fused_forward_ws.cuh"
 #include "tc_common.cuh"
 
 namespace srcnn {
@@ -121,8 +120,8 @@ __device__ long long pl_trace[8][16];
 #define PL_REPORT(name)
 #endif
 
-using fused_ws::mbar_arrive;
-using fused_ws::named_bar_sync;
+using tc::mbar_arrive;
+using tc::named_bar_sync;
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float v[16]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);

@@ -7,8 +7,6 @@
 
 #include "context.cuh"
 #include "fused_forward.cuh"
-#include "fused_forward_tc.cuh"
-#include "fused_forward_ws.cuh"
 #include "fused_forward_pl.cuh"
 #include "fused_forward_hp.cuh"
 #include "fused_forward_hpw.cuh"
@@ -17,6 +15,7 @@
 #include "wgrad_tc.cuh"
 #include "wgrad1_fused_tc.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -62,8 +61,6 @@ __global__ void update_all_kernel(UpdateAllArgs a) {
 // one-time per-context setup (opt-in shared memory sizes etc.)
 inline int configure(srcnn_ctx* ctx) {
   SRCNN_TRY(fused::configure());
-  SRCNN_TRY(fused_tc::configure());
-  SRCNN_TRY(fused_ws::configure());
   SRCNN_TRY(fused_pl::configure());
   SRCNN_TRY(fused_hp::configure());
   SRCNN_TRY(fused_hpw::configure());
@@ -72,8 +69,6 @@ inline int configure(srcnn_ctx* ctx) {
   ctx->fused_impl = 4;                                           // "hp": planes, FP16 split
   if (impl && std::strcmp(impl, "pl") == 0) ctx->fused_impl = 3;  // planes, 3xTF32
   if (impl && std::strcmp(impl, "simt") == 0) ctx->fused_impl = 0;
-  if (impl && std::strcmp(impl, "tc") == 0) ctx->fused_impl = 1;  // lockstep tcgen05
-  if (impl && std::strcmp(impl, "ws") == 0) ctx->fused_impl = 2;  // warp-specialised, im2col
   const char* d1 = std::getenv("SRCNN_D1_IMPL");   // "simt": FP32 kernel for the f=1 deltas
   ctx->deltas_tc = !(d1 && std::strcmp(d1, "simt") == 0);
   const char* gw = std::getenv("SRCNN_GW_IMPL");   // "simt": FP32 kernel for the layer-1 gradient
@@ -190,6 +185,21 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
                          int S, const void* scales = nullptr) {
   if (!fused::supported(n1, n2, f1, f2, f3))
     return fail(SRCNN_EINVAL, "no fused forward instantiation");
+  // the per-image launches put the sample index in gridDim.z (at most 65 535): larger sample
+  // counts that do not take the virtual-image path go out in slices
+  constexpr int kMaxZ = 65535;
+  const bool virtual_image = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30) &&
+                             ctx->fused_impl >= 3 && fused_pl::supported(n1, n2, f1, f2, f3);
+  const bool virtual_wide = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30) &&
+                            ctx->fused_impl == 4 && fused_hpw::supported(n1, n2, f1, f2, f3);
+  if (S > kMaxZ && !virtual_image && !virtual_wide) {
+    const int pad = f1 + f2 + f3 - 3;
+    const size_t in_px = (size_t)in_w * in_h, out_px = (size_t)(in_w - pad) * (in_h - pad);
+    for (int s0 = 0; s0 < S; s0 += kMaxZ)
+      SRCNN_TRY(forward_fused(ctx, n1, n2, f1, f2, f3, in + s0 * in_px, out + s0 * out_px, w1, b1,
+                              w2, b2, w3, b3, in_w, in_h, std::min(kMaxZ, S - s0), scales));
+    return SRCNN_OK;
+  }
   fused::Args a{in, out, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
   if (ctx->fused_impl == 4 && fused_hpw::supported(n1, n2, f1, f2, f3)) {
@@ -202,15 +212,14 @@ inline int forward_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     return fused_hpw::launch(ctx, a, S, as_batch, static_cast<const fused_hpw::Scales*>(scales),
                              reinterpret_cast<int*>(ws));
   }
-  if (ctx->fused_impl >= 1 && fused_tc::supported(n1, n2, f1, f2, f3)) {
+  if (ctx->fused_impl >= 3 && fused_pl::supported(n1, n2, f1, f2, f3)) {
     // batches of small samples (validation patches) go through the virtual-image variant
     const bool as_batch = S > 1 && in_w <= 512 && (long long)S * in_w < (1LL << 30);
     if (ctx->fused_impl == 4)
       return fused_hp::launch(ctx, a, S, as_batch, nullptr, nullptr,
                               static_cast<const fused_hp::Scales*>(scales));
-    if (ctx->fused_impl == 3 && as_batch) return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
-    if (ctx->fused_impl == 3) return fused_pl::launch(ctx, a, S);
-    return ctx->fused_impl == 2 ? fused_ws::launch(ctx, a, S) : fused_tc::launch(ctx, a, S);
+    if (as_batch) return fused_pl::launch_batch(ctx, a, S, nullptr, nullptr);
+    return fused_pl::launch(ctx, a, S);
   }
   return fused::launch(ctx, n1, n2, a, S);
 }
@@ -235,14 +244,17 @@ inline bool fused_train_supported(srcnn_ctx* ctx, int n1, int n2, int f1, int f2
 inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
                                const float* in, float* out1, float* out2, float* out3,
                                const float* w1, const float* b1, const float* w2, const float* b2,
-                               const float* w3, const float* b3, int in_w, int in_h, int S) {
+                               const float* w3, const float* b3, int in_w, int in_h, int S,
+                               const void* scales = nullptr) {
   if (ctx->fused_impl < 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
   if ((long long)S * in_w >= (1LL << 30)) return 0;
   if ((long long)S * in_w * in_h >= (1LL << 31)) return 0;   // 32-bit pixel indices of out1 / out2
   fused::Args a{in, out3, w1, b1, w2, b2, w3, b3, in_w, in_h, in_w - (f1 + f2 + f3 - 3),
                 in_h - (f1 + f2 + f3 - 3)};
-  const int rc = ctx->fused_impl == 4 ? fused_hp::launch(ctx, a, S, true, out1, out2)
-                                      : fused_pl::launch_batch(ctx, a, S, out1, out2);
+  const int rc = ctx->fused_impl == 4
+                     ? fused_hp::launch(ctx, a, S, true, out1, out2,
+                                        static_cast<const fused_hp::Scales*>(scales))
+                     : fused_pl::launch_batch(ctx, a, S, out1, out2);
   return rc == SRCNN_OK ? 1 : rc;
 }
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <new>
 
+#include "comm.cuh"
 #include "context.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_generic.cuh"
@@ -111,6 +112,8 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (!ctx) return SRCNN_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm && comm::api()) comm::api()->CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
   for (Allocation& a : ctx->allocs)
     if (a.owned && !a.released && a.ptr) cudaFree(a.ptr);
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
@@ -144,14 +147,14 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
 }
 
 int srcnn_block(srcnn_ctx* ctx) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
   return SRCNN_OK;
 }
 
 int srcnn_device_info(srcnn_ctx* ctx, char* name, size_t name_len, int* sm_count,
                       size_t* global_mem_bytes) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   cudaDeviceProp prop;
   SRCNN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
   if (name && name_len) {
@@ -164,7 +167,7 @@ int srcnn_device_info(srcnn_ctx* ctx, char* name, size_t name_len, int* sm_count
 }
 
 int srcnn_profile_get(srcnn_ctx* ctx, int kernel_id, uint64_t* total_ns, uint64_t* launches) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(kernel_id >= 0 && kernel_id < SRCNN_K_COUNT, "bad kernel id %d", kernel_id);
   if (total_ns) *total_ns = ctx->stats[kernel_id].total_ns;
   if (launches) *launches = ctx->stats[kernel_id].launches;
@@ -187,6 +190,7 @@ int srcnn_stream(srcnn_ctx* ctx, void** cuda_stream) {
 
 int srcnn_alloc(srcnn_ctx* ctx, size_t bytes, srcnn_mem* out) {
   SRCNN_REQUIRE(ctx && out, "null argument");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(bytes > 0, "cannot allocate 0 bytes");
   SRCNN_REQUIRE(ctx->allocs.size() < (size_t)SRCNN_NULL_MEM, "handle table full");
   Allocation a;
@@ -202,9 +206,10 @@ int srcnn_alloc(srcnn_ctx* ctx, size_t bytes, srcnn_mem* out) {
 }
 
 int srcnn_wrap(srcnn_ctx* ctx, void* device_ptr, size_t bytes, srcnn_mem* out) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && out && device_ptr, "null argument");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(bytes > 0, "cannot wrap 0 bytes");
+  SRCNN_REQUIRE(ctx->allocs.size() < (size_t)SRCNN_NULL_MEM, "handle table full");
   Allocation a;
   a.ptr = device_ptr;
   a.bytes = bytes;
@@ -215,9 +220,9 @@ int srcnn_wrap(srcnn_ctx* ctx, void* device_ptr, size_t bytes, srcnn_mem* out) {
 }
 
 int srcnn_release(srcnn_ctx* ctx, srcnn_mem mem) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   if (mem >= ctx->allocs.size()) return fail(SRCNN_EHANDLE, "invalid memory handle");
+  ctx->note_write(mem);
   Allocation& a = ctx->allocs[mem];
   if (!a.released && a.ptr && a.owned) {
     SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -240,6 +245,10 @@ int srcnn_mem_ptr(srcnn_ctx* ctx, srcnn_mem mem, void** device_ptr) {
   SRCNN_REQUIRE(ctx && device_ptr, "null argument");
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle");
+  // the raw pointer leaves the device layer: writes through it are invisible to note_write, so
+  // nothing derived from this allocation is cached any more (see srcnn_invalidate_params)
+  a->exposed = true;
+  ctx->note_write(mem);
   *device_ptr = a->ptr;
   return SRCNN_OK;
 }
@@ -255,13 +264,14 @@ int srcnn_mem_usage(srcnn_ctx* ctx, size_t* buffer_bytes) {
 
 int srcnn_write(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, const void* src,
                 int block) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && src, "null argument");
+  SRCNN_ENTER(ctx);
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in write");
-  if (offset + bytes > a->bytes)
+  if (bytes > a->bytes || offset > a->bytes - bytes)
     return fail(SRCNN_ERANGE, "Tried to write more then is allocated (%zu+%zu > %zu)", offset,
                 bytes, a->bytes);
+  ctx->note_write(mem);
   SRCNN_CUDA(cudaMemcpyAsync((char*)a->ptr + offset, src, bytes, cudaMemcpyHostToDevice,
                              ctx->stream));
   if (block) SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -271,9 +281,10 @@ int srcnn_write(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, cons
 int srcnn_read(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, void* dst,
                int block) {
   SRCNN_REQUIRE(ctx && dst, "null argument");
+  SRCNN_ENTER(ctx);
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in read");
-  if (offset + bytes > a->bytes)
+  if (bytes > a->bytes || offset > a->bytes - bytes)
     return fail(SRCNN_ERANGE, "Tried to read more then is allocated (%zu+%zu > %zu)", offset,
                 bytes, a->bytes);
   SRCNN_CUDA(cudaMemcpyAsync(dst, (const char*)a->ptr + offset, bytes, cudaMemcpyDeviceToHost,
@@ -284,32 +295,32 @@ int srcnn_read(srcnn_ctx* ctx, srcnn_mem mem, size_t offset, size_t bytes, void*
 
 int srcnn_copy_region(srcnn_ctx* ctx, srcnn_mem src, size_t src_offset, srcnn_mem dst,
                       size_t dst_offset, size_t bytes) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   Allocation* s = ctx->get(src);
   Allocation* d = ctx->get(dst);
   if (!s || !d) return fail(SRCNN_EHANDLE, "invalid memory handle in copy");
-  if (src_offset + bytes > s->bytes)
+  if (bytes > s->bytes || src_offset > s->bytes - bytes)
     return fail(SRCNN_ERANGE, "buffer copy would read after src end");
-  if (dst_offset + bytes > d->bytes)
+  if (bytes > d->bytes || dst_offset > d->bytes - bytes)
     return fail(SRCNN_ERANGE, "When performing buffer copy, would write after dst end");
+  ctx->note_write(dst);
   SRCNN_CUDA(cudaMemcpyAsync((char*)d->ptr + dst_offset, (const char*)s->ptr + src_offset, bytes,
                              cudaMemcpyDeviceToDevice, ctx->stream));
   return SRCNN_OK;
 }
 
 int srcnn_copy(srcnn_ctx* ctx, srcnn_mem src, srcnn_mem dst, size_t dst_offset) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   Allocation* s = ctx->get(src);
   if (!s) return fail(SRCNN_EHANDLE, "invalid memory handle in copy");
   return srcnn_copy_region(ctx, src, 0, dst, dst_offset, s->bytes);
 }
 
 int srcnn_fill_float(srcnn_ctx* ctx, srcnn_mem mem, float value) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   Allocation* a = ctx->get(mem);
   if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in fill");
+  ctx->note_write(mem);
   const size_t len = a->bytes / sizeof(float);
   if (len == 0) return SRCNN_OK;
   if (value == 0.f) {
@@ -337,8 +348,7 @@ int srcnn_host_free(void* host_ptr) {
 
 int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W, srcnn_mem B,
                         int k, int n, int f, int skip_relu, int in_w, int in_h, int S) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(k > 0 && n > 0 && f > 0 && S > 0, "bad layer shape k=%d n=%d f=%d S=%d", k, n, f, S);
   SRCNN_REQUIRE(in_w >= f && in_h >= f, "input %dx%d smaller than filter %d", in_w, in_h, f);
   const int ow = in_w - f + 1, oh = in_h - f + 1;
@@ -346,6 +356,7 @@ int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W
   float* pout;
   SRCNN_TRY(resolve(ctx, in, sizeof(float) * (size_t)S * in_w * in_h * k, &pin, "layer input"));
   SRCNN_TRY(resolve(ctx, out, sizeof(float) * (size_t)S * ow * oh * n, &pout, "layer output"));
+  ctx->note_write(out);
   SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f * f * k * n, &pW, "weights"));
   SRCNN_TRY(resolve(ctx, B, sizeof(float) * (size_t)n, &pB, "bias"));
   LaunchScope scope(ctx, SRCNN_K_FORWARD);
@@ -360,8 +371,7 @@ int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W
 
 int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
                         int gt_w, int gt_h, int algo_w, int algo_h, int S) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
                 "bad squared_error dimensions");
   const float *pgt, *palgo;
@@ -369,6 +379,7 @@ int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem 
   SRCNN_TRY(resolve(ctx, gt, sizeof(float) * (size_t)S * gt_w * gt_h, &pgt, "ground truth"));
   SRCNN_TRY(resolve(ctx, algo, sizeof(float) * (size_t)S * algo_w * algo_h, &palgo, "algo result"));
   SRCNN_TRY(resolve(ctx, target, sizeof(float), &pt, "squared error target"));
+  ctx->note_write(target);
   const size_t total = (size_t)S * algo_w * algo_h;
   const int blocks = grid_1d(total, generic::RED_THREADS, generic::RED_MAX_BLOCKS);
   LaunchScope scope(ctx, SRCNN_K_SQUARED_ERR, 2);
@@ -381,8 +392,7 @@ int srcnn_squared_error(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem 
 
 int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_mem target,
                            int gt_w, int gt_h, int algo_w, int algo_h, int S) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(S > 0 && algo_w > 0 && algo_h > 0 && gt_w >= algo_w && gt_h >= algo_h,
                 "bad last_layer_delta dimensions");
   const float *pgt, *palgo;
@@ -391,6 +401,7 @@ int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_m
   SRCNN_TRY(resolve(ctx, gt, sizeof(float) * (size_t)S * gt_w * gt_h, &pgt, "ground truth"));
   SRCNN_TRY(resolve(ctx, algo, sizeof(float) * total, &palgo, "algo result"));
   SRCNN_TRY(resolve(ctx, target, sizeof(float) * total, &pt, "last layer delta target"));
+  ctx->note_write(target);
   LaunchScope scope(ctx, SRCNN_K_LAST_LAYER_DELTA);
   generic::last_layer_delta_kernel<<<grid_1d(total, 256, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
       pgt, palgo, pt, gt_w, gt_h, algo_w, algo_h, S);
@@ -400,8 +411,7 @@ int srcnn_last_layer_delta(srcnn_ctx* ctx, srcnn_mem gt, srcnn_mem algo, srcnn_m
 int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
                  srcnn_mem target, srcnn_mem W, int n_curr, int f_next, int n_next, int out_w,
                  int out_h, int S) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(n_curr > 0 && f_next > 0 && n_next > 0 && S > 0, "bad deltas shape");
   SRCNN_REQUIRE(out_w >= f_next && out_h >= f_next, "layer output smaller than next filter");
   const int nw = out_w - f_next + 1, nh = out_h - f_next + 1;
@@ -411,6 +421,7 @@ int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
   SRCNN_TRY(resolve(ctx, deltas_next, sizeof(float) * (size_t)S * nw * nh * n_next, &pdn, "next layer deltas"));
   SRCNN_TRY(resolve(ctx, layer_output, sizeof(float) * cur, &plo, "layer output"));
   SRCNN_TRY(resolve(ctx, target, sizeof(float) * cur, &pt, "deltas target"));
+  ctx->note_write(target);
   SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f_next * f_next * n_curr * n_next, &pW, "next layer weights"));
   LaunchScope scope(ctx, SRCNN_K_DELTAS);
   if (fast::deltas(ctx, pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h, S))
@@ -425,8 +436,7 @@ int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
 int srcnn_backpropagate(srcnn_ctx* ctx, srcnn_mem deltas, srcnn_mem layer_input,
                         srcnn_mem grad_w, srcnn_mem grad_b, int n, int k, int f, int out_w,
                         int out_h, int S) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(n > 0 && k > 0 && f > 0 && S > 0 && out_w > 0 && out_h > 0, "bad backpropagate shape");
   const int iw = out_w + f - 1, ih = out_h + f - 1;
   const float *pd, *pin;
@@ -435,6 +445,8 @@ int srcnn_backpropagate(srcnn_ctx* ctx, srcnn_mem deltas, srcnn_mem layer_input,
   SRCNN_TRY(resolve(ctx, layer_input, sizeof(float) * (size_t)S * iw * ih * k, &pin, "layer input"));
   SRCNN_TRY(resolve(ctx, grad_w, sizeof(float) * (size_t)f * f * k * n, &pgw, "grad_w"));
   SRCNN_TRY(resolve(ctx, grad_b, sizeof(float) * (size_t)n, &pgb, "grad_b"));
+  ctx->note_write(grad_w);
+  ctx->note_write(grad_b);
   LaunchScope scope(ctx, SRCNN_K_BACKPROPAGATE, 2);
   int rc_fast = fast::backpropagate(ctx, pd, pin, pgw, pgb, n, k, f, out_w, out_h, S);
   if (rc_fast < 0) return rc_fast;
@@ -463,8 +475,7 @@ int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad
                         srcnn_mem grad_b, srcnn_mem prev_dw, srcnn_mem prev_db, float momentum,
                         float weight_decay, float learning_rate, unsigned batch_size,
                         unsigned weights_size, unsigned bias_size) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
   float *pw, *pb, *ppw, *ppb;
   const float *pgw, *pgb;
@@ -475,6 +486,11 @@ int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad
   SRCNN_TRY(resolve(ctx, grad_b, bb, &pgb, "grad_b"));
   SRCNN_TRY(resolve(ctx, prev_dw, wb, &ppw, "previous delta w"));
   SRCNN_TRY(resolve(ctx, prev_db, bb, &ppb, "previous delta b"));
+  ctx->note_write(w);
+  ctx->note_write(b);
+  ctx->note_write(prev_dw);
+  ctx->note_write(prev_db);
+  if (weights_size == 0 && bias_size == 0) return SRCNN_OK;   // nothing to update
   const unsigned total = std::max(weights_size, bias_size);
   LaunchScope scope(ctx, SRCNN_K_UPDATE_PARAMS);
   generic::update_params_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(
@@ -484,12 +500,12 @@ int srcnn_update_params(srcnn_ctx* ctx, srcnn_mem w, srcnn_mem b, srcnn_mem grad
 }
 
 int srcnn_sum(srcnn_ctx* ctx, srcnn_mem data, unsigned len, int squared, srcnn_mem target) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   const float* pd;
   float* pt;
   SRCNN_TRY(resolve(ctx, data, sizeof(float) * (size_t)len, &pd, "sum data"));
   SRCNN_TRY(resolve(ctx, target, sizeof(float), &pt, "sum target"));
+  ctx->note_write(target);
   const int blocks = grid_1d(len, generic::RED_THREADS, generic::RED_MAX_BLOCKS);
   LaunchScope scope(ctx, SRCNN_K_SUM, 2);
   generic::sum_stage1<<<blocks, generic::RED_THREADS, 0, ctx->stream>>>(
@@ -500,10 +516,10 @@ int srcnn_sum(srcnn_ctx* ctx, srcnn_mem data, unsigned len, int squared, srcnn_m
 }
 
 int srcnn_sub_from_all(srcnn_ctx* ctx, srcnn_mem data, float value, unsigned len) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   float* pd;
   SRCNN_TRY(resolve(ctx, data, sizeof(float) * (size_t)len, &pd, "sub_from_all data"));
+  ctx->note_write(data);
   if (len == 0) return SRCNN_OK;
   LaunchScope scope(ctx, SRCNN_K_SUB_FROM_ALL);
   generic::sub_from_all_kernel<<<grid_1d(len, 256, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
@@ -513,23 +529,24 @@ int srcnn_sub_from_all(srcnn_ctx* ctx, srcnn_mem data, float value, unsigned len
 
 int srcnn_extract_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem target, int w, int h,
                        int normalize) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(w > 0 && h > 0, "bad image size");
   const uchar4* pi;
   float* pt;
   SRCNN_TRY(resolve(ctx, rgba, (size_t)w * h * 4, &pi, "rgba image"));
   SRCNN_TRY(resolve(ctx, target, sizeof(float) * (size_t)w * h, &pt, "luma target"));
+  ctx->note_write(target);
   LaunchScope scope(ctx, SRCNN_K_EXTRACT_LUMA);
-  generic::extract_luma_kernel<<<(w * h + 255) / 256, 256, 0, ctx->stream>>>(pi, pt, w * h,
-                                                                            normalize);
+  const size_t npx = (size_t)w * h;
+  SRCNN_REQUIRE(npx < ((size_t)1 << 31), "image of %dx%d pixels is too large for one launch", w, h);
+  generic::extract_luma_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(
+      pi, pt, (int)npx, normalize);
   return check_launch("extract_luma");
 }
 
 int srcnn_swap_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem new_luma, srcnn_mem target,
                     int gt_w, int gt_h, int luma_w, int luma_h) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_REQUIRE(gt_w > 0 && gt_h > 0 && luma_w > 0 && luma_h > 0 && luma_w <= gt_w && luma_h <= gt_h,
                 "bad swap_luma dimensions");
   const uchar4* pi;
@@ -538,6 +555,7 @@ int srcnn_swap_luma(srcnn_ctx* ctx, srcnn_mem rgba, srcnn_mem new_luma, srcnn_me
   SRCNN_TRY(resolve(ctx, rgba, (size_t)gt_w * gt_h * 4, &pi, "rgba image"));
   SRCNN_TRY(resolve(ctx, new_luma, sizeof(float) * (size_t)luma_w * luma_h, &pl, "new luma"));
   SRCNN_TRY(resolve(ctx, target, (size_t)gt_w * gt_h * 3, &pt, "rgb target"));
+  ctx->note_write(target);
   LaunchScope scope(ctx, SRCNN_K_SWAP_LUMA);
   dim3 block(32, 8), grid((gt_w + 31) / 32, (gt_h + 7) / 8);
   generic::swap_luma_kernel<<<grid, block, 0, ctx->stream>>>(pi, pl, pt, gt_w, gt_h, luma_w, luma_h);
@@ -553,11 +571,43 @@ bool params_owned(srcnn_ctx* ctx, const srcnn_net* net) {
   for (int l = 0; l < 3; l++) {
     const Allocation* w = ctx->get(net->w[l]);
     const Allocation* b = ctx->get(net->b[l]);
-    if (!w || !b || !w->owned || !b->owned) return false;
+    if (!w || !b || !w->owned || !b->owned || w->exposed || b->exposed) return false;
   }
   return true;
 }
+
+// the prepared operand image of `net` for the fused kernels (from the context's cache while the
+// six parameter buffers are untouched, context-owned and never exposed; else packed afresh)
+int net_prepare(srcnn_ctx* ctx, const srcnn_net* net, const float* w1, const float* b1,
+                const float* w2, const float* b2, const float* w3, const float* b3,
+                const void** scales) {
+  SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
+                                b3, params_owned(ctx, net), scales));
+  for (int l = 0; l < 3; l++) {
+    ctx->hp_cache_h[2 * l] = net->w[l];
+    ctx->hp_cache_h[2 * l + 1] = net->b[l];
+  }
+  return SRCNN_OK;
+}
+
+// drops the handles a scope appended to the table (wrapped views of a workspace, staging
+// buffers) on EVERY exit path, so that errors do not grow the table
+struct TableScope {
+  srcnn_ctx* ctx;
+  size_t size;
+  explicit TableScope(srcnn_ctx* c) : ctx(c), size(c->allocs.size()) {}
+  ~TableScope() {
+    if (ctx->allocs.size() > size) ctx->allocs.resize(size);
+  }
+};
 }  // namespace
+
+int srcnn_invalidate_params(srcnn_ctx* ctx) {
+  SRCNN_ENTER(ctx);
+  ctx->write_gen++;
+  ctx->hp_cache_valid = false;
+  return SRCNN_OK;
+}
 
 int srcnn_forward_fused_supported(const srcnn_net* net) {
   if (!net) return 0;
@@ -566,7 +616,7 @@ int srcnn_forward_fused_supported(const srcnn_net* net) {
 
 int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem out,
                         int in_w, int in_h, int S, srcnn_mem scratch1, srcnn_mem scratch2) {
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, in_w, in_h);
   SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "image %dx%d too small for the network", in_w, in_h);
@@ -581,11 +631,9 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
     SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
     SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
     SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
-    for (int l = 0; l < 3; l++)   // writing the result into a parameter buffer?  (nobody does)
-      if (out == net->w[l] || out == net->b[l]) ctx->write_gen++;
+    ctx->note_write(out);
     const void* scales = nullptr;
-    SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2,
-                                  w3, b3, params_owned(ctx, net), &scales));
+    SRCNN_TRY(net_prepare(ctx, net, w1, b1, w2, b2, w3, b3, &scales));
     LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
     SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin, pout, w1,
                                   b1, w2, b2, w3, b3, in_w, in_h, S, scales));
@@ -605,6 +653,7 @@ int srcnn_forward_fused(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcn
 int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int in_w,
                           int in_h, int out_row0, int out_row1, float* host_out) {
   SRCNN_REQUIRE(ctx && host_in && host_out, "null argument");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, in_w, in_h);
   SRCNN_REQUIRE(d.w3 > 0 && d.h3 > 0, "image %dx%d too small for the network", in_w, in_h);
@@ -639,7 +688,11 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // clock of the call with the 0.9 ms kernel: 12 sub-bands 1.84-1.88 ms, 14: 1.78, 16: 1.73-1.78,
   // 18: 1.78, 20 (cap 3): 1.79, 24: 1.83, 32: 1.96; ramp cap 3 / 5 / 6 at 16: 1.78 / 1.83 / 1.79.
   static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 16;
-  int n_sub = band_out_h >= 1024 ? std::min(std::max(kSubDefault, 2), kMaxSub) : 1;
+  // bands of a multi-GPU partition are pipelined too (an 8-way split of C3 leaves 511 rows per
+  // rank): about one sub-band per 128 output rows, at most the default count
+  int n_sub = band_out_h >= 256
+                  ? std::min(std::min(std::max(kSubDefault, 2), kMaxSub), std::max(2, band_out_h / 128))
+                  : 1;
   int sub_r0[kMaxSub + 1] = {0};
   {
     // shares ramp up from a small first sub-band and down to a small last one: 1,2,3,..,3,2,1
@@ -671,8 +724,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // one set of operand scales for all sub-bands (computed on the context stream, before the
   // event the side streams wait for)
   const void* scales = nullptr;
-  SRCNN_TRY(fast::fused_prepare(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, w1, b1, w2, b2, w3,
-                                b3, params_owned(ctx, net), &scales));
+  SRCNN_TRY(net_prepare(ctx, net, w1, b1, w2, b2, w3, b3, &scales));
   if (n_sub == 1) {
     SRCNN_CUDA(cudaMemcpyAsync(din, host_in + (size_t)out_row0 * in_w, in_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
@@ -733,6 +785,19 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     SRCNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
   }
+  // ends (and discards) the capture on every early exit below, so that a failed call never
+  // leaves the context stream and the side streams capturing
+  struct CaptureGuard {
+    cudaStream_t s;
+    bool active;
+    ~CaptureGuard() {
+      if (!active) return;
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(s, &g);
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+    }
+  } capture{ctx->stream, use_graph};
   const uint64_t launches_before = ctx->launch_count;
   // order the side streams after whatever the context stream was doing with the buffers
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[0], ctx->stream));
@@ -753,15 +818,15 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     SRCNN_CUDA(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
     cudaStream_t cs = (i & 1) ? ctx->compute2 : main_stream;
     SRCNN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_in[i], 0));
+    ctx->stream = cs;   // the launch helpers (and the profile timers) use the context stream
     {
       LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
-      ctx->stream = cs;   // the launch helpers use the context stream
       rc = fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3,
                                din + (size_t)r0 * in_w, dout + (size_t)r0 * d.w3, w1, b1, w2, b2,
                                w3, b3, in_w, r1 - r0 + halo, 1, scales);
-      ctx->stream = main_stream;
       if (rc == SRCNN_OK) rc = check_launch("forward_fused");
     }
+    ctx->stream = main_stream;
     if (rc != SRCNN_OK) break;
     SRCNN_CUDA(cudaEventRecord(ctx->ev_k[i], cs));
     SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
@@ -777,6 +842,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_join[1], ctx->compute2);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->ev_join[1], 0);
     const cudaError_t e2 = cudaStreamEndCapture(main_stream, &graph);
+    capture.active = false;
     if (e == cudaSuccess) e = e2;
     if (rc == SRCNN_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ctx->e2e_graph, graph, 0);
     if (graph) cudaGraphDestroy(graph);
@@ -828,9 +894,6 @@ int carve(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem work, int w, int h, in
   SRCNN_TRY(srcnn_wrap(ctx, base + 2 * e1 + 2 * e2 + e3, e3, &wk->d3));
   return SRCNN_OK;
 }
-// wrapped handles are always the last six table entries: drop them again so a long
-// training run does not grow the table
-void uncarve(srcnn_ctx* ctx) { ctx->allocs.resize(ctx->allocs.size() - 6); }
 
 // last_layer_delta + deltas(layer 2) + backpropagate(layer 3) in one launch (+ the reduce)
 int backward3_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem gt, const Work& wk,
@@ -894,11 +957,16 @@ int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
   SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
   SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
   SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
-  LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3));
+  // the operand image only changes when the parameters do (srcnn_update_all, srcnn_write ...):
+  // the chunks of an epoch share the context's cached copy
+  const void* scales = nullptr;
+  SRCNN_TRY(net_prepare(ctx, net, w1, b1, w2, b2, w3, b3, &scales));
+  LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
   const int rc = fast::forward_train_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin,
-                                           o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S);
+                                           o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S, scales);
   if (rc < 0) return rc;
   *launched = rc;
+  if (!rc) scope.n_launches = 0;
   return rc ? check_launch("forward_train_fused") : SRCNN_OK;
 }
 }  // namespace
@@ -945,23 +1013,20 @@ int srcnn_train_materializes_d1(srcnn_ctx* ctx, const srcnn_net* net) {
 
 int srcnn_train_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt, int w,
                       int h, int S, srcnn_mem work) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
   SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  TableScope views(ctx);   // the six wrapped views of `work` leave the table on every exit path
   Work wk;
   SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
-  const int rc = train_chunk_on(ctx, net, in, gt, w, h, S, wk);
-  uncarve(ctx);
-  return rc;
+  return train_chunk_on(ctx, net, in, gt, w, h, S, wk);
 }
 
 int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                               int w, int h, int S, srcnn_mem out1, srcnn_mem out2,
                               srcnn_mem out3, srcnn_mem d1, srcnn_mem d2, srcnn_mem d3) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
   SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
@@ -972,8 +1037,8 @@ int srcnn_train_chunk_buffers(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
 int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in,
                             const float* host_gt, int w, int h, int n_samples, int chunk,
                             srcnn_mem work) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && host_in && host_gt, "null argument");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
   SRCNN_REQUIRE(n_samples > 0 && chunk > 0 && d.w3 > 0 && d.h3 > 0,
@@ -1012,16 +1077,13 @@ int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* h
                                cudaMemcpyHostToDevice, ctx->copy_in));
     SRCNN_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->copy_in));
     SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+    TableScope views(ctx);   // staging + workspace views leave the table on every exit path
     srcnn_mem mi, mg;
     SRCNN_TRY(srcnn_wrap(ctx, ctx->stage_in[b], per * S, &mi));
     SRCNN_TRY(srcnn_wrap(ctx, ctx->stage_gt[b], per * S, &mg));
     Work wk;
-    rc = carve(ctx, net, work, w, h, S, &wk);
-    if (rc == SRCNN_OK) {
-      rc = train_chunk_on(ctx, net, mi, mg, w, h, S, wk);
-      uncarve(ctx);
-    }
-    ctx->allocs.resize(ctx->allocs.size() - 2);   // the two staging handles
+    SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
+    rc = train_chunk_on(ctx, net, mi, mg, w, h, S, wk);
     if (rc == SRCNN_OK) SRCNN_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
   }
   SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_in));   // the host buffers may be reused
@@ -1030,8 +1092,8 @@ int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* h
 
 int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, float momentum,
                      float weight_decay, const float lr[3]) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
   SRCNN_REQUIRE(ctx && lr, "null argument");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   SRCNN_REQUIRE(batch_size > 0, "batch_size must be > 0");
   fast::UpdateAllArgs a;
@@ -1046,6 +1108,8 @@ int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, 
     SRCNN_TRY(resolve(ctx, net->grad_b[l], sizeof(float) * bs, &a.gb[l], "grad_b"));
     SRCNN_TRY(resolve(ctx, net->prev_dw[l], sizeof(float) * ws, &a.pw[l], "previous delta w"));
     SRCNN_TRY(resolve(ctx, net->prev_db[l], sizeof(float) * bs, &a.pb[l], "previous delta b"));
+    ctx->note_write(net->w[l]);
+    ctx->note_write(net->b[l]);
     a.ws[l] = ws;
     a.bs[l] = bs;
     a.lr[l] = lr[l];
@@ -1061,17 +1125,135 @@ int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, 
 
 int srcnn_validate_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                          int w, int h, int S, srcnn_mem work, srcnn_mem target) {
-  if (ctx) ctx->write_gen++;   // device memory changes: cached operand images are stale
-  SRCNN_REQUIRE(ctx, "ctx is null");
+  SRCNN_ENTER(ctx);
   SRCNN_TRY(check_net(net));
   const Dims d = net_dims(net, w, h);
   SRCNN_REQUIRE(S > 0 && d.w3 > 0 && d.h3 > 0, "sample %dx%d too small for the network", w, h);
+  TableScope views(ctx);
   Work wk;
   SRCNN_TRY(carve(ctx, net, work, w, h, S, &wk));
-  int rc = srcnn_forward_fused(ctx, net, in, wk.out3, w, h, S, wk.out1, wk.out2);
-  if (rc == SRCNN_OK) rc = srcnn_squared_error(ctx, gt, wk.out3, target, w, h, d.w3, d.h3, S);
-  uncarve(ctx);
-  return rc;
+  SRCNN_TRY(srcnn_forward_fused(ctx, net, in, wk.out3, w, h, S, wk.out1, wk.out2));
+  return srcnn_squared_error(ctx, gt, wk.out3, target, w, h, d.w3, d.h3, S);
+}
+
+// ======================================================================= multi-GPU ====
+
+int srcnn_comm_unique_id(unsigned char id[SRCNN_COMM_ID_BYTES]) {
+  SRCNN_REQUIRE(id != nullptr, "id is null");
+  comm::Api* api = comm::api();
+  if (!api) return fail(SRCNN_ECUDA, "libnccl.so.2 could not be loaded: %s", dlerror());
+  static_assert(sizeof(comm::UniqueId) == SRCNN_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  comm::UniqueId u;
+  SRCNN_NCCL(api->GetUniqueId(&u), "ncclGetUniqueId");
+  std::memcpy(id, &u, sizeof(u));
+  return SRCNN_OK;
+}
+
+int srcnn_comm_init(srcnn_ctx* ctx, int rank, int world,
+                    const unsigned char id[SRCNN_COMM_ID_BYTES]) {
+  SRCNN_ENTER(ctx);
+  SRCNN_REQUIRE(id != nullptr, "id is null");
+  SRCNN_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d of %d", rank, world);
+  SRCNN_REQUIRE(ctx->nccl_comm == nullptr, "this context already has a communicator");
+  comm::Api* api = comm::api();
+  if (!api) return fail(SRCNN_ECUDA, "libnccl.so.2 could not be loaded: %s", dlerror());
+  comm::UniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  comm::ncclComm_t c = nullptr;
+  SRCNN_NCCL(api->CommInitRank(&c, world, u, rank), "ncclCommInitRank");
+  ctx->nccl_comm = c;
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return SRCNN_OK;
+}
+
+int srcnn_comm_destroy(srcnn_ctx* ctx) {
+  SRCNN_ENTER(ctx);
+  if (ctx->nccl_comm) {
+    SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    SRCNN_NCCL(comm::api()->CommDestroy(ctx->nccl_comm), "ncclCommDestroy");
+  }
+  ctx->nccl_comm = nullptr;
+  ctx->comm_rank = 0;
+  ctx->comm_world = 1;
+  return SRCNN_OK;
+}
+
+int srcnn_comm_info(srcnn_ctx* ctx, int* rank, int* world) {
+  SRCNN_ENTER(ctx);
+  if (rank) *rank = ctx->comm_rank;
+  if (world) *world = ctx->comm_world;
+  return SRCNN_OK;
+}
+
+int srcnn_allreduce_sum(srcnn_ctx* ctx, srcnn_mem buf, size_t offset_floats, size_t count) {
+  SRCNN_ENTER(ctx);
+  Allocation* a = ctx->get(buf);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in allreduce");
+  const size_t total = a->bytes / sizeof(float);
+  if (count > total || offset_floats > total - count)
+    return fail(SRCNN_ERANGE, "allreduce of %zu floats at %zu outside a buffer of %zu", count,
+                offset_floats, total);
+  if (!ctx->nccl_comm || ctx->comm_world == 1 || count == 0) return SRCNN_OK;   // sum over one rank
+  ctx->note_write(buf);
+  float* p = reinterpret_cast<float*>(a->ptr) + offset_floats;
+  SRCNN_NCCL(comm::api()->AllReduce(p, p, count, comm::kNcclFloat, comm::kNcclSum, ctx->nccl_comm,
+                                    ctx->stream),
+             "ncclAllReduce");
+  return SRCNN_OK;
+}
+
+int srcnn_broadcast(srcnn_ctx* ctx, srcnn_mem buf, size_t count, int root) {
+  SRCNN_ENTER(ctx);
+  Allocation* a = ctx->get(buf);
+  if (!a) return fail(SRCNN_EHANDLE, "invalid memory handle in broadcast");
+  if (count > a->bytes / sizeof(float))
+    return fail(SRCNN_ERANGE, "broadcast of %zu floats outside a buffer of %zu bytes", count, a->bytes);
+  SRCNN_REQUIRE(root >= 0 && root < ctx->comm_world, "bad broadcast root %d", root);
+  if (!ctx->nccl_comm || ctx->comm_world == 1 || count == 0) return SRCNN_OK;
+  ctx->note_write(buf);
+  SRCNN_NCCL(comm::api()->Broadcast(a->ptr, a->ptr, count, comm::kNcclFloat, root, ctx->nccl_comm,
+                                    ctx->stream),
+             "ncclBroadcast");
+  return SRCNN_OK;
+}
+
+int srcnn_allreduce_grads(srcnn_ctx* ctx, const srcnn_net* net) {
+  SRCNN_ENTER(ctx);
+  SRCNN_TRY(check_net(net));
+  if (!ctx->nccl_comm || ctx->comm_world == 1) return SRCNN_OK;
+  const int ks[3] = {1, net->n1, net->n2}, ns[3] = {net->n1, net->n2, 1},
+            fs[3] = {net->f1, net->f2, net->f3};
+  float* p[6];
+  size_t cnt[6];
+  for (int l = 0; l < 3; l++) {
+    cnt[2 * l] = (size_t)fs[l] * fs[l] * ks[l] * ns[l];
+    cnt[2 * l + 1] = (size_t)ns[l];
+    SRCNN_TRY(resolve(ctx, net->grad_w[l], sizeof(float) * cnt[2 * l], &p[2 * l], "grad_w"));
+    SRCNN_TRY(resolve(ctx, net->grad_b[l], sizeof(float) * cnt[2 * l + 1], &p[2 * l + 1], "grad_b"));
+  }
+  // the six accumulators normally are views of ONE flat buffer (gw1 | gb1 | gw2 | gb2 | gw3 |
+  // gb3): then the exchange step of the path is a single all-reduce
+  bool flat = true;
+  size_t total = cnt[0];
+  for (int i = 1; i < 6; i++) {
+    flat = flat && p[i] == p[i - 1] + cnt[i - 1];
+    total += cnt[i];
+  }
+  comm::Api* api = comm::api();
+  if (flat) {
+    SRCNN_NCCL(api->AllReduce(p[0], p[0], total, comm::kNcclFloat, comm::kNcclSum, ctx->nccl_comm,
+                              ctx->stream),
+               "ncclAllReduce(gradients)");
+    return SRCNN_OK;
+  }
+  SRCNN_NCCL(api->GroupStart(), "ncclGroupStart");
+  for (int i = 0; i < 6; i++)
+    SRCNN_NCCL(api->AllReduce(p[i], p[i], cnt[i], comm::kNcclFloat, comm::kNcclSum, ctx->nccl_comm,
+                              ctx->stream),
+               "ncclAllReduce(gradient tensor)");
+  SRCNN_NCCL(api->GroupEnd(), "ncclGroupEnd");
+  return SRCNN_OK;
 }
 
 }  // extern "C"

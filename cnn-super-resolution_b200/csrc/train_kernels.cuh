@@ -654,13 +654,7 @@ template <int MODE, int F, int K, int N>
 inline int launch_grad_stream(srcnn_ctx* ctx, const float* d, const float* in, int ow, int oh,
                               long long P, int* count) {
   using G = GradCfg<MODE, F, K, N>;
-  static bool configured = false;
-  if (!configured) {
-    SRCNN_CUDA(cudaFuncSetAttribute(grad_stream_kernel<MODE, F, K, N>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)G::SMEM_BYTES));
-    configured = true;
-  }
+  SRCNN_TRY(ensure_func_setup(ctx, grad_stream_kernel<MODE, F, K, N>, G::SMEM_BYTES));
   const long long nblocks = (P + G::PB - 1) / G::PB;
   long long ctas = std::min<long long>(2LL * ctx->sm_count, nblocks);
   const long long bpc = (nblocks + ctas - 1) / ctas;
@@ -819,23 +813,12 @@ inline int bwd3_fused(srcnn_ctx* ctx, const float* gt, const float* out3, const 
   if (smem > 96 * 1024) return 0;   // image-sized samples: the per-kernel path handles them
   // one wave of resident CTAs, each walking S / count samples: with more CTAs than fit, the
   // leftover ones run as a second wave at a fraction of the occupancy
-  // (the attribute and the occupancy only depend on the instantiation and the smem size)
-  static size_t cached_smem[2] = {0, 0};
-  static int cached_occ[2] = {0, 0};
-  const int inst = k <= 32 ? 0 : 1;
-  if (cached_smem[inst] != smem) {
-    int q = 0;
-    if (inst == 0) {
-      SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, bwd3_fused_kernel<1>, B3_NT, smem));
-    } else {
-      SRCNN_CUDA(cudaFuncSetAttribute(bwd3_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SRCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, bwd3_fused_kernel<2>, B3_NT, smem));
-    }
-    cached_smem[inst] = smem;
-    cached_occ[inst] = q;
-  }
-  int occ = cached_occ[inst];
+  // (attribute and occupancy are cached per context: they depend on the device)
+  int occ = 0;
+  if (k <= 32)
+    SRCNN_TRY(ensure_func_setup(ctx, bwd3_fused_kernel<1>, smem, B3_NT, &occ));
+  else
+    SRCNN_TRY(ensure_func_setup(ctx, bwd3_fused_kernel<2>, smem, B3_NT, &occ));
   if (occ < 1) occ = 1;
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int count = (int)std::min<long long>(S, (long long)occ * sms);

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
   using fused_pl::elect_one;
   using fused_pl::tmem_ld16_nowait;
   using fused_pl::tmem_ld_wait;
-  using fused_ws::mbar_arrive;
-  using fused_ws::named_bar_sync;
+  using tc::mbar_arrive;
+  using tc::named_bar_sync;
   extern __shared__ __align__(128) float wg_smem[];
   int* sBase = reinterpret_cast<int*>(wg_smem + C::oBase);
   float* sD2 = wg_smem + C::oD2;
@@ -527,16 +527,8 @@ inline int wgrad1_fused_tc(srcnn_ctx* ctx, const float* d2, const float* out1, c
   const long long tiles = (P + Cfg::PX - 1) / Cfg::PX;
   if (tiles > 0x7fffffffLL) return 0;
   if (P > 0x7fffffffLL - Cfg::PX) return 0;
-  static bool configured = false;
-  if (!configured) {
-    SRCNN_CUDA(cudaFuncSetAttribute(wgrad1_fused_tc_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    SRCNN_CUDA(cudaFuncSetAttribute(wgrad1_fused_tc_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  SRCNN_TRY(ensure_func_setup(ctx, wgrad1_fused_tc_kernel<true>, Cfg::SMEM_BYTES));
+  SRCNN_TRY(ensure_func_setup(ctx, wgrad1_fused_tc_kernel<false>, Cfg::SMEM_BYTES));
   const bool staged = ow >= Cfg::MIN_OW && ow + Cfg::F - 1 <= Cfg::SPITCH && oh >= 3;
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int grid = (int)(tiles < sms ? tiles : sms);

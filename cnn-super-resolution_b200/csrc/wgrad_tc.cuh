@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
   using fused_pl::elect_one;
   using fused_pl::tmem_ld16_nowait;
   using fused_pl::tmem_ld_wait;
-  using fused_ws::mbar_arrive;
-  using fused_ws::named_bar_sync;
+  using tc::mbar_arrive;
+  using tc::named_bar_sync;
   extern __shared__ __align__(128) float wg_smem[];
   int* sBase = reinterpret_cast<int*>(wg_smem + C::oBase);
   __shared__ __align__(8) uint64_t full[2], empty[2], done;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(Cfg2::NT, 1) wgrad2_tc_kernel(const float* __r
   using fused_pl::elect_one;
   using fused_pl::tmem_ld16_nowait;
   using fused_pl::tmem_ld_wait;
-  using fused_ws::mbar_arrive;
+  using tc::mbar_arrive;
   extern __shared__ __align__(128) float wg_smem[];
   float* sX = wg_smem + C::oX;
   __shared__ __align__(8) uint64_t full[C::NS], empty[C::NS], done;
@@ -430,12 +430,7 @@ inline int wgrad2_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int
   const long long P = (long long)S * ow * oh;
   const long long tiles = (P + Cfg2::PX - 1) / Cfg2::PX;
   if (tiles > 0x7fffffffLL) return 0;
-  static bool configured = false;
-  if (!configured) {
-    SRCNN_CUDA(cudaFuncSetAttribute(wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg2::SMEM_BYTES));
-    configured = true;
-  }
+  SRCNN_TRY(ensure_func_setup(ctx, wgrad2_tc_kernel, Cfg2::SMEM_BYTES));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
   *count = grid;
@@ -456,12 +451,7 @@ inline int wgrad1_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int
   if (in_elems > 0x7fffffffLL) return 0;   // 32-bit input offsets
   const long long tiles = (P + Cfg::PX - 1) / Cfg::PX;
   if (tiles > 0x7fffffffLL) return 0;
-  static bool configured = false;
-  if (!configured) {
-    SRCNN_CUDA(cudaFuncSetAttribute(wgrad1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  SRCNN_TRY(ensure_func_setup(ctx, wgrad1_tc_kernel, Cfg::SMEM_BYTES));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
   *count = grid;

@@ -260,6 +260,38 @@ int srcnn_update_all(srcnn_ctx* ctx, const srcnn_net* net, unsigned batch_size, 
 int srcnn_validate_chunk(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem gt,
                          int w, int h, int S, srcnn_mem work, srcnn_mem target);
 
+/* The fused kernels cache a packed copy of a network's parameters per context while the six
+ * parameter buffers are context-owned, were never handed out by srcnn_mem_ptr, and no call of
+ * this layer has written them.  A buffer whose raw pointer was obtained with srcnn_mem_ptr is
+ * never cached (anything may write through it).  Call this after writing parameters by any
+ * other route (a kernel of your own on the context stream, a peer copy ...). */
+int srcnn_invalidate_params(srcnn_ctx* ctx);
+
+/* ---------------------------------------------------------------- multi-GPU -------- */
+/* New (the reference is single-device: src/opencl/Context.cpp:52-60).  One context per GPU /
+ * process; the communicator enqueues on the context stream, so collectives order with the
+ * launches around them.  NCCL (libnccl.so.2) is loaded on first use.  Partitioning:
+ * inference = row bands, no collective; training = patches split across ranks, replicated
+ * parameters, ONE sum all-reduce of the gradient accumulators before each
+ * srcnn_update_all(batch_size = GLOBAL sample count); validation = 1-float all-reduce of the
+ * squared error (src/ConfigBasedDataPipeline.cpp:177-187, src/Main_cl.cpp:174-192). */
+#define SRCNN_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands it to the other ranks (file, pipe, launcher ...) */
+int srcnn_comm_unique_id(unsigned char id[SRCNN_COMM_ID_BYTES]);
+/* collective over all ranks: joins this context to the communicator */
+int srcnn_comm_init(srcnn_ctx* ctx, int rank, int world,
+                    const unsigned char id[SRCNN_COMM_ID_BYTES]);
+int srcnn_comm_destroy(srcnn_ctx* ctx);
+/* rank / world of the context (0 / 1 without a communicator) */
+int srcnn_comm_info(srcnn_ctx* ctx, int* rank, int* world);
+/* in-place sum over ranks of `count` floats at buf[offset_floats..]; no-op on one rank */
+int srcnn_allreduce_sum(srcnn_ctx* ctx, srcnn_mem buf, size_t offset_floats, size_t count);
+/* in-place sum over ranks of the six gradient accumulators of `net`: one all-reduce when they
+ * are consecutive views of one flat buffer, a grouped call otherwise */
+int srcnn_allreduce_grads(srcnn_ctx* ctx, const srcnn_net* net);
+/* the first `count` floats of `buf` on rank `root` replace everybody's (parameter sync) */
+int srcnn_broadcast(srcnn_ctx* ctx, srcnn_mem buf, size_t count, int root);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../tc_common.cuh"
+#include "../../cnn-super-resolution_b200/csrc/tc_common.cuh"
 using namespace srcnn::tc;
 
 constexpr int M = 128, N1 = 64, F1 = 9, KS = 6, K1 = KS * 16;   // K in halves

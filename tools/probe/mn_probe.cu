@@ -10,7 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../tc_common.cuh"
+#include "../../cnn-super-resolution_b200/csrc/tc_common.cuh"
 using namespace srcnn::tc;
 constexpr int M = 128, N = 64, K = 64;
 

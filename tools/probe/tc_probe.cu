@@ -14,7 +14,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../tc_common.cuh"
+#include "../../cnn-super-resolution_b200/csrc/tc_common.cuh"
 
 using namespace srcnn::tc;
 

@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
-#include "../tc_common.cuh"
+#include "../../cnn-super-resolution_b200/csrc/tc_common.cuh"
 using namespace srcnn::tc;
 
 template <int X>

@@ -1,19 +1,24 @@
 #!/usr/bin/env python3
-"""bench.py -- SRCNN 9-1-5 (n1=64, n2=32) hot path on B200.
+"""bench.py -- the SRCNN hot path on B200, BASELINE.json's configurations.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workloads c3,c2,c4,c5]
 
-Prints ONE JSON line (rank 0).  Workloads (BASELINE.json):
-  * primary  : INFERENCE of one 4096x4096 luma image (config C3), halo row-sharded across the
-               N ranks (no collective; strong scaling).  A step = one forward pass of the
-               whole image.  metric = input MPix/s = 4096*4096/1e6 / step time.
-  * secondary: TRAINING, one epoch over 4096 synthetic 33x33 patches per rank (config C2,
-               data-parallel, weak scaling): forward + backward + ONE all-reduce of the flat
-               8129-float gradient + momentum/weight-decay update.  Reported under "train".
-`value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer entry
-points (srcnn_infer_rows_host / write+train+read) with H2D and D2H inside the timed region.
-`--impl reference` times the reference's own kernels (oracle/_ref, or the oracle port when
-that was not built) on the host cores, on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  Workloads (BASELINE.json `configs`):
+  * c3 (primary: `metric`/`value`/`e2e`/`roofline`): INFERENCE of one 4096x4096 luma image with
+    the 9-1-5 n1=64 n2=32 network, halo row-sharded across the N ranks (no collective; strong
+    scaling).  A step = one forward pass of the whole image.  MPix/s = input pixels / step time.
+  * c2 (`train`): TRAINING, one epoch over 4096 synthetic 33x33 patches PER RANK (weak scaling):
+    forward + backward in chunks of 2048, ONE all-reduce of the flat 8129-float gradient through
+    the product's own communicator (srcnn_allreduce_grads), momentum + weight-decay update.
+  * c4 (`train_c4`): the 9-5-5 network, 65 536 patches in TOTAL split data-parallel across the
+    ranks (strong scaling), same step.
+  * c5 (`c5`): the 9-1-5 n1=128 n2=64 network on 256 frames of 1920x1080 in TOTAL, frames split
+    across the ranks (strong scaling, no collective).
+`value`s are measured with inputs resident in HBM; every `e2e` goes through the host-buffer
+C-ABI entry (srcnn_infer_rows_host / srcnn_train_chunks_host / srcnn_infer_frames_host) with
+pinned HOST buffers, H2D and D2H inside the timed region.  `--impl reference` times the
+reference's own kernels (oracle/_ref; the oracle port when that was not built) on all host cores.
 """
 import argparse
 import json
@@ -29,22 +34,63 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N1, N2, F1, F2, F3 = 64, 32, 9, 1, 5
 IMG = 4096
 PATCH = 33
-PATCHES_PER_RANK = 4096
-PAD = F1 + F2 + F3 - 3
 MOMENTUM, DECAY = 0.9, 0.001
 LR = np.array([1e-4, 1e-4, 1e-5], np.float32)   # example_config.json:8-10
+C2_PATCHES_PER_RANK = 4096
+C4_PATCHES_TOTAL = 65536
+C5_FRAMES_TOTAL, C5_W, C5_H = 256, 1920, 1080
 
-# algorithmic work (SURVEY 8d / BASELINE.md section 2)
-FWD_FLOP_C3 = 2 * ((IMG - 8) ** 2 * 81 * 64 + (IMG - 8) ** 2 * 64 * 32 + (IMG - 12) ** 2 * 25 * 32)
-FUSED_BYTES_C3 = 4 * (IMG * IMG + (IMG - PAD) ** 2)
-TRAIN_FLOP_PER_PATCH = 23.05e6
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused launch on C3 (ncu --set full,
-# profiles/r1s_fused_hp_ncu_summary.txt): 67.2 MB read (the input, once) + 28.5 MB written back
-# during the launch (the rest of the 66.7 MB output is still dirty in the 126 MB L2 at exit)
-TRAFFIC_NCU_BYTES = 95.7e6
+NETS = {"c3": (64, 32, 9, 1, 5), "c2": (64, 32, 9, 1, 5), "c4": (64, 32, 9, 5, 5),
+        "c5": (128, 64, 9, 1, 5)}
+
+
+def net_pad(cfg):
+    return cfg[2] + cfg[3] + cfg[4] - 3
+
+
+def fwd_flop(cfg, w, h):
+    """Algorithmic forward FLOPs of one w x h sample: each layer's own output extent x 2 f^2 k n
+    (SURVEY 8d)."""
+    n1, n2, f1, f2, f3 = cfg
+    w1, h1 = w - f1 + 1, h - f1 + 1
+    w2, h2 = w1 - f2 + 1, h1 - f2 + 1
+    w3, h3 = w2 - f3 + 1, h2 - f3 + 1
+    return 2.0 * (w1 * h1 * f1 * f1 * n1 + w2 * h2 * f2 * f2 * n1 * n2 + w3 * h3 * f3 * f3 * n2)
+
+
+def train_flop_per_patch(cfg):
+    """forward + deltas + weight gradients of one 33x33 patch (23.05 MFLOP for 9-1-5
+    64/32, 168.9 MFLOP for 9-5-5)."""
+    n1, n2, f1, f2, f3 = cfg
+    w1 = PATCH - f1 + 1
+    w2 = w1 - f2 + 1
+    w3 = w2 - f3 + 1
+    fwd = fwd_flop(cfg, PATCH, PATCH)
+    d2 = 2.0 * w2 * w2 * n2 * f3 * f3            # deltas 2 <- 3
+    d1 = 2.0 * w1 * w1 * n1 * f2 * f2 * n2       # deltas 1 <- 2
+    gw = 2.0 * (w3 * w3 * f3 * f3 * n2 + w2 * w2 * f2 * f2 * n1 * n2 + w1 * w1 * f1 * f1 * n1)
+    return fwd + d2 + d1 + gw
+
+
+def train_bytes_per_patch(cfg):
+    """Algorithmic HBM bytes of one patch through a training chunk, per kernel of the chunk
+    (every tensor the backward needs is materialised once and read by each consumer)."""
+    n1, n2, f1, f2, f3 = cfg
+    w1 = PATCH - f1 + 1
+    w2 = w1 - f2 + 1
+    w3 = w2 - f3 + 1
+    px = 4 * PATCH * PATCH
+    o1, o2, o3 = 4 * w1 * w1 * n1, 4 * w2 * w2 * n2, 4 * w3 * w3
+    if f2 == 1:   # 9-1-5: d1 lives inside the layer-1 gradient kernel
+        return {"forward_fused": px + o1 + o2 + o3,
+                "bwd3_fused (d3, d2, gW3)": px + o3 + o2 + o3 + o2,
+                "wgrad1_fused (d1 + gW1)": o2 + o1 + px,
+                "wgrad2 (gW2)": o2 + o1}
+    return {"forward l1": px + o1, "forward l2": o1 + o2, "forward l3": o2 + o3,
+            "bwd3_fused (d3, d2, gW3)": px + o3 + o2 + o3 + o2,
+            "deltas l1": o2 + o1 + o1, "gW2": o2 + o1, "gW1": o1 + px}
 
 
 def peaks():
@@ -53,6 +99,18 @@ def peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
     return 6650.0, 1590.0, "fallback"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    ncu --set full capture (profiles/traffic.json, written by tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel)
+    if not d:
+        return None, None
+    return d.get("dram_bytes"), d.get("source")
 
 
 class ClockSampler:
@@ -106,84 +164,132 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synthetic_inputs(seed=1234):
-    from helpers import luma_image, make_params, patches
-    rng = np.random.default_rng(seed)
-    params = make_params(rng, N1, N2, F1, F2, F3)
-    return rng, params, luma_image, patches
+def synthetic_params(cfg, seed=1234):
+    from helpers import make_params
+    rng = np.random.default_rng(seed + cfg[0] + 7 * cfg[3])
+    return make_params(rng, *cfg)
+
+
+def frames_like(rng, n, h, w):
+    """n distinct synthetic frames: a few generated ones, rolled (cheap on the host)."""
+    from helpers import luma_image
+    base = [luma_image(rng, h, w) for _ in range(min(n, 4))]
+    out = np.empty((n, h, w), np.float32)
+    for i in range(n):
+        out[i] = np.roll(base[i % len(base)], 17 * (i // len(base)), axis=1)
+    return out
+
+
+def workload_config(n, wl):
+    return {"workload": "C3: SRCNN 9-1-5 n1=64 n2=32 inference, one 4096x4096 luma image, halo "
+                        "row bands over %d GPU(s)" % n,
+            "secondary": {"train": "C2: 9-1-5 training, 4096 patches 33x33 PER GPU (weak), chunks "
+                                   "of 2048, momentum + weight decay, one all-reduce of 8129 floats",
+                          "train_c4": "C4: 9-5-5 training, 65536 patches in total split over the "
+                                      "GPUs (strong), one all-reduce of 57281 floats",
+                          "c5": "C5: 9-1-5 n1=128 n2=64 inference of 256 frames 1920x1080 in total, "
+                                "frames split over the GPUs (strong)"},
+            "workloads_run": wl, "net": "9-1-5 n1=64 n2=32", "image": [IMG, IMG],
+            "patch": [PATCH, PATCH], "halo_rows": 12,
+            "parallelism": "inference: row bands / frames, no collective; training: dp%d, one "
+                           "all-reduce per update (NCCL communicator owned by the C-ABI)" % n,
+            "l2": "inference rotates 4 input/output buffer pairs (>= 4x the band size) so no step "
+                  "finds its input in the 126 MB L2; training streams > 1 GB of activations per "
+                  "epoch; C5 walks >= 265 MB of frames per step"}
 
 
 # ======================================================================= reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path on the host cores."""
-    if rank != 0:
-        return
+def reference_numbers(args, wl):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref)."""
+    from helpers import luma_image, patches
     from oracle.loader import NetState, Oracle, have
     kind = "reference" if have("reference") else "port"
     orc = Oracle(kind)
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     orc.set_num_threads(len(os.sched_getaffinity(0)))
     cores = orc.num_threads()
-    rng, params, luma_image, patches = synthetic_inputs()
-    net = NetState(N1, N2, F1, F2, F3, params)
-    # bounded sample of C3: a band of `rows` output rows of the 4096-wide image
-    rows = args.ref_rows
-    band = luma_image(rng, rows + PAD, IMG)
-    t = []
-    for i in range(args.warmup + args.steps):
+    rng = np.random.default_rng(1234)
+    out = {"kind": kind, "cores": cores}
+    if "c3" in wl:
+        cfg = NETS["c3"]
+        pad = net_pad(cfg)
+        net = NetState(*cfg, synthetic_params(cfg))
+        rows = min(args.ref_rows, IMG - pad)
+        band = luma_image(rng, rows + pad, IMG)
+        t = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            orc.net_forward(net, band, IMG, rows + pad, 1)
+            t.append(time.perf_counter() - t0)
+        sec = float(np.mean(t[args.warmup:]))
+        frac = rows / float(IMG - pad)
+        out["c3"] = {"mpix": IMG * IMG * frac / 1e6 / sec, "sec_per_step": sec, "frac": frac,
+                     "sample": "%d of %d output rows of the 4096-wide image per step (%.1f%% of "
+                               "C3)%s" % (rows, IMG - pad, 100 * frac,
+                                          "" if frac == 1.0 else ", scaled linearly")}
+    for key, npat in (("c2", args.ref_patches), ("c4", max(64, args.ref_patches // 4))):
+        if key in wl:
+            cfg = NETS[key]
+            net = NetState(*cfg, synthetic_params(cfg))
+            x, gt = patches(rng, npat, PATCH, PATCH)
+            tt = []
+            for i in range(2):
+                t0 = time.perf_counter()
+                orc.net_train_epoch(net, x, gt, PATCH, PATCH, npat, MOMENTUM, DECAY, LR)
+                tt.append(time.perf_counter() - t0)
+            out[key] = {"patches_per_s": npat / min(tt), "sample": "%d patches, 1 epoch, best of 2" % npat}
+    if "c5" in wl:
+        cfg = NETS["c5"]
+        net = NetState(*cfg, synthetic_params(cfg))
+        rows = 128
+        band = luma_image(rng, rows + 12, C5_W)
+        orc.net_forward(net, band, C5_W, rows + 12, 1)
         t0 = time.perf_counter()
-        orc.net_forward(net, band, IMG, rows + PAD, 1)
-        t.append(time.perf_counter() - t0)
-    t = t[args.warmup:]
-    sec = float(np.mean(t))
-    frac = rows / float(IMG - PAD)
-    mpix = IMG * IMG * frac / 1e6 / sec
-    # training sample: `ref_patches` patches of C2, one epoch incl. the update
-    x, gt = patches(rng, args.ref_patches, PATCH, PATCH)
-    tt = []
-    for i in range(2):
-        t0 = time.perf_counter()
-        orc.net_train_epoch(net, x, gt, PATCH, PATCH, args.ref_patches, MOMENTUM, DECAY, LR)
-        tt.append(time.perf_counter() - t0)
-    pps = args.ref_patches / min(tt)
-    sample = ("inference: %d of %d output rows of the 4096-wide image per step (%.1f%% of C3), "
-              "scaled linearly; train: %d of 4096 patches" % (rows, IMG - PAD, 100 * frac,
-                                                              args.ref_patches))
+        orc.net_forward(net, band, C5_W, rows + 12, 1)
+        sec = time.perf_counter() - t0
+        frac = rows / float(C5_H - 12)
+        out["c5"] = {"mpix": C5_W * C5_H * frac / 1e6 / sec,
+                     "sample": "%d of %d output rows of one 1920-wide frame, scaled linearly" % (rows, C5_H - 12)}
+    return out
+
+
+def run_reference(args, rank, world, wl):
+    if rank != 0:
+        return
+    r = reference_numbers(args, wl)
+    c3 = r.get("c3", {"mpix": None, "sec_per_step": 0.0, "frac": 1.0, "sample": "not run"})
+    mpix = c3["mpix"]
     line = {
         "impl": "reference", "metric": "srcnn_915_inference_mpix_per_s", "value": mpix,
         "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec / frac, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * c3["sec_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": mpix, "unit": "MPix/s", "cores": cores, "kind": kind,
-                         "sample": sample},
+        "config": workload_config(args.gpus, wl),
+        "cpu_baseline": {"value": mpix, "unit": "MPix/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": c3["sample"]},
         "e2e": {"value": mpix, "unit": "MPix/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "train": {"metric": "srcnn_915_train_patches_per_s", "value": pps, "unit": "patches/s"},
         "gpu_launches": 0,
     }
+    if "c2" in r:
+        line["train"] = {"metric": "srcnn_915_train_patches_per_s", "value": r["c2"]["patches_per_s"],
+                         "unit": "patches/s", "sample": r["c2"]["sample"]}
+    if "c4" in r:
+        line["train_c4"] = {"metric": "srcnn_955_train_patches_per_s", "value": r["c4"]["patches_per_s"],
+                            "unit": "patches/s", "sample": r["c4"]["sample"]}
+    if "c5" in r:
+        line["c5"] = {"metric": "srcnn_915_wide_frames_mpix_per_s", "value": r["c5"]["mpix"],
+                      "unit": "MPix/s", "sample": r["c5"]["sample"]}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
-    return {"workload": "C3: SRCNN 9-1-5 n1=64 n2=32 inference, one 4096x4096 luma image, "
-                        "halo row bands over %d GPU(s); secondary C2: training, 4096 patches "
-                        "33x33 per GPU, momentum+weight decay" % n,
-            "net": "9-1-5 n1=64 n2=32", "image": [IMG, IMG], "patch": [PATCH, PATCH],
-            "patches_per_gpu": PATCHES_PER_RANK, "halo_rows": PAD,
-            "parallelism": "inference: row bands, no collective; training: dp%d, one all-reduce "
-                           "of 8129 floats per update" % n,
-            "l2": "inference rotates 4 input/output buffer pairs (>= 4x the band size) so no "
-                  "step finds its input in the 126 MB L2; training streams > 1 GB of "
-                  "activations per epoch"}
-
-
 # ======================================================================= our arm
-def run_ours(args, rank, world, local_rank):
+def run_ours(args, rank, world, local_rank, wl):
     import torch
     import torch.distributed as dist
 
     import _pkg
+    from helpers import luma_image, patches
     pkg = _pkg.load()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -192,7 +298,6 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     hbm_peak, bf16_peak, peak_kind = peaks()
-    rng, params, luma_image, patches = synthetic_inputs()
 
     def barrier():
         if world > 1:
@@ -206,45 +311,16 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    res = {}
     with torch.cuda.stream(stream):
         ctx = pkg.Context(local_rank, stream=stream.cuda_stream)
-        grad = torch.zeros(sum(f * f * k * n + n for (k, n, f) in
-                               [(1, N1, F1), (N1, N2, F2), (N2, 1, F3)]),
-                           device="cuda", dtype=torch.float32)
-        gh = ctx.wrap(grad.data_ptr(), grad.numel() * 4)
-        net = pkg.Net(ctx, N1, N2, F1, F2, F3, params, grad_flat=gh)
-
-        # ---------------------------------------------------------------- inference
-        h3 = IMG - PAD
-        w3 = IMG - PAD
-        r0, r1 = pkg.row_bands(h3, world)[rank]
-        band_h = r1 - r0 + PAD
-        R = 4
-        img = pkg.PinnedBuffer((IMG, IMG))
-        img.array[:] = luma_image(rng, IMG, IMG)
-        out_host = pkg.PinnedBuffer((r1 - r0, w3))
-        ins, outs = [], []
-        for i in range(R):
-            m = ctx.alloc(4 * band_h * IMG)
-            ctx.write(m, np.roll(img.array[r0:r0 + band_h], i, axis=1))
-            ins.append(m)
-            outs.append(ctx.alloc(4 * (r1 - r0) * w3))
-        fused = net.fused_supported()
-        (w1, h1), (w2, h2), _ = net.out_dims(IMG, band_h)
-        s1 = s2 = pkg.NULL_MEM
-        if not fused:   # three-launch path needs the n1/n2-channel maps in HBM
-            s1, s2 = ctx.alloc(4 * w1 * h1 * N1), ctx.alloc(4 * w2 * h2 * N2)
-
-        def infer_step(i):
-            net.forward_fused(ins[i % R], outs[i % R], IMG, band_h, 1, s1, s2)
-
-        def infer_e2e_step(i):
-            if fused:
-                net.infer_rows_host(img.array, IMG, IMG, r0, r1, out_host.array)
-            else:
-                ctx.write(ins[i % R], img.array[r0:r0 + band_h], block=False)
-                net.forward_fused(ins[i % R], outs[i % R], IMG, band_h, 1, s1, s2)
-                ctx.L.srcnn_read(ctx.h, outs[i % R], 0, out_host.nbytes, out_host.ptr, 1)
+        if world > 1:
+            # the product's own communicator: rank 0 creates the id, torch only carries it over
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.tensor(list(pkg.Context.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            ctx.comm_init(rank, world, bytes(uid.cpu().tolist()))
 
         def timed(step_fn, steps, warmup):
             for i in range(warmup):
@@ -263,165 +339,350 @@ def run_ours(args, rank, world, local_rank):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        inf_ms, inf_launches = timed(infer_step, args.steps, args.warmup)
-        e2e_ms, _ = timed(infer_e2e_step, max(2, args.steps // 2), 2)
 
-        # ---------------------------------------------------------------- training
-        n_loc = PATCHES_PER_RANK
-        px = pkg.PinnedBuffer((n_loc, PATCH, PATCH))
-        pg = pkg.PinnedBuffer((n_loc, PATCH, PATCH))
-        rng_r = np.random.default_rng(99 + rank)
-        px.array[:], pg.array[:] = patches(rng_r, n_loc, PATCH, PATCH)
-        chunk = min(args.chunk, n_loc)
-        d_in, d_gt = ctx.alloc(px.nbytes), ctx.alloc(pg.nbytes)
-        ctx.write(d_in, px.array)
-        ctx.write(d_gt, pg.array)
-        work = ctx.alloc(net.train_workspace_bytes(PATCH, PATCH, chunk))
-        bytes_per = 4 * PATCH * PATCH
-        chunks = []
-        for i in range(0, n_loc, chunk):
-            S = min(chunk, n_loc - i)
-            base_i, base_g = ctx.mem_ptr(d_in), ctx.mem_ptr(d_gt)
-            chunks.append((ctx.wrap(base_i + i * bytes_per, S * bytes_per),
-                           ctx.wrap(base_g + i * bytes_per, S * bytes_per), S))
-        params_host = pkg.PinnedBuffer((grad.numel(),))
+        # ---------------------------------------------------------------- PCIe reference rates
+        pc_n = 64 << 20
+        pc_h, pc_d = pkg.PinnedBuffer((pc_n // 4,)), ctx.alloc(pc_n)
 
-        def train_step(i):
-            for (ci, cg, S) in chunks:
-                net.train_chunk(ci, cg, PATCH, PATCH, S, work)
-            if world > 1:
-                dist.all_reduce(grad)       # the ONE exchange step of the path (sum)
-            net.update_all(n_loc * world, MOMENTUM, DECAY, LR)
-
-        def train_e2e_step(i):
-            # HOST samples in (pinned), upload of chunk i+1 overlapping the training of chunk i
-            net.train_chunks_host(px.array, pg.array, PATCH, PATCH, chunk, work)
-            if world > 1:
-                dist.all_reduce(grad)
-            net.update_all(n_loc * world, MOMENTUM, DECAY, LR)
-            off = 0
-            for l in range(3):     # read the updated parameters back (the step's result)
-                for hnd, cnt in ((net.c.w[l], net.sizes[l][0]), (net.c.b[l], net.sizes[l][1])):
-                    ctx.L.srcnn_read(ctx.h, hnd, 0, 4 * cnt, params_host.ptr + 4 * off, 0)
-                    off += cnt
+        def copy_rate(fn):
+            fn()
             ctx.block()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(4):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return 4 * pc_n / (e0.elapsed_time(e1) / 1e3) / 1e9
 
-        tr_steps = max(2, args.steps // 2)
-        tr_ms, tr_launches = timed(train_step, tr_steps, args.warmup)
-        tr_e2e_ms, _ = timed(train_e2e_step, tr_steps, 2)
+        h2d_gbs = copy_rate(lambda: ctx.L.srcnn_write(ctx.h, pc_d, 0, pc_n, pc_h.ptr, 0))
+        d2h_gbs = copy_rate(lambda: ctx.L.srcnn_read(ctx.h, pc_d, 0, pc_n, pc_h.ptr, 0))
+        ctx.release(pc_d)
+        pc_h.free()
+
+        def pcie_block(h2d, d2h, ms):
+            floor = max(h2d / h2d_gbs, d2h / d2h_gbs) / 1e6    # ms, both directions overlapped
+            return {"h2d_gbs_measured": h2d_gbs, "d2h_gbs_measured": d2h_gbs,
+                    "floor_ms": floor, "frac_of_floor": floor / ms if ms else None,
+                    "note": "floor = max(h2d bytes / measured pinned H2D rate, d2h bytes / D2H rate)"
+                            " of this rank: a perfectly overlapped pipeline; 64 MiB srcnn_write / "
+                            "srcnn_read copies timed alone in this run"}
+
+        # ---------------------------------------------------------------- C3 inference (primary)
+        if "c3" in wl:
+            cfg = NETS["c3"]
+            pad = net_pad(cfg)
+            rng = np.random.default_rng(1234)
+            net = pkg.Net(ctx, *cfg, synthetic_params(cfg))
+            h3 = w3 = IMG - pad
+            r0, r1 = pkg.row_bands(h3, world)[rank]
+            band_h = r1 - r0 + pad
+            R = 4
+            img = pkg.PinnedBuffer((IMG, IMG))
+            img.array[:] = luma_image(rng, IMG, IMG)
+            out_host = pkg.PinnedBuffer((r1 - r0, w3))
+            ins, outs = [], []
+            for i in range(R):
+                m = ctx.alloc(4 * band_h * IMG)
+                ctx.write(m, np.roll(img.array[r0:r0 + band_h], i, axis=1))
+                ins.append(m)
+                outs.append(ctx.alloc(4 * (r1 - r0) * w3))
+            assert net.fused_supported()
+
+            def infer_step(i):
+                net.forward_fused(ins[i % R], outs[i % R], IMG, band_h, 1)
+
+            def infer_e2e_step(i):
+                net.infer_rows_host(img.array, IMG, IMG, r0, r1, out_host.array)
+
+            inf_ms, inf_launches = timed(infer_step, args.steps, args.warmup)
+            e2e_ms, _ = timed(infer_e2e_step, max(2, args.steps // 2), 3)
+            res["c3"] = dict(ms=inf_ms, launches=inf_launches, e2e_ms=e2e_ms, rows=(r0, r1),
+                             band_h=band_h, h2d=4 * band_h * IMG, d2h=4 * (r1 - r0) * w3)
+            for m in ins + outs:
+                ctx.release(m)
+            img.free()
+            out_host.free()
+
+        # ---------------------------------------------------------------- training (C2 weak, C4 strong)
+        def train_workload(key, n_loc, n_global):
+            cfg = NETS[key]
+            grad = torch.zeros(sum(f * f * k * n + n for (k, n, f) in
+                                   [(1, cfg[0], cfg[2]), (cfg[0], cfg[1], cfg[3]), (cfg[1], 1, cfg[4])]),
+                               device="cuda", dtype=torch.float32)
+            gh = ctx.wrap(grad.data_ptr(), grad.numel() * 4)
+            net = pkg.Net(ctx, *cfg, synthetic_params(cfg), grad_flat=gh)
+            px = pkg.PinnedBuffer((n_loc, PATCH, PATCH))
+            pg = pkg.PinnedBuffer((n_loc, PATCH, PATCH))
+            rng_r = np.random.default_rng(99 + rank)
+            px.array[:], pg.array[:] = patches(rng_r, n_loc, PATCH, PATCH)
+            chunk = min(args.chunk, n_loc)
+            d_in, d_gt = ctx.alloc(px.nbytes), ctx.alloc(pg.nbytes)
+            ctx.write(d_in, px.array)
+            ctx.write(d_gt, pg.array)
+            work = ctx.alloc(net.train_workspace_bytes(PATCH, PATCH, chunk))
+            bytes_per = 4 * PATCH * PATCH
+            base_i, base_g = ctx.mem_ptr(d_in), ctx.mem_ptr(d_gt)
+            chunks = []
+            for i in range(0, n_loc, chunk):
+                S = min(chunk, n_loc - i)
+                chunks.append((ctx.wrap(base_i + i * bytes_per, S * bytes_per),
+                               ctx.wrap(base_g + i * bytes_per, S * bytes_per), S))
+            params_host = pkg.PinnedBuffer((grad.numel(),))
+
+            def train_step(i):
+                for (ci, cg, S) in chunks:
+                    net.train_chunk(ci, cg, PATCH, PATCH, S, work)
+                net.allreduce_grads()       # the ONE exchange step of the path (no-op on 1 rank)
+                net.update_all(n_global, MOMENTUM, DECAY, LR)
+
+            def train_e2e_step(i):
+                # HOST samples in (pinned), upload of chunk i+1 overlapping the training of chunk i
+                net.train_chunks_host(px.array, pg.array, PATCH, PATCH, chunk, work)
+                net.allreduce_grads()
+                net.update_all(n_global, MOMENTUM, DECAY, LR)
+                off = 0
+                for l in range(3):     # read the updated parameters back (the step's result)
+                    for hnd, cnt in ((net.c.w[l], net.sizes[l][0]), (net.c.b[l], net.sizes[l][1])):
+                        ctx.L.srcnn_read(ctx.h, hnd, 0, 4 * cnt, params_host.ptr + 4 * off, 0)
+                        off += cnt
+                ctx.block()
+
+            steps = max(2, args.steps // 2) if key == "c2" else max(2, args.steps // 10)
+            ms, launches = timed(train_step, steps, args.warmup)
+            e2e_ms, _ = timed(train_e2e_step, steps, 3)
+            # per-kernel-id device time of ONE epoch through a profiling context (not the timed run)
+            kern = None
+            if rank == 0:
+                pctx = pkg.Context(local_rank, profile=True)
+                pnet = pkg.Net(pctx, *cfg, synthetic_params(cfg))
+                pS = chunks[0][2]
+                pin_, pgt_ = pctx.upload(px.array[:pS]), pctx.upload(pg.array[:pS])
+                pwork = pctx.alloc(pnet.train_workspace_bytes(PATCH, PATCH, pS))
+                pnet.train_chunk(pin_, pgt_, PATCH, PATCH, pS, pwork)     # warm-up
+                before = pctx.profile()
+                pnet.train_chunk(pin_, pgt_, PATCH, PATCH, pS, pwork)
+                after = pctx.profile()
+                kern = {k: {"ms": (after[k][0] - before[k][0]) / 1e6,
+                            "launches": after[k][1] - before[k][1]}
+                        for k in after if after[k][1] != before[k][1]}
+                kern["_chunk_patches"] = pS
+                pctx.close()
+            out = dict(ms=ms, launches=launches, e2e_ms=e2e_ms, steps=steps, chunk=chunk,
+                       n_loc=n_loc, n_global=n_global, grad_floats=grad.numel(), kernels=kern,
+                       h2d=2 * n_loc * bytes_per, d2h=4 * grad.numel())
+            for m in (d_in, d_gt, work):
+                ctx.release(m)
+            px.free()
+            pg.free()
+            params_host.free()
+            return out
+
+        if "c2" in wl:
+            res["c2"] = train_workload("c2", C2_PATCHES_PER_RANK, C2_PATCHES_PER_RANK * world)
+        if "c4" in wl:
+            res["c4"] = train_workload("c4", C4_PATCHES_TOTAL // world, C4_PATCHES_TOTAL)
+
+        # ---------------------------------------------------------------- C5 frames
+        if "c5" in wl:
+            cfg = NETS["c5"]
+            pad = net_pad(cfg)
+            net = pkg.Net(ctx, *cfg, synthetic_params(cfg))
+            n_loc = C5_FRAMES_TOTAL // world
+            w3, h3 = C5_W - pad, C5_H - pad
+            rng = np.random.default_rng(77 + rank)
+            fin = pkg.PinnedBuffer((n_loc, C5_H, C5_W))
+            fin.array[:] = frames_like(rng, n_loc, C5_H, C5_W)
+            fout = pkg.PinnedBuffer((n_loc, h3, w3))
+            G = 4
+            d_in = ctx.alloc(fin.nbytes)
+            ctx.write(d_in, fin.array)
+            d_out = ctx.alloc(fout.nbytes)
+            bi, bo = ctx.mem_ptr(d_in), ctx.mem_ptr(d_out)
+            groups = []
+            for f0 in range(0, n_loc, G):
+                S = min(G, n_loc - f0)
+                groups.append((ctx.wrap(bi + 4 * f0 * C5_W * C5_H, 4 * S * C5_W * C5_H),
+                               ctx.wrap(bo + 4 * f0 * w3 * h3, 4 * S * w3 * h3), S))
+
+            def frames_step(i):
+                for gi, go, S in groups:
+                    net.forward_fused(gi, go, C5_W, C5_H, S)
+
+            def frames_e2e_step(i):
+                net.infer_frames_host(fin.array, C5_W, C5_H, fout.array)
+
+            steps = max(2, args.steps // 10)
+            ms, launches = timed(frames_step, steps, args.warmup)
+            e2e_ms, _ = timed(frames_e2e_step, steps, 3)
+            res["c5"] = dict(ms=ms, launches=launches, e2e_ms=e2e_ms, steps=steps, n_loc=n_loc,
+                             h2d=fin.nbytes, d2h=fout.nbytes)
+            ctx.release(d_in)
+            ctx.release(d_out)
+            fin.free()
+            fout.free()
+
         clocks = sampler.stop() if rank == 0 else None
         barrier()
+        if world > 1:
+            ctx.comm_destroy()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    mpix = IMG * IMG / 1e6 / (inf_ms / 1e3)
-    e2e_mpix = IMG * IMG / 1e6 / (e2e_ms / 1e3)
-    pps = n_loc * world / (tr_ms / 1e3)
-    e2e_pps = n_loc * world / (tr_e2e_ms / 1e3)
-    # roofline of the dominant kernel of the primary workload.  One rank's launch processes
-    # 1/world of the image; per-launch duration = inf_ms (one fused launch per step) when the
-    # fused kernel runs, else the step is three launches and the figure is for the whole step.
-    frac_img = (r1 - r0) / float(h3)
-    alg_bytes = FUSED_BYTES_C3 * frac_img
-    alg_flop = FWD_FLOP_C3 * frac_img
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_clock * 1e6 / 1e12
-    achieved_gbs = alg_bytes / (inf_ms / 1e3) / 1e9
-    achieved_tf = alg_flop / (inf_ms / 1e3) / 1e12
-    impl = os.environ.get("SRCNN_FUSED_IMPL", "hp")
-    use_tc = fused and impl != "simt"
-    # Dominant kernel of the primary workload = the fused forward launch (its duration is the
-    # step time measured above with CUDA events, minus two ~3 us helper launches).  It moves
-    # 8 B/pixel, so it is compute-bound: all three layers run on the tensor cores (layer 3 as a
-    # tap GEMM + 25-term gather) with error-compensated split operands, because the 1e-4
-    # tolerance rules out plain 16/19-bit inputs: every FP32 product costs THREE tensor-core
-    # products -- FP16 halves at the bf16 rate (default kernel), or TF32 at half that rate.
-    if use_tc:
-        split = 6.0 if impl in ("pl", "ws", "tc") else 3.0
-        roofline = {
-            "kernel": ("forward_fused_hp_kernel (tcgen05 kind::f16, FP16-split operands, all "
-                       "three layers)" if split == 3.0 else
-                       "forward_fused_%s_kernel (tcgen05 3xTF32, all three layers)" % impl),
-            "bound": "tensor", "achieved": achieved_tf, "peak": bf16_peak, "unit": "TFLOP/s",
-            "frac": achieved_tf / bf16_peak, "traffic": TRAFFIC_NCU_BYTES * frac_img,
-            "peak_kind": peak_kind + " dense bf16 (MEASURED_PEAKS.json)",
-            "algorithmic_flop_per_launch": alg_flop,
-            "precision_ceiling_tflops": bf16_peak / split,
-            "frac_of_precision_ceiling": achieved_tf / (bf16_peak / split),
-            "note": "algorithmic FP32 FLOPs / launch time against the measured bf16 peak; the "
-                    "split-operand scheme the tolerance requires issues 3 tensor-core products "
-                    "per FP32 product (at the fp16/bf16 rate for the FP16-split kernel, at half "
-                    "of it for 3xTF32), so peak/%d is the ceiling at this precision" % split,
-            "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": hbm_peak,
-                    "frac": achieved_gbs / hbm_peak,
-                    "algorithmic_bytes_per_launch": alg_bytes},
-        }
-    else:
-        roofline = {
-            "kernel": "forward_fused_kernel (FP32 SIMT)" if fused else "forward x3 (unfused)",
-            "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-            "note": "fused inference moves only input+output luma (8 B/px): compute-bound, "
-                    "see fp32",
-            "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,
-                     "frac": achieved_tf / fp32_peak,
-                     "peak_kind": "148 SM x 128 lanes x 2 x median SM clock under load"},
-        }
-    line = {
-        "metric": "srcnn_915_inference_mpix_per_s", "value": mpix, "unit": "MPix/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": inf_ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e_mpix, "unit": "MPix/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 4 * band_h * IMG, "d2h_bytes_per_step": 4 * (r1 - r0) * w3},
-        "gpu_launches": int(inf_launches),
-        "roofline": roofline,
-        "clocks": clocks,
-        "train": {"metric": "srcnn_915_train_patches_per_s", "value": pps, "unit": "patches/s",
-                  "ms_per_step": tr_ms, "steps": tr_steps, "scaling": "weak",
-                  "patches_per_step": n_loc * world, "chunk": chunk,
-                  "gpu_launches": int(tr_launches),
-                  "achieved_tflops": TRAIN_FLOP_PER_PATCH * pps / 1e12,
-                  "e2e": {"value": e2e_pps, "unit": "patches/s", "ms_per_step": tr_e2e_ms,
-                          "h2d_bytes_per_step": 2 * n_loc * bytes_per,
-                          "d2h_bytes_per_step": 4 * grad.numel()}},
-    }
+    line = {"metric": "srcnn_915_inference_mpix_per_s", "value": None, "unit": "MPix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world, wl)}
+
+    if "c3" in res:
+        c = res["c3"]
+        cfg = NETS["c3"]
+        pad = net_pad(cfg)
+        r0, r1 = c["rows"]
+        mpix = IMG * IMG / 1e6 / (c["ms"] / 1e3)
+        e2e_mpix = IMG * IMG / 1e6 / (c["e2e_ms"] / 1e3)
+        # roofline of the dominant kernel of the primary workload: one rank's launch processes
+        # 1/world of the image; per-launch duration = the step time (one fused launch + a ~3 us
+        # gated fallback launch per step, CUDA events on the launching stream)
+        frac_img = (r1 - r0) / float(IMG - pad)
+        alg_bytes = 4.0 * (IMG * IMG + (IMG - pad) ** 2) * frac_img
+        alg_flop = fwd_flop(cfg, IMG, IMG) * frac_img
+        achieved_gbs = alg_bytes / (c["ms"] / 1e3) / 1e9
+        achieved_tf = alg_flop / (c["ms"] / 1e3) / 1e12
+        impl = os.environ.get("SRCNN_FUSED_IMPL", "hp")
+        split = 6.0 if impl == "pl" else 3.0
+        traffic, traffic_src = ncu_traffic("forward_fused_hp_kernel<0>")
+        if impl == "simt":
+            roofline = {"kernel": "forward_fused_kernel (FP32 SIMT)", "bound": "hbm",
+                        "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                        "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak,
+                                 "frac": achieved_tf / fp32_peak}}
+        else:
+            roofline = {
+                "kernel": ("forward_fused_hp_kernel (tcgen05 kind::f16, FP16-split operands, all "
+                           "three layers)" if split == 3.0 else
+                           "forward_fused_pl_kernel (tcgen05 3xTF32, all three layers)"),
+                "bound": "tensor", "achieved": achieved_tf, "peak": bf16_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / bf16_peak,
+                "traffic": traffic * frac_img if traffic else None, "traffic_source": traffic_src,
+                "peak_kind": peak_kind + " dense bf16 (MEASURED_PEAKS.json)",
+                "algorithmic_flop_per_launch": alg_flop,
+                "precision_ceiling_tflops": bf16_peak / split,
+                "frac_of_precision_ceiling": achieved_tf / (bf16_peak / split),
+                "note": "algorithmic FP32 FLOPs / launch time against the measured bf16 peak; the "
+                        "split-operand scheme the 1e-4 tolerance requires issues 3 tensor-core "
+                        "products per FP32 product, so peak/%d is the ceiling at this precision" % split,
+                "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": hbm_peak,
+                        "frac": achieved_gbs / hbm_peak,
+                        "algorithmic_bytes_per_launch": alg_bytes}}
+        line.update({"value": mpix, "ms_per_step": c["ms"], "gpu_launches": int(c["launches"]),
+                     "roofline": roofline,
+                     "e2e": {"value": e2e_mpix, "unit": "MPix/s", "ms_per_step": c["e2e_ms"],
+                             "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"],
+                             "pcie": pcie_block(c["h2d"], c["d2h"], c["e2e_ms"])}})
+    line["clocks"] = clocks
+
+    for key, name, metric in (("c2", "train", "srcnn_915_train_patches_per_s"),
+                              ("c4", "train_c4", "srcnn_955_train_patches_per_s")):
+        if key not in res:
+            continue
+        t = res[key]
+        cfg = NETS[key]
+        pps = t["n_global"] / (t["ms"] / 1e3)
+        e2e_pps = t["n_global"] / (t["e2e_ms"] / 1e3)
+        bpp = train_bytes_per_patch(cfg)
+        total_bpp = float(sum(bpp.values()))
+        gbs = total_bpp * t["n_loc"] / (t["ms"] / 1e3) / 1e9        # this rank's HBM stream
+        flop = train_flop_per_patch(cfg)
+        tf = flop * pps / world / 1e12
+        tensor_frac = tf / (bf16_peak / 3.0)
+        block = {"metric": metric, "value": pps, "unit": "patches/s", "ms_per_step": t["ms"],
+                 "steps": t["steps"], "scaling": "weak" if key == "c2" else "strong",
+                 "patches_per_step": t["n_global"], "patches_per_gpu": t["n_loc"],
+                 "chunk": t["chunk"], "gpu_launches": int(t["launches"]),
+                 "allreduce_floats": t["grad_floats"],
+                 "roofline": {
+                     "bound": "hbm" if key == "c2" else "tensor",
+                     "achieved": gbs if key == "c2" else tf,
+                     "peak": hbm_peak if key == "c2" else bf16_peak / 3.0,
+                     "unit": "GB/s" if key == "c2" else "TFLOP/s",
+                     "frac": gbs / hbm_peak if key == "c2" else tensor_frac,
+                     "algorithmic_bytes_per_patch": total_bpp,
+                     "algorithmic_bytes_per_patch_by_kernel": bpp,
+                     "algorithmic_flop_per_patch": flop,
+                     "hbm_gbs_per_gpu": gbs, "hbm_frac": gbs / hbm_peak,
+                     "tflops_per_gpu": tf, "tensor_frac_of_split_ceiling": tensor_frac,
+                     "note": ("whole-step figure per GPU: every activation / delta tensor the "
+                              "backward needs written once and read once per consumer kernel, / "
+                              "step time, against the measured HBM peak" if key == "c2" else
+                              "whole-step figure per GPU: algorithmic FP32 FLOPs / step time against "
+                              "bf16 peak / 3 (split operands); the 5x5 layer-2 contractions are "
+                              "87% of the FLOPs")},
+                 "e2e": {"value": e2e_pps, "unit": "patches/s", "ms_per_step": t["e2e_ms"],
+                         "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
+                         "pcie": pcie_block(t["h2d"], t["d2h"], t["e2e_ms"])}}
+        if t["kernels"]:
+            k = dict(t["kernels"])
+            pS = k.pop("_chunk_patches")
+            block["kernels_one_chunk"] = {"patches": pS, "by_kernel_id": k,
+                                          "note": "device time per C-ABI kernel id for one chunk, "
+                                                  "cudaEvent pairs in a separate profiling context "
+                                                  "(launches serialised); not the timed run"}
+        line[name] = block
+
+    if "c5" in res:
+        c = res["c5"]
+        cfg = NETS["c5"]
+        mp = C5_FRAMES_TOTAL * C5_W * C5_H / 1e6
+        tf = fwd_flop(cfg, C5_W, C5_H) * c["n_loc"] / (c["ms"] / 1e3) / 1e12
+        traffic, traffic_src = ncu_traffic("forward_fused_hpw_kernel<0>")
+        line["c5"] = {"metric": "srcnn_915_wide_frames_mpix_per_s", "value": mp / (c["ms"] / 1e3),
+                      "unit": "MPix/s", "ms_per_step": c["ms"], "steps": c["steps"],
+                      "scaling": "strong", "frames_per_step": C5_FRAMES_TOTAL,
+                      "frames_per_gpu": c["n_loc"], "frame": [C5_W, C5_H],
+                      "ms_per_frame": c["ms"] / c["n_loc"], "gpu_launches": int(c["launches"]),
+                      "roofline": {"kernel": "forward_fused_hpw_kernel (tcgen05 kind::f16, FP16-split)",
+                                   "bound": "tensor", "achieved": tf, "peak": bf16_peak,
+                                   "unit": "TFLOP/s", "frac": tf / bf16_peak,
+                                   "precision_ceiling_tflops": bf16_peak / 3.0,
+                                   "frac_of_precision_ceiling": tf / (bf16_peak / 3.0),
+                                   "traffic": traffic, "traffic_source": traffic_src},
+                      "e2e": {"value": mp / (c["e2e_ms"] / 1e3), "unit": "MPix/s",
+                              "ms_per_step": c["e2e_ms"], "h2d_bytes_per_step": c["h2d"],
+                              "d2h_bytes_per_step": c["d2h"],
+                              "pcie": pcie_block(c["h2d"], c["d2h"], c["e2e_ms"])}}
+
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+        line["cpu_baseline"] = cpu_baseline(args, wl)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args):
-    """The oracle/_ref (reference kernels on host cores) timed on a bounded sample."""
-    from oracle.loader import NetState, Oracle, have
-    kind = "reference" if have("reference") else "port"
-    orc = Oracle(kind)
-    orc.set_num_threads(len(os.sched_getaffinity(0)))
-    rng, params, luma_image, patches = synthetic_inputs()
-    net = NetState(N1, N2, F1, F2, F3, params)
-    rows = args.ref_rows
-    band = luma_image(rng, rows + PAD, IMG)
-    orc.net_forward(net, band, IMG, rows + PAD, 1)
-    t = []
-    for _ in range(3):
-        t0 = time.perf_counter()
-        orc.net_forward(net, band, IMG, rows + PAD, 1)
-        t.append(time.perf_counter() - t0)
-    frac = rows / float(IMG - PAD)
-    mpix = IMG * IMG * frac / 1e6 / min(t)
-    x, gt = patches(rng, args.ref_patches, PATCH, PATCH)
-    t0 = time.perf_counter()
-    orc.net_train_epoch(net, x, gt, PATCH, PATCH, args.ref_patches, MOMENTUM, DECAY, LR)
-    pps = args.ref_patches / (time.perf_counter() - t0)
-    return {"value": mpix, "unit": "MPix/s", "cores": orc.num_threads(), "kind": kind,
-            "sample": "best of 3 on %d of %d output rows of the 4096-wide image (%.1f%% of C3), "
-                      "scaled linearly" % (rows, IMG - PAD, 100 * frac),
-            "train_patches_per_s": pps, "train_sample": "%d patches, 1 epoch" % args.ref_patches}
+def cpu_baseline(args, wl):
+    """oracle/_ref (the reference's kernels on the host cores) timed on a bounded sample."""
+    a = argparse.Namespace(**vars(args))
+    a.steps, a.warmup = 2, 1
+    a.ref_rows = min(args.ref_rows, 1024)
+    r = reference_numbers(a, wl)
+    out = {"value": r.get("c3", {}).get("mpix"), "unit": "MPix/s", "cores": r["cores"],
+           "kind": r["kind"], "sample": r.get("c3", {}).get("sample")}
+    if "c2" in r:
+        out["train_patches_per_s"] = r["c2"]["patches_per_s"]
+        out["train_sample"] = r["c2"]["sample"]
+    if "c4" in r:
+        out["train_c4_patches_per_s"] = r["c4"]["patches_per_s"]
+        out["train_c4_sample"] = r["c4"]["sample"]
+    if "c5" in r:
+        out["c5_mpix_per_s"] = r["c5"]["mpix"]
+        out["c5_sample"] = r["c5"]["sample"]
+    return out
 
 
 def main():
@@ -430,21 +691,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workloads", default="c3,c2,c4,c5")
     ap.add_argument("--chunk", type=int, default=2048,
                     help="patches per training chunk (the reference chunks an epoch in two: "
                          "src/Main_cl.cpp:93,128-129)")
-    ap.add_argument("--ref-rows", type=int, default=128)
-    ap.add_argument("--ref-patches", type=int, default=256)
+    ap.add_argument("--ref-rows", type=int, default=IMG - 12,
+                    help="output rows of C3 the reference arm computes per step (default: all)")
+    ap.add_argument("--ref-patches", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = [w for w in args.workloads.split(",") if w]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, wl)
     else:
-        run_ours(args, rank, world, local_rank)
+        run_ours(args, rank, world, local_rank, wl)
 
 
 if __name__ == "__main__":

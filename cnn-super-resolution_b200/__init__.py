@@ -100,6 +100,7 @@ _SIGS = {
     "srcnn_forward_fused_supported": (_i, [C.POINTER(CNet)]),
     "srcnn_forward_fused": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
     "srcnn_infer_rows_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _i, _vp]),
+    "srcnn_infer_frames_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _vp]),
     "srcnn_train_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64]),
     "srcnn_train_chunks_host": (_i, [_vp, C.POINTER(CNet), _vp, _vp, _i, _i, _i, _i, _u64]),
     "srcnn_train_chunk_buffers": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i,
@@ -411,6 +412,14 @@ class Net:
         assert host_in.dtype == np.float32 and host_out.dtype == np.float32
         _check(self.ctx.L.srcnn_infer_rows_host(self.ctx.h, C.byref(self.c), _np_ptr(host_in), w,
                                                 h, row0, row1, _np_ptr(host_out)))
+
+    def infer_frames_host(self, host_in, w, h, host_out):
+        """host_in: [n][h][w] float32 frames; host_out: [n][h3][w3].  Upload / forward / download
+        of consecutive frame groups overlap."""
+        assert host_in.dtype == np.float32 and host_out.dtype == np.float32
+        assert host_in.flags.c_contiguous and host_out.flags.c_contiguous
+        _check(self.ctx.L.srcnn_infer_frames_host(self.ctx.h, C.byref(self.c), _np_ptr(host_in), w,
+                                                  h, int(host_in.shape[0]), _np_ptr(host_out)))
 
     def train_workspace_bytes(self, w, h, S):
         return self.ctx.L.srcnn_train_workspace_bytes(C.byref(self.c), w, h, S)

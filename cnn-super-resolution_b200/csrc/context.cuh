@@ -125,6 +125,7 @@ struct srcnn_ctx {
   cudaEvent_t ev_join[2] = {};
   static constexpr int kEvents = 32;
   cudaEvent_t ev_in[kEvents] = {}, ev_k[kEvents] = {};
+  cudaEvent_t ev_d[4] = {};   // download-finished events of srcnn_infer_frames_host's ring
   // data-parallel communicator (NCCL, loaded at run time: comm.cuh); null = single GPU
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;

@@ -138,6 +138,8 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
       cudaEventDestroy(ctx->ev_in[i]);
       cudaEventDestroy(ctx->ev_k[i]);
     }
+    for (int i = 0; i < 4; i++)
+      if (ctx->ev_d[i]) cudaEventDestroy(ctx->ev_d[i]);
   }
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -590,6 +592,22 @@ int net_prepare(srcnn_ctx* ctx, const srcnn_net* net, const float* w1, const flo
   return SRCNN_OK;
 }
 
+// the copy-in / copy-out / second compute stream and the events of the pipelined host-buffer
+// entries (created on first use)
+int ensure_side_streams(srcnn_ctx* ctx) {
+  if (ctx->copy_in) return SRCNN_OK;
+  SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
+  for (int i = 0; i < srcnn_ctx::kEvents; i++) {
+    SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+    SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 4; i++)
+    SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_d[i], cudaEventDisableTiming));
+  return SRCNN_OK;
+}
+
 // drops the handles a scope appended to the table (wrapped views of a workspace, staging
 // buffers) on EVERY exit path, so that errors do not grow the table
 struct TableScope {
@@ -710,15 +728,7 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
     }
     if (n_sub == 1) sub_r0[1] = band_out_h;
   }
-  if (n_sub > 1 && !ctx->copy_in) {
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
-    for (int i = 0; i < kMaxSub; i++) {
-      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
-    }
-  }
+  if (n_sub > 1) SRCNN_TRY(ensure_side_streams(ctx));
   float* din = (float*)ctx->band_in;
   float* dout = (float*)ctx->band_out;
   // one set of operand scales for all sub-bands (computed on the context stream, before the
@@ -861,6 +871,72 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   SRCNN_CUDA(cudaStreamSynchronize(ctx->compute2));
   SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
   return rc;
+}
+
+int srcnn_infer_frames_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int w,
+                            int h, int n_frames, float* host_out) {
+  SRCNN_REQUIRE(ctx && host_in && host_out, "null argument");
+  SRCNN_ENTER(ctx);
+  SRCNN_TRY(check_net(net));
+  const Dims d = net_dims(net, w, h);
+  SRCNN_REQUIRE(n_frames > 0 && d.w3 > 0 && d.h3 > 0, "bad frame set: %d frames of %dx%d", n_frames, w, h);
+  SRCNN_REQUIRE(fast::fused_supported(net->n1, net->n2, net->f1, net->f2, net->f3),
+                "srcnn_infer_frames_host needs a fused instantiation for %d-%d-%d n1=%d n2=%d",
+                net->f1, net->f2, net->f3, net->n1, net->n2);
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  SRCNN_TRY(resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1"));
+  SRCNN_TRY(resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1"));
+  SRCNN_TRY(resolve(ctx, net->w[1], sizeof(float) * (size_t)net->f2 * net->f2 * net->n1 * net->n2, &w2, "w2"));
+  SRCNN_TRY(resolve(ctx, net->b[1], sizeof(float) * (size_t)net->n2, &b2, "b2"));
+  SRCNN_TRY(resolve(ctx, net->w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &w3, "w3"));
+  SRCNN_TRY(resolve(ctx, net->b[2], sizeof(float), &b3, "b3"));
+  // groups of frames go through a ring of device slots: the upload of group g+1 and the download
+  // of group g-1 overlap the fused forward of group g (one launch per group, frame = gridDim.z)
+  constexpr int kRing = 3;
+  static const int kGroupEnv = std::getenv("SRCNN_FRAMES_GROUP") ? std::atoi(std::getenv("SRCNN_FRAMES_GROUP")) : 0;
+  const size_t in_px = (size_t)w * h, out_px = (size_t)d.w3 * d.h3;
+  // ~16 MB of input per group: long enough launches to fill the GPU, short enough that the
+  // exposed first upload / last download stay small
+  int group = kGroupEnv > 0 ? kGroupEnv : (int)std::max<size_t>(1, ((size_t)16 << 20) / (in_px * sizeof(float)));
+  group = std::min(group, n_frames);
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->band_in, &ctx->band_in_bytes, sizeof(float) * in_px * group * kRing));
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->band_out, &ctx->band_out_bytes, sizeof(float) * out_px * group * kRing));
+  SRCNN_TRY(ensure_side_streams(ctx));
+  const void* scales = nullptr;
+  SRCNN_TRY(net_prepare(ctx, net, w1, b1, w2, b2, w3, b3, &scales));
+  // the side streams start behind whatever the context stream was doing with the staging
+  SRCNN_CUDA(cudaEventRecord(ctx->ev_k[kRing], ctx->stream));
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[kRing], 0));
+  SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[kRing], 0));
+  float* din = (float*)ctx->band_in;
+  float* dout = (float*)ctx->band_out;
+  for (int g = 0, f0 = 0; f0 < n_frames; g++, f0 += group) {
+    const int S = std::min(group, n_frames - f0), r = g % kRing;
+    float* si = din + (size_t)r * group * in_px;
+    float* so = dout + (size_t)r * group * out_px;
+    // input slot r was last read by the forward of group g - kRing
+    if (g >= kRing) SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[r], 0));
+    SRCNN_CUDA(cudaMemcpyAsync(si, host_in + (size_t)f0 * in_px, sizeof(float) * in_px * S,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_in[r], ctx->copy_in));
+    SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[r], 0));
+    // output slot r was last downloaded for group g - kRing
+    if (g >= kRing) SRCNN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d[r], 0));
+    {
+      LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
+      SRCNN_TRY(fast::forward_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, si, so, w1, b1,
+                                    w2, b2, w3, b3, w, h, S, scales));
+      SRCNN_TRY(check_launch("forward_fused"));
+    }
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_k[r], ctx->stream));
+    SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[r], 0));
+    SRCNN_CUDA(cudaMemcpyAsync(host_out + (size_t)f0 * out_px, so, sizeof(float) * out_px * S,
+                               cudaMemcpyDeviceToHost, ctx->copy_out));
+    SRCNN_CUDA(cudaEventRecord(ctx->ev_d[r], ctx->copy_out));
+  }
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  SRCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SRCNN_OK;
 }
 
 size_t srcnn_train_workspace_bytes(const srcnn_net* net, int w, int h, int S) {
@@ -1049,15 +1125,7 @@ int srcnn_train_chunks_host(srcnn_ctx* ctx, const srcnn_net* net, const float* h
     SRCNN_TRY(ensure_scratch(ctx, &ctx->stage_in[b], &ctx->stage_in_bytes[b], need));
     SRCNN_TRY(ensure_scratch(ctx, &ctx->stage_gt[b], &ctx->stage_gt_bytes[b], need));
   }
-  if (!ctx->copy_in) {
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-    SRCNN_CUDA(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
-    for (int i = 0; i < srcnn_ctx::kEvents; i++) {
-      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      SRCNN_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
-    }
-  }
+  SRCNN_TRY(ensure_side_streams(ctx));
   // the copy stream starts behind whatever the context stream was doing with the staging
   SRCNN_CUDA(cudaEventRecord(ctx->ev_k[2], ctx->stream));
   SRCNN_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[2], 0));

@@ -205,13 +205,23 @@ int srcnn_forward_fused_supported(const srcnn_net* net);
  * output rows [row0,row1) of the [h3][w3] result into host_out (which points at row row0).
  * halo = f1+f2+f3-3 input rows per band.  Used by bench.py e2e and by the
  * multi-GPU row-band sharding: rank g calls it with its own [row0,row1).
- * Bands of >= 1024 output rows are cut into sub-bands whose upload, compute and download
+ * Bands of >= 256 output rows are cut into sub-bands whose upload, compute and download
  * overlap on separate streams; that pipeline is captured into a CUDA graph owned by the
  * context and replayed while the call's arguments (both host pointers, shape, band, network
  * buffers) repeat -- the buffers' CONTENTS are read afresh on every call.  Synchronous: the
  * result is in host_out on return.  Pinned host buffers give the PCIe rate; pageable ones work. */
 int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int in_w,
                           int in_h, int out_row0, int out_row1, float* host_out);
+
+/* ConfigBasedDataPipeline::forward(sample) for MANY frames (src/ConfigBasedDataPipeline.cpp:
+ * 114-126 is called once per image by src/Main_cl.cpp:217-239): `n_frames` luma frames of
+ * w x h floats in host memory -> n_frames results of w3 x h3 floats in host_out.  Groups of
+ * frames go through a ring of device slots so that the upload of the next group and the download
+ * of the previous one overlap the fused forward of the current one.  Synchronous.  Frames are
+ * independent: a multi-GPU caller gives each rank its own slice of the frame set (SURVEY 8e,
+ * BASELINE config C5). */
+int srcnn_infer_frames_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int w,
+                            int h, int n_frames, float* host_out);
 
 /* One training chunk on device-resident samples: forward (keeping out1/out2), last-layer
  * delta, deltas 2<-3 and 1<-2, the three weight/bias gradients accumulated into

@@ -18,6 +18,19 @@ Two kinds of fixture:
      ref_train_915.npz       same chain on a 9-1-5 n1=8 n2=4 net with 33x33 patches (outputs only:
                              parameters after 2 epochs + final SSE)
 
+     ref_train_c2_epoch.npz  BASELINE config C2 exactly as bench.py trains it: 9-1-5 n1=64 n2=32,
+                             4096 patches 33x33, chunks of 2048, momentum 0.9, decay 1e-3,
+                             lr 1e-4/1e-4/1e-5; parameters after epochs 1 and 2 (inputs are
+                             regenerated from the seed by tests/helpers.py)
+     ref_train_c4_epoch.npz  the 9-5-5 network of config C4 on 512 patches, chunks of 256
+3. *Reference image fixtures* for the luma kernels, decoded with the reference's own vendored
+   stb_image (libs/include/stb, compiled here into a throw-away decoder: PIL's JPEG decoder
+   differs from it by up to 2 levels, which would break SwapLumaTest's exact comparison):
+     color_grid_5x5.rgba                 <- test/data/color_grid.png        (ExtractLumaTest.cpp)
+     color_grid2_32x32.rgba              <- test/data/color_grid2.jpg       (SwapLumaTest.cpp)
+     color_grid2_luma_swapped_32x32.rgb  <- test/data/color_grid2_luma_swapped.png
+     luma_goldens.json                   <- test/specs/ExtractLumaTest.cpp:24-28 (25 values)
+
 Nothing under /root/reference is needed at test time.
 """
 import json
@@ -194,13 +207,83 @@ def reference_train_chain(ref, name, cfg, n_samples, w, h, chunk, epochs, full):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def reference_train_big(ref, name, cfg, n_samples, chunk, epochs, seed, lr):
+    """Per-epoch parameters of the reference kernels on a BASELINE-sized training run.  Inputs
+    are NOT stored: tests regenerate them from `seed` with tests/helpers.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    n1, n2, f1, f2, f3 = cfg
+    rng = np.random.default_rng(seed)
+    params = helpers.make_params(rng, n1, n2, f1, f2, f3)
+    x, gt = helpers.patches(rng, n_samples, 33, 33)
+    net = NetState(n1, n2, f1, f2, f3, params)
+    ref.set_num_threads(len(os.sched_getaffinity(0)))
+    out = dict(cfg=np.array(cfg), dims=np.array([n_samples, 33, 33, chunk, epochs]),
+               seed=np.int64(seed), momentum=np.float32(0.9), decay=np.float32(0.001),
+               lr=np.asarray(lr, np.float32),
+               x_checksum=np.float64(x.astype(np.float64).sum()),
+               gt_checksum=np.float64(gt.astype(np.float64).sum()))
+    for e in range(epochs):
+        ref.net_train_epoch(net, x, gt, 33, 33, chunk, 0.9, 0.001, out["lr"], True)
+        for i in range(3):
+            out["e%d_w%d" % (e + 1, i + 1)] = net.w[i].copy()
+            out["e%d_b%d" % (e + 1, i + 1)] = net.b[i].copy()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
+def luma_fixtures():
+    """Decode the reference's image fixtures with the reference's own stb_image."""
+    import subprocess
+    import tempfile
+    src = r"""
+#define STB_IMAGE_IMPLEMENTATION
+#include "stb/stb_image.h"
+#include <stdio.h>
+int main(int argc, char** argv) {
+  int w, h, n, want = argv[3][0] - '0';
+  unsigned char* d = stbi_load(argv[1], &w, &h, &n, want);
+  if (!d) return 1;
+  FILE* f = fopen(argv[2], "wb");
+  fwrite(d, 1, (size_t)w * h * want, f);
+  fclose(f);
+  printf("%d %d\n", w, h);
+  return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "dec.c")
+        open(c, "w").write(src)
+        exe = os.path.join(tmp, "dec")
+        subprocess.check_call(["gcc", "-O1", "-w", "-I", os.path.join(REF, "libs/include"), "-o", exe,
+                               c, "-lm"])
+        for name, out, ch, dims in (
+                ("color_grid.png", "color_grid_5x5.rgba", 4, "5 5"),
+                ("color_grid2.jpg", "color_grid2_32x32.rgba", 4, "32 32"),
+                ("color_grid2_luma_swapped.png", "color_grid2_luma_swapped_32x32.rgb", 3, "32 32")):
+            got = subprocess.check_output([exe, os.path.join(REF, "test/data", name),
+                                           os.path.join(HERE, out), str(ch)]).decode().strip()
+            assert got == dims, (name, got)
+    spec = open(os.path.join(REF, "test/specs/ExtractLumaTest.cpp")).read()
+    with open(os.path.join(HERE, "luma_goldens.json"), "w") as fh:
+        json.dump({"source": "test/specs/ExtractLumaTest.cpp:24-28; SwapLumaTest.cpp:21-24,47-53",
+                   "extract_luma_normalized_5x5": c_array(spec, "output"),
+                   "margin": 0.005, "swap_padding": 10,
+                   "swap_new_luma": "new_luma[i] = i * 1.0f / (luma_w * luma_w), luma_w = 32 - 20"},
+                  fh, indent=1)
+
+
 def main():
     transcribe_reference_specs()
+    luma_fixtures()
     copy_config_fixtures()
     ref = Oracle("reference")
     reference_kernel_outputs(ref)
     reference_train_chain(ref, "ref_train_chain.npz", (4, 3, 3, 1, 3), 5, 9, 8, 2, 2, True)
     reference_train_chain(ref, "ref_train_915.npz", (8, 4, 9, 1, 5), 6, 33, 33, 4, 2, False)
+    reference_train_big(ref, "ref_train_c2_epoch.npz", (64, 32, 9, 1, 5), 4096, 2048, 2, 4242,
+                        [1e-4, 1e-4, 1e-5])
+    reference_train_big(ref, "ref_train_c4_epoch.npz", (64, 32, 9, 5, 5), 512, 256, 2, 4343,
+                        [1e-4, 1e-4, 1e-5])
     for f in sorted(os.listdir(HERE)):
         print("%8d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))
 

@@ -300,6 +300,28 @@ def test_luma_kernels_bit_exact(ctx, port):
                                   port.swap_luma(rgba, new_luma, w - 2 * pad, h - 2 * pad))
 
 
+def test_luma_kernels_reference_fixtures(ctx):
+    """The reference's own luma fixtures (decoded by its stb_image, tests/golden/make_golden.py):
+    all 25 goldens of ExtractLumaTest.cpp:24-28 (both data sets) and the exact image of
+    SwapLumaTest.cpp:39-90."""
+    rd = lambda n, shape: np.fromfile(os.path.join(GOLDEN, n), np.uint8).reshape(shape)
+    gold = _json("luma_goldens.json")
+    grid = rd("color_grid_5x5.rgba", (5, 5, 4))
+    exp = np.array(gold["extract_luma_normalized_5x5"], np.float32).reshape(5, 5)
+    mi, ml = ctx.upload(grid, np.uint8), ctx.alloc(4 * 25)
+    ctx.extract_luma(mi, ml, 5, 5, True)
+    np.testing.assert_allclose(ctx.read(ml, (5, 5)), exp, atol=gold["margin"], rtol=0)
+    ctx.extract_luma(mi, ml, 5, 5, False)
+    np.testing.assert_allclose(ctx.read(ml, (5, 5)), exp * 255.0, atol=255 * gold["margin"], rtol=0)
+    img = rd("color_grid2_32x32.rgba", (32, 32, 4))
+    expected = rd("color_grid2_luma_swapped_32x32.rgb", (32, 32, 3))
+    lw = 32 - 2 * gold["swap_padding"]
+    new_luma = (np.arange(lw * lw, dtype=np.float32) * np.float32(1.0) / np.float32(lw * lw))
+    mi, mn, mt = ctx.upload(img, np.uint8), ctx.upload(new_luma), ctx.alloc(32 * 32 * 3)
+    ctx.swap_luma(mi, mn, mt, 32, 32, lw, lw)
+    np.testing.assert_array_equal(ctx.read(mt, (32, 32, 3), np.uint8), expected)
+
+
 # ------------------------------------------------------------------ errors
 def test_error_behaviour(ctx):
     """Validation mirrors the reference's (src/DataPipeline.cpp:339-356, Context.cpp:235-341):
@@ -455,6 +477,57 @@ def test_training_epochs_vs_committed_reference(ctx, name):
     work2 = ctx.alloc(net.train_workspace_bytes(w, h, ns))
     net.validate_chunk(mi, mg, w, h, ns, work2, tgt)
     assert float(ctx.read(tgt, (1,))[0]) == pytest.approx(float(g["final_sse"]), rel=1e-4)
+
+
+def _epoch_fixture_inputs(g):
+    from helpers import make_params, patches
+    n1, n2, f1, f2, f3 = (int(v) for v in g["cfg"])
+    ns, w, h, chunk, epochs = (int(v) for v in g["dims"])
+    rng = np.random.default_rng(int(g["seed"]))
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x, gt = patches(rng, ns, w, h)
+    assert float(x.astype(np.float64).sum()) == pytest.approx(float(g["x_checksum"]), rel=1e-12)
+    return (n1, n2, f1, f2, f3), (ns, w, h, chunk, epochs), params, x, gt
+
+
+def _assert_params_close(p, g, e, what):
+    for l in range(3):
+        np.testing.assert_allclose(p["w%d" % (l + 1)], g["e%d_w%d" % (e, l + 1)], rtol=1e-4,
+                                   atol=1e-7, err_msg="%s epoch %d w%d" % (what, e, l + 1))
+        np.testing.assert_allclose(p["b%d" % (l + 1)], g["e%d_b%d" % (e, l + 1)], rtol=1e-4,
+                                   atol=1e-7, err_msg="%s epoch %d b%d" % (what, e, l + 1))
+
+
+@pytest.mark.parametrize("name,route", [("ref_train_c2_epoch.npz", "device"),
+                                        ("ref_train_c2_epoch.npz", "host"),
+                                        ("ref_train_c4_epoch.npz", "device")])
+def test_baseline_sized_epochs_vs_committed_reference(ctx, name, route):
+    """The BENCHMARKED training configuration, exactly as bench.py runs it: config C2 (9-1-5
+    n1=64 n2=32, 4096 patches 33x33, chunks of 2048 -> the persistent tensor-core kernels
+    forward_fused_hp<BATCH>, bwd3_fused, wgrad1_fused_tc, wgrad2_tc), momentum 0.9, decay 1e-3,
+    lr 1e-4/1e-4/1e-5, srcnn_update_all -- and the 9-5-5 network of C4 at chunks of 256.  All six
+    parameter tensors after epochs 1 and 2 must be within 1e-4 relative of what the reference's
+    own kernels (oracle/_ref, fixture committed by make_golden.py) produce.  `host` goes through
+    srcnn_train_chunks_host (pinned host samples, the e2e route of the bench)."""
+    g = load_npz(name)
+    cfg, (ns, w, h, chunk, epochs), params, x, gt = _epoch_fixture_inputs(g)
+    net = pkg.Net(ctx, *cfg, params)
+    work = ctx.alloc(net.train_workspace_bytes(w, h, chunk))
+    mi, mg = ctx.upload(x), ctx.upload(gt)
+    per = 4 * w * h
+    views = [(ctx.wrap(ctx.mem_ptr(mi) + i * per, min(chunk, ns - i) * per),
+              ctx.wrap(ctx.mem_ptr(mg) + i * per, min(chunk, ns - i) * per), min(chunk, ns - i))
+             for i in range(0, ns, chunk)]
+    for e in range(1, epochs + 1):
+        if route == "host":
+            net.train_chunks_host(x, gt, w, h, chunk, work)
+        else:
+            for vi, vg, S in views:
+                net.train_chunk(vi, vg, w, h, S, work)
+        net.update_all(ns, float(g["momentum"]), float(g["decay"]), g["lr"])
+        _assert_params_close(net.params(), g, e, "%s/%s" % (name, route))
+    for m in (work, mi, mg):
+        ctx.release(m)
 
 
 INFER = [

@@ -66,7 +66,8 @@ def main():
         return v * mult.get(unit, 1)
 
     for name, r in last.items():
-        short = re.sub(r"\(.*", "", name).replace("srcnn::", "")
+        m = re.match(r"^(?:void\s+)?([\w:]+(?:<.*?>)?)", name)
+        short = (m.group(1) if m else name).replace("srcnn::", "")
         out.append("")
         out.append("== %s" % short)
         for k in KEEP:

@@ -84,6 +84,7 @@ _SIGS = {
     "srcnn_read": (_i, [_vp, _u64, _sz, _sz, _vp, _i]),
     "srcnn_copy": (_i, [_vp, _u64, _u64, _sz]),
     "srcnn_copy_region": (_i, [_vp, _u64, _sz, _u64, _sz, _sz]),
+    "srcnn_gather": (_i, [_vp, C.POINTER(_u64), _i, _sz, _u64]),
     "srcnn_fill_float": (_i, [_vp, _u64, _f]),
     "srcnn_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "srcnn_host_free": (_i, [_vp]),
@@ -309,6 +310,11 @@ class Context:
 
     def copy_region(self, src, src_offset, dst, dst_offset, nbytes):
         _check(self.L.srcnn_copy_region(self.h, src, src_offset, dst, dst_offset, nbytes))
+
+    def gather(self, handles, nbytes_each, dst):
+        """copies the equally-sized buffers `handles` into consecutive slots of dst (one launch)"""
+        arr = (_u64 * len(handles))(*handles)
+        _check(self.L.srcnn_gather(self.h, arr, len(handles), int(nbytes_each), dst))
 
     def fill_float(self, mem, value):
         _check(self.L.srcnn_fill_float(self.h, mem, float(value)))

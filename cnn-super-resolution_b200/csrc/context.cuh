@@ -108,6 +108,8 @@ struct srcnn_ctx {
   // context-owned scratch: reduction partials, split-K partial tiles, row-band staging
   void* red_scratch = nullptr;      // fixed: kRedScratchBytes
   void* splitk_scratch = nullptr;   // grown on demand
+  void* gather_tab = nullptr;       // pointer table of srcnn_gather
+  size_t gather_tab_bytes = 0;
   size_t splitk_bytes = 0;
   void* band_in = nullptr;          // srcnn_infer_rows_host staging (device)
   void* band_out = nullptr;

@@ -417,6 +417,16 @@ reduce_stage2(const double* __restrict__ partial, int count, float* __restrict__
   if (threadIdx.x == 0) *target = (float)r;
 }
 
+// batched sample gather: block (x, y) copies a slice of source y into slot y of dst
+__global__ void gather_kernel(const float* const* __restrict__ src, float* __restrict__ dst,
+                              size_t floats_each) {
+  const float* s = src[blockIdx.y];
+  float* d = dst + (size_t)blockIdx.y * floats_each;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < floats_each;
+       i += (size_t)gridDim.x * blockDim.x)
+    d[i] = __ldg(s + i);
+}
+
 // ------------------------------------------------------------------ luma -------------
 // reference: src/kernel/extract_luma.cl:7-23
 __global__ void extract_luma_kernel(const uchar4* __restrict__ rgba, float* __restrict__ target,

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "comm.cuh"
 #include "context.cuh"
@@ -118,6 +119,7 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
     if (a.owned && !a.released && a.ptr) cudaFree(a.ptr);
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
   if (ctx->splitk_scratch) cudaFree(ctx->splitk_scratch);
+  if (ctx->gather_tab) cudaFree(ctx->gather_tab);
   if (ctx->band_in) cudaFree(ctx->band_in);
   if (ctx->band_out) cudaFree(ctx->band_out);
   for (int i = 0; i < 2; i++) {
@@ -316,6 +318,33 @@ int srcnn_copy(srcnn_ctx* ctx, srcnn_mem src, srcnn_mem dst, size_t dst_offset) 
   Allocation* s = ctx->get(src);
   if (!s) return fail(SRCNN_EHANDLE, "invalid memory handle in copy");
   return srcnn_copy_region(ctx, src, 0, dst, dst_offset, s->bytes);
+}
+
+int srcnn_gather(srcnn_ctx* ctx, const srcnn_mem* src, int n, size_t bytes_each, srcnn_mem dst) {
+  SRCNN_ENTER(ctx);
+  SRCNN_REQUIRE(src != nullptr && n > 0, "nothing to gather");
+  SRCNN_REQUIRE(bytes_each > 0 && bytes_each % sizeof(float) == 0, "bytes_each must be a multiple of 4");
+  SRCNN_REQUIRE(n <= 65535 * 64, "too many buffers in one gather");
+  float* pd;
+  SRCNN_TRY(resolve(ctx, dst, bytes_each * (size_t)n, &pd, "gather destination"));
+  ctx->note_write(dst);
+  std::vector<const float*> tab((size_t)n);
+  for (int i = 0; i < n; i++)
+    SRCNN_TRY(resolve(ctx, src[i], bytes_each, &tab[(size_t)i], "gather source"));
+  SRCNN_TRY(ensure_scratch(ctx, &ctx->gather_tab, &ctx->gather_tab_bytes, sizeof(void*) * (size_t)n));
+  // pageable source: the runtime stages the table before the call returns, so `tab` may go
+  SRCNN_CUDA(cudaMemcpyAsync(ctx->gather_tab, tab.data(), sizeof(void*) * (size_t)n,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  const size_t floats_each = bytes_each / sizeof(float);
+  for (int y0 = 0; y0 < n; y0 += 65535) {
+    const int ny = std::min(65535, n - y0);
+    dim3 grid((unsigned)std::min<size_t>(64, (floats_each + 255) / 256), (unsigned)ny);
+    generic::gather_kernel<<<grid, 256, 0, ctx->stream>>>(
+        reinterpret_cast<const float* const*>(ctx->gather_tab) + y0, pd + (size_t)y0 * floats_each,
+        floats_each);
+    ctx->launch_count++;
+  }
+  return check_launch("gather");
 }
 
 int srcnn_fill_float(srcnn_ctx* ctx, srcnn_mem mem, float value) {

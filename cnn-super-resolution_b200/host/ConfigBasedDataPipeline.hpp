@@ -72,9 +72,17 @@ class ConfigBasedDataPipeline : public DataPipeline {
   /** forward() + backpropagate() of one training chunk in one device-layer call */
   void train_chunk(LayerAllocationPool&, LayerAllocationPool&, LayerAllocationPool&, size_t w,
                    size_t h, size_t sample_count);
+  /** the three layers' device buffers as the C-ABI's srcnn_net */
+  srcnn_net device_net(LayerAllocationPool&, LayerAllocationPool&, LayerAllocationPool&,
+                       bool with_gradients, bool with_momentum);
+  void ensure_momentum_on_device(int layer, LayerData&, LayerAllocationPool&);
   void fill_random_parameters(LayerData&, ParametersDistribution&);
   size_t load_parameters_file(const char* const);
 
+  /** momentum state read from the optional "resume" key of a parameters file (uploaded when the
+   * previous_batch_delta buffers are first needed) */
+  std::vector<float> _resume_prev_w[3], _resume_prev_b[3];
+  std::vector<opencl::MemoryHandle> _gather_in, _gather_gt;
   Config* const _config;
   LayerData layer_data_1, layer_data_2, layer_data_3;
   size_t epochs = 0;

@@ -2,7 +2,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -115,10 +117,42 @@ ProfiledLaunch::~ProfiledLaunch() {
 Context::Context() {}
 Context::~Context() { cleanup(); }
 
+// rank 0 publishes the 128-byte NCCL id through a file (written under a temporary name and
+// renamed, so that readers never see a partial id); the other ranks poll for it
+static void exchange_comm_id(int rank, const char* path, unsigned char id[SRCNN_COMM_ID_BYTES]) {
+  if (rank == 0) {
+    if (srcnn_comm_unique_id(id) != SRCNN_OK) throw std::runtime_error(srcnn_last_error());
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+      std::ofstream f(tmp, std::ios::binary);
+      if (!f.is_open()) throw std::ios_base::failure("Could not write CNN_SR_COMM_FILE");
+      f.write(reinterpret_cast<const char*>(id), SRCNN_COMM_ID_BYTES);
+    }
+    if (std::rename(tmp.c_str(), path) != 0)
+      throw std::ios_base::failure("Could not publish CNN_SR_COMM_FILE");
+    return;
+  }
+  for (int tries = 0; tries < 3000; tries++) {   // up to ~5 minutes
+    std::ifstream f(path, std::ios::binary);
+    if (f.is_open()) {
+      f.read(reinterpret_cast<char*>(id), SRCNN_COMM_ID_BYTES);
+      if (f.gcount() == SRCNN_COMM_ID_BYTES) return;
+    }
+    struct timespec ts = {0, 100 * 1000 * 1000};
+    nanosleep(&ts, nullptr);
+  }
+  throw std::runtime_error("Timed out waiting for rank 0 to publish CNN_SR_COMM_FILE");
+}
+
 void Context::init(bool profile) {
   _profiling = profile;
+  const char* world_env = std::getenv("CNN_SR_WORLD");
+  const char* rank_env = std::getenv("CNN_SR_RANK");
+  _world = world_env ? std::max(1, std::atoi(world_env)) : 1;
+  _rank = rank_env ? std::atoi(rank_env) : 0;
+  if (_rank < 0 || _rank >= _world) throw std::runtime_error("CNN_SR_RANK outside CNN_SR_WORLD");
   const char* dev_env = std::getenv("CNN_SR_DEVICE");
-  const int device = dev_env ? std::atoi(dev_env) : 0;
+  const int device = dev_env ? std::atoi(dev_env) : _rank;
   const int rc = srcnn_ctx_create(device, profile ? 1 : 0, &_ctx);
   if (rc != SRCNN_OK) {
     std::cout << "[GPU ERROR] (" << rc << ") : " << srcnn_last_error() << std::endl;
@@ -132,6 +166,27 @@ void Context::init(bool profile) {
   std::cout << "DEVICE:" << name << ", " << sms << " SMs, " << (_device_mem >> 20) << " MB"
             << std::endl;
   _initialized = true;
+  if (_world > 1) {
+    const char* file = std::getenv("CNN_SR_COMM_FILE");
+    if (!file) throw std::runtime_error("CNN_SR_WORLD > 1 needs CNN_SR_COMM_FILE (a path all ranks can reach)");
+    unsigned char id[SRCNN_COMM_ID_BYTES];
+    exchange_comm_id(_rank, file, id);
+    check_status(srcnn_comm_init(_ctx, _rank, _world, id), "joining the communicator");
+    std::cout << "DATA PARALLEL: rank " << _rank << " of " << _world << " (NCCL)" << std::endl;
+  }
+}
+
+void Context::allreduce_sum(MemoryHandle h, size_t count) {
+  check_status(srcnn_allreduce_sum(_ctx, mem(h), 0, count), "all-reduce");
+}
+
+float Context::allreduce_scalar(float value) {
+  if (_world == 1) return value;
+  if (_scalar_buf == ((MemoryHandle)1 << 30)) _scalar_buf = allocate(CL_MEM_READ_WRITE, sizeof(float));
+  write_buffer(_scalar_buf, &value, true);
+  allreduce_sum(_scalar_buf, 1);
+  read_buffer(_scalar_buf, &value, true);
+  return value;
 }
 
 void Context::cleanup() {

@@ -158,6 +158,17 @@ class Context {
   Event write_image(MemoryHandle, utils::ImageData&, bool block, Event* es = nullptr,
                     int event_count = 0);
 
+  // --- data parallel (new; the reference is single-device) ----------------------------
+  /** rank / world of this process: CNN_SR_RANK / CNN_SR_WORLD in the environment of init().
+   * With CNN_SR_WORLD > 1 init() joins the NCCL communicator of the device layer; the id is
+   * handed over through the file CNN_SR_COMM_FILE (rank 0 writes it, the others wait for it). */
+  int rank() const { return _rank; }
+  int world() const { return _world; }
+  /** in-place sum over all ranks of the first `count` floats of the buffer (no-op on 1 rank) */
+  void allreduce_sum(MemoryHandle, size_t count);
+  /** sum of one host float over all ranks (validation squared error) */
+  float allreduce_scalar(float value);
+
   bool is_initialized() const { return _initialized; }
   bool is_running_profile_mode() const { return _profiling; }
   RawMemoryHandle* raw_memory(MemoryHandle);
@@ -176,6 +187,8 @@ class Context {
   bool _profiling = false;
   srcnn_ctx* _ctx = nullptr;
   uint64_t _ticket = 0;
+  int _rank = 0, _world = 1;
+  MemoryHandle _scalar_buf = (MemoryHandle)1 << 30;
   std::string _device_name;
   size_t _device_mem = 0;
   std::deque<Kernel> _kernels;               // stable addresses

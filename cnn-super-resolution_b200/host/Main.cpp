@@ -94,6 +94,15 @@ static void divide_samples(size_t validation_set_size, GpuAllocationPool& pool,
     (i < validation_set_size ? validation_set : train_set).push_back(&pool.samples[i]);
 }
 
+// contiguous even split of a sample set across the ranks
+static std::vector<SampleAllocationPool*> shard(const std::vector<SampleAllocationPool*>& set,
+                                                int rank, int world) {
+  const size_t base = set.size() / (size_t)world, rem = set.size() % (size_t)world;
+  const size_t begin = (size_t)rank * base + std::min<size_t>((size_t)rank, rem);
+  const size_t count = base + ((size_t)rank < rem ? 1 : 0);
+  return std::vector<SampleAllocationPool*>(set.begin() + (long)begin, set.begin() + (long)(begin + count));
+}
+
 int main(int argc, char** argv) {
   cnn_sr::utils::Argparse argparse("cnn", "SRCNN super-resolution (B200 CUDA build)");
   argparse.add_argument("train").help("Train mode");
@@ -184,26 +193,42 @@ int main(int argc, char** argv) {
     // the reference shuffles with an unseeded std::random_shuffle; CNN_SR_SEED pins it
     std::mt19937 rng(std::getenv("CNN_SR_SEED") ? (unsigned)std::atoi(std::getenv("CNN_SR_SEED")) : 5489u);
     std::vector<SampleAllocationPool*> train_set, validation_set;
+    const int rank = context.rank(), world = context.world();
+    if (world > 1 && !std::getenv("CNN_SR_SEED"))
+      std::cout << "[WARNING] data parallel run without CNN_SR_SEED: the ranks share the default "
+                   "shuffle seed" << std::endl;
     for (size_t epoch_id = 0; epoch_id < epochs; epoch_id++) {
       divide_samples(validation_set_size, gpu_alloc, train_set, validation_set, rng);
-      data_pipeline.execute_batch(true, gpu_alloc, train_set);
+      // data parallel (CNN_SR_WORLD > 1): every rank draws the SAME split (same seed), trains its
+      // contiguous share of it, and update_parameters sums the gradients over the ranks before
+      // the one update with the GLOBAL batch size
+      const size_t global_train = train_set.size(), global_val = validation_set.size();
+      if (world > 1) {
+        train_set = shard(train_set, rank, world);
+        validation_set = shard(validation_set, rank, world);
+      }
+      if (!train_set.empty()) data_pipeline.execute_batch(true, gpu_alloc, train_set);
       data_pipeline.update_parameters(gpu_alloc.layer_1, gpu_alloc.layer_2, gpu_alloc.layer_3,
-                                      train_set.size());
-      if (((epoch_id % 25) == 0 || epoch_id == epochs - 1) && !validation_set.empty()) {
-        const float sq_err = data_pipeline.execute_batch(false, gpu_alloc, validation_set);
+                                      global_train);
+      if (((epoch_id % 25) == 0 || epoch_id == epochs - 1) && global_val != 0) {
+        float sq_err = validation_set.empty()
+                           ? 0.0f
+                           : data_pipeline.execute_batch(false, gpu_alloc, validation_set);
+        sq_err = context.allreduce_scalar(sq_err);   // 1-float all-reduce (no-op on one rank)
         if (std::isnan(sq_err)) {
           std::cout << "Error: squared error is NAN, after " << epoch_id << "/" << epochs
                     << " epochs" << std::endl;
           error = true;
           break;
         }
-        const float mean_err = sq_err / validation_set.size();
-        std::cout << "[" << epoch_id << "] mean validation error: " << mean_err << " ("
-                  << (mean_err / per_sample_px) << " per px)" << std::endl;
+        const float mean_err = sq_err / global_val;
+        if (rank == 0)
+          std::cout << "[" << epoch_id << "] mean validation error: " << mean_err << " ("
+                    << (mean_err / per_sample_px) << " per px)" << std::endl;
       }
       context.block();
     }
-    if (out_path)
+    if (out_path && rank == 0)   // replicas are identical: rank 0 writes
       data_pipeline.write_params_to_file(out_path, gpu_alloc.layer_1, gpu_alloc.layer_2, gpu_alloc.layer_3);
     context.block();
     std::cout << "DONE" << std::endl;

@@ -230,6 +230,51 @@ void sum_test(DataPipeline* p) {
   expect_near((float)s2, p->sum(h, true), 20.f, "sum squared");
 }
 
+// ---- ExtractLumaTest / SwapLumaTest (reference image fixtures, decoded by its stb_image) ---
+std::vector<unsigned char> read_bytes(const std::string& path, size_t expect) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f.is_open()) throw SpecFailure("cannot open fixture " + path);
+  std::vector<unsigned char> v((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  if (v.size() != expect) throw SpecFailure("fixture " + path + " has the wrong size");
+  return v;
+}
+
+// test/specs/ExtractLumaTest.cpp:24-28,50-74: 25 goldens on color_grid.png, both data sets
+void extract_luma_test(DataPipeline* p) {
+  const json::Value g = json::parse_file((golden_dir + "/luma_goldens.json").c_str());
+  const std::vector<float> expected = floats(*g.find("extract_luma_normalized_5x5"));
+  std::vector<unsigned char> rgba = read_bytes(golden_dir + "/color_grid_5x5.rgba", 100);
+  for (int normalize = 1; normalize >= 0; normalize--) {
+    opencl::utils::ImageData img(5, 5, 4, rgba.data());
+    MemoryHandle raw = gpu_nullptr, luma = gpu_nullptr;
+    p->extract_luma(img, raw, luma, normalize != 0);
+    std::vector<float> exp = expected;
+    if (!normalize) for (float& v : exp) v *= 255.f;
+    expect_all_near(exp, download(p->context(), luma, 25), normalize ? 0.005f : 1.275f,
+                    normalize ? "extract_luma normalized" : "extract_luma raw");
+  }
+}
+
+// test/specs/SwapLumaTest.cpp:39-90: exact integer image
+void swap_luma_test(DataPipeline* p) {
+  std::vector<unsigned char> rgba = read_bytes(golden_dir + "/color_grid2_32x32.rgba", 32 * 32 * 4);
+  const std::vector<unsigned char> expected =
+      read_bytes(golden_dir + "/color_grid2_luma_swapped_32x32.rgb", 32 * 32 * 3);
+  const size_t padding = 10, lw = 32 - 2 * padding, n = lw * lw;
+  std::vector<float> new_luma(n);
+  for (size_t i = 0; i < n; i++) new_luma[i] = i * 1.0f / n;
+  opencl::utils::ImageData img(32, 32, 4, rgba.data());
+  MemoryHandle raw = gpu_nullptr, target = gpu_nullptr;
+  MemoryHandle luma = upload(p->context(), new_luma);
+  p->swap_luma(img, raw, luma, target, lw, lw);
+  std::vector<unsigned char> got(32 * 32 * 3);
+  p->context()->read_buffer(target, got.data(), true);
+  for (size_t i = 0; i < got.size(); i++)
+    if (got[i] != expected[i])
+      throw SpecFailure("swap_luma: [INT] Expected " + std::to_string((int)got[i]) + " to be " +
+                        std::to_string((int)expected[i]) + " at byte " + std::to_string(i));
+}
+
 void subtract_from_all_test(DataPipeline* p) {
   std::vector<float> data(900), exp(900);
   for (size_t i = 0; i < 900; i++) {
@@ -345,13 +390,15 @@ int run_specs() {
   opencl::Context context;
   context.init();
   DataPipeline pipeline(&context);
-  pipeline.init(DataPipeline::LOAD_KERNEL_MISC | DataPipeline::LOAD_KERNEL_BACKPROPAGATE);
+  pipeline.init(DataPipeline::LOAD_KERNEL_MISC | DataPipeline::LOAD_KERNEL_BACKPROPAGATE |
+                DataPipeline::LOAD_KERNEL_LUMA);
   struct Spec { const char* name; std::function<void(DataPipeline*)> fn; };
   const Spec specs[] = {
       {"Layer test", layer_test}, {"Layer deltas test", layer_deltas_test},
       {"Backpropagation test", backpropagation_test}, {"Last layer delta test", last_layer_delta_test},
       {"Squared error test", squared_error_test}, {"Update parameters test", update_parameters_test},
       {"Sum all test", sum_test}, {"Subtract from all test", subtract_from_all_test},
+      {"Extract luma test", extract_luma_test}, {"Swap luma test", swap_luma_test},
       {"Config test", config_test}, {"Error behaviour test", error_behaviour_test},
   };
   int failures = 0;

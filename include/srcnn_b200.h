@@ -114,6 +114,11 @@ int srcnn_copy(srcnn_ctx* ctx, srcnn_mem src, srcnn_mem dst, size_t dst_offset);
 /* partial device-to-device copy (new; used by the batched sample gather) */
 int srcnn_copy_region(srcnn_ctx* ctx, srcnn_mem src, size_t src_offset, srcnn_mem dst,
                       size_t dst_offset, size_t bytes);
+/* the sample gather of ConfigBasedDataPipeline::execute_batch
+ * (src/ConfigBasedDataPipeline.cpp:149-161: one clEnqueueCopyBuffer per sample and tensor) as
+ * ONE launch: `n` buffers of `bytes_each` bytes (a multiple of 4) land in consecutive slots of
+ * dst */
+int srcnn_gather(srcnn_ctx* ctx, const srcnn_mem* src, int n, size_t bytes_each, srcnn_mem dst);
 /* Context::fill_float / zeros_float  (Context.cpp:296-310): whole buffer, on the device */
 int srcnn_fill_float(srcnn_ctx* ctx, srcnn_mem mem, float value);
 /* pinned host staging memory for the e2e path (new) */

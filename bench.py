@@ -416,7 +416,8 @@ def run_ours(args, rank, world, local_rank, wl):
             pg = pkg.PinnedBuffer((n_loc, PATCH, PATCH))
             rng_r = np.random.default_rng(99 + rank)
             px.array[:], pg.array[:] = patches(rng_r, n_loc, PATCH, PATCH)
-            chunk = min(args.chunk, n_loc)
+            # 9-5-5: 3031 patches = 592 strips of 128 virtual columns = 4 full waves of 148 CTAs
+            chunk = min(args.chunk if key == "c2" else args.chunk_c4, n_loc)
             d_in, d_gt = ctx.alloc(px.nbytes), ctx.alloc(pg.nbytes)
             ctx.write(d_in, px.array)
             ctx.write(d_gt, pg.array)
@@ -695,6 +696,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=2048,
                     help="patches per training chunk (the reference chunks an epoch in two: "
                          "src/Main_cl.cpp:93,128-129)")
+    ap.add_argument("--chunk-c4", type=int, default=3031)
     ap.add_argument("--ref-rows", type=int, default=IMG - 12,
                     help="output rows of C3 the reference arm computes per step (default: all)")
     ap.add_argument("--ref-patches", type=int, default=512)

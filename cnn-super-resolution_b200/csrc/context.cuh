@@ -101,6 +101,18 @@ struct srcnn_ctx {
   // the device layer (note_write) or by srcnn_invalidate_params
   unsigned long long write_gen = 0;
   srcnn_mem hp_cache_h[6] = {};
+  // 9-5-5 layer 2 on the tensor cores (conv5_tc.cuh): packed FP16 hi/lo images of W2, valid
+  // while the allocation behind c5_h is untouched; per-chunk maxima of the split operands
+  void* c5_images = nullptr;
+  bool c5_valid = false;
+  const void* c5_key = nullptr;
+  srcnn_mem c5_h = SRCNN_NULL_MEM;
+  void* c5_maxes = nullptr;
+  // tensors whose maxima are in c5_maxes (set by the conv5 launches of the current training
+  // chunk, so that its layer-2 gradient does not measure them again)
+  const void* c5_max_out1_of = nullptr;
+  const void* c5_max_d2_of = nullptr;
+  bool c5_maxes_known = false;
   // per-context (= per-device) one-time kernel setup: opt-in dynamic shared memory sizes and
   // occupancy queries, keyed by the kernel's address.  cudaFuncSetAttribute is per DEVICE, so a
   // process-wide flag would leave a second context on another GPU unconfigured.
@@ -141,6 +153,7 @@ struct srcnn_ctx {
   void note_write(srcnn_mem h) {
     for (int i = 0; i < 6; i++)
       if (hp_cache_valid && hp_cache_h[i] == h) write_gen++;
+    if (c5_valid && c5_h == h) c5_valid = false;
   }
 
   srcnn::Allocation* get(srcnn_mem h) {

@@ -1,0 +1,432 @@
+// The two 5x5 contractions over ACTIVATIONS of the 9-5-5 network (BASELINE config C4) on the
+// 5th-gen tensor cores, one kernel template:
+//
+//   MODE 0  layer-2 forward   out2[s][y][x][n] = relu(b2[n] + sum_{dy,dx,k} W2[dy][dx][k][n] *
+//                                                     out1[s][y+dy][x+dx][k])          (K = 25*64)
+//           reference: src/kernel/layer_uber_kernel.cl:36-96 with F_SPATIAL_SIZE=5,
+//           PREVIOUS_FILTER_COUNT=64, CURRENT_FILTER_COUNT=32
+//   MODE 1  layer-1 deltas    d1[s][j][i][n] = [out1[s][j][i][n] > 0] * sum_{dy,dx,k}
+//                                              W2[dy][dx][n][k] * d2[s][j-dy][i-dx][k]  (K = 25*32)
+//           reference: src/kernel/layer_deltas.cl:42-127 (zero outside d2's extent)
+//
+// Both are "out[y][x][co] = sum_{dy,dx,ci} Wg[dy][dx][ci][co] * in[y+dy-P][x+dx-P][ci]" (P = 0 /
+// 4, in = 0 outside; for MODE 1 Wg is W2 with the taps flipped and the channel roles swapped),
+// i.e. implicit GEMMs  M = pixels, N = co, K = 25 taps x ci.
+//
+// No im2col.  The samples of a chunk (33x33 patches -> 25x25 maps) lie side by side as one
+// VIRTUAL image whose slots are 25 columns wide (MODE 1: a 21-wide d2 row + 4 zero columns, which
+// also are the left padding of the next sample).  A CTA owns a strip of 128 virtual output
+// columns and marches down the INPUT rows.  One input row slice (132 pixels x 16 channels) is
+// converted ONCE into FP16 hi/lo "planes" [8-channel chunk][pixel][8 halves]: with SBO = 128 the
+// 128 rows of a K-major A operand are consecutive 16-byte units, so the tile of tap (dy, dx) is
+// the same plane read at base + dx*16 bytes -- the 25 taps of an input row reuse one conversion
+// and one shared-memory copy.  The 5 output rows an input row contributes to (dy = 0..4) each
+// have their own accumulator in tensor memory; a row leaves through the epilogue when its last
+// input row has been issued.  W (hi | lo, 204 800 bytes) stays resident in shared memory.
+//
+// Precision: operands are split x*s = hi + lo into two halves (lo unscaled), the three products
+// hi.hi + hi.lo + lo.hi accumulate in ONE FP32 accumulator (same scheme as the wide inference
+// kernel, fused_forward_hpw.cuh): 22 operand bits.  s is a power of two that maps the largest
+// |x| of the tensor (found on the device by absmax_kernel) to 2^14; the weights likewise.
+//
+//   P  (5 warps)  input row slice -> split -> planes                          -> full[slot]
+//   I0, I1        MMA issuers (output rows of even / odd parity): 5 dx x 3 products per dy
+//                                                                            -> empty[slot], done[acc]
+//   E  (4 warps)  accumulator -> bias + relu / relu' mask -> global          -> acc_free[acc]
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "context.cuh"
+#include "fused_forward_hp.cuh"
+#include "fused_forward_pl.cuh"
+#include "tc_common.cuh"
+
+namespace srcnn {
+namespace c5 {
+
+// per-chunk device scalars: bit patterns of max |x| (non-negative floats order like unsigned)
+struct Maxes {
+  unsigned out1, d2;
+};
+
+// |x| maximum of a tensor, as an unsigned bit pattern (atomicMax); `out` must be zeroed first
+__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, size_t n4,
+                                                     unsigned* out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// 2^14 / pow2ceil(max): the scale that maps the tensor into the FP16 range with headroom
+__host__ __device__ __forceinline__ float scale_for(float mx) {
+  if (!(mx > 0.f) || !(mx < 1e30f)) return 1.f;
+  int e;
+  frexpf(mx, &e);   // mx = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+
+constexpr int F = 5, T = F * F;
+
+template <int CIN_, int COUT_, int MODE_>
+struct Cfg {
+  static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_;
+  static constexpr int KT = T * CIN;                  // K of the GEMM (halves per weight row)
+  static constexpr int NSLICE = CIN / 16;             // 16-channel slices of an input row
+  static constexpr int M = 128;                       // output pixels per strip
+  static constexpr int PW = 136;                      // plane entries (>= M + F - 1)
+  static constexpr int PB = PW * 16;                  // bytes per plane
+  static constexpr int SLOT_BYTES = 4 * PB;           // hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1
+  static constexpr int NSLOT = 3, NACC = 7;
+  static constexpr int W_BYTES = 2 * COUT * KT * 2;   // [W_hi rows ; W_lo rows][KT] halves
+  static constexpr int W_SBO = 128 * (KT / 8);        // bytes between 8-row groups of the image
+  static constexpr int oW = 0, oSlots = W_BYTES, oBias = oSlots + NSLOT * SLOT_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)oBias + COUT * 4;
+  static constexpr int W_E = 0, W_P = 4, N_P = 5, W_I = W_P + N_P, NT = (W_I + 2) * 32;
+  static constexpr uint32_t TMEM_COLS = NACC * COUT <= 256 ? 256 : 512;
+  static_assert(NACC * COUT <= 512, "accumulators must fit tensor memory");
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0, "channel counts");
+  static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory");
+};
+
+// header + packed weight images of the 9-5-5 layer 2 (fp16 hi | lo, canonical K-major), built
+// once per parameter change by prepare_kernel
+struct Images {
+  float sw, inv_sw;        // weights were multiplied by sw
+  float pad_[2];
+  unsigned char fwd[Cfg<64, 32, 0>::W_BYTES];   // rows = n2 (hi 0..31, lo 32..63), k = tap*64 + ci
+  unsigned char d1[Cfg<32, 64, 1>::W_BYTES];    // rows = n1 (hi 0..63, lo 64..127), k = tap*32 + ci
+};
+static_assert(offsetof(Images, fwd) % 16 == 0 && offsetof(Images, d1) % 16 == 0, "uint4 copies");
+
+// W2 [5][5][64][32] -> both images.  Every CTA recomputes max|W2| (51 200 loads) and packs its
+// share.
+__global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ w2, Images* img) {
+  __shared__ float red[8];
+  __shared__ float s_sw;
+  constexpr int N1 = 64, N2 = 32, NW = T * N1 * N2;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < NW; i += 256) m = fmaxf(m, fabsf(__ldg(w2 + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = red[0];
+    for (int w = 1; w < 8; w++) r = fmaxf(r, red[w]);
+    s_sw = scale_for(r);
+    if (blockIdx.x == 0) {
+      img->sw = s_sw;
+      img->inv_sw = 1.f / s_sw;
+    }
+  }
+  __syncthreads();
+  const float sw = s_sw;
+  __half* f = reinterpret_cast<__half*>(img->fwd);
+  __half* d = reinterpret_cast<__half*>(img->d1);
+  const int gtid = blockIdx.x * 256 + threadIdx.x, gn = gridDim.x * 256;
+  {   // forward image: Wg[t][ci][n] = W2[t][ci][n]
+    constexpr int KT = T * N1;
+    for (int i = gtid; i < N2 * KT; i += gn) {
+      const int n = i / KT, k = i % KT;            // k = t*64 + ci
+      unsigned short hi, lo;
+      fused_hp::split_h(__ldg(w2 + (size_t)k * N2 + n) * sw, hi, lo);
+      f[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
+      f[fused_hp::kmajor16(N2 + n, k, KT)] = __ushort_as_half(lo);
+    }
+  }
+  {   // deltas image: Wg[t][ci = k2][co = n1] = W2[24 - t][n1][k2]
+    constexpr int KT = T * N2;
+    for (int i = gtid; i < N1 * KT; i += gn) {
+      const int n = i / KT, k = i % KT;            // k = t*32 + ci
+      const int t = k / N2, ci = k % N2;
+      unsigned short hi, lo;
+      fused_hp::split_h(__ldg(w2 + ((size_t)(T - 1 - t) * N1 + n) * N2 + ci) * sw, hi, lo);
+      d[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
+      d[fused_hp::kmajor16(N1 + n, k, KT)] = __ushort_as_half(lo);
+    }
+  }
+}
+
+struct Args {
+  const float* in;       // MODE 0: out1 [S][h1][w1][64];  MODE 1: d2 [S][h1-4][w1-4][32]
+  const float* aux;      // MODE 0: b2 [32];               MODE 1: out1 (relu' mask)
+  float* out;            // MODE 0: out2 [S][h1-4][w1-4][32];  MODE 1: d1 [S][h1][w1][64]
+  const unsigned char* wimg;   // packed weight image of this mode
+  const float* sw;       // -> Images::sw
+  const unsigned* in_max;      // bit pattern of max |in|
+  int S, w1, h1;         // samples, extent of the layer-1 map (25 x 25 for 33 x 33 patches)
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
+  using namespace tc;
+  using fused_hp::make_idesc_f16;
+  using fused_hp::mma_f16_ss;
+  using fused_hp::split_h2;
+  using fused_pl::elect_one;
+  using fused_pl::tmem_ld16_nowait;
+  using fused_pl::tmem_ld_wait;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[C::NSLOT], empty[C::NSLOT], done[C::NACC], acc_free[C::NACC];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int P = C::MODE == 0 ? 0 : F - 1;               // zero padding of the input
+  const int iw = C::MODE == 0 ? a.w1 : a.w1 - (F - 1);       // input map extent
+  const int ih = C::MODE == 0 ? a.h1 : a.h1 - (F - 1);
+  const int ow = C::MODE == 0 ? a.w1 - (F - 1) : a.w1;       // output map extent
+  const int oh = C::MODE == 0 ? a.h1 - (F - 1) : a.h1;
+  const int slot_w = a.w1;                                   // virtual-image slot of one sample
+  const long long vw = (long long)a.S * slot_w;              // virtual width
+  const long long X0 = (long long)blockIdx.x * C::M;         // first output column of the strip
+
+  // ---- resident B operand: the packed image, and the bias ------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw + C::oW);
+    for (int i = tid; i < C::W_BYTES / 16; i += C::NT) dst[i] = __ldg(src + i);
+    // plane pads are read by the tensor core (rows beyond the strip, times real weights, into
+    // accumulator rows nobody stores): keep them finite
+    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw + C::oSlots);
+    for (int i = tid; i < C::NSLOT * C::SLOT_BYTES / 4; i += C::NT) z[i] = 0u;
+    if (C::MODE == 0) {
+      float* sB = reinterpret_cast<float*>(smem_raw + C::oBias);
+      for (int i = tid; i < C::COUT; i += C::NT) sB[i] = __ldg(a.aux + i);
+    }
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
+  if (tid == 0) {
+    if (smem_u32(smem_raw) & 127u) __trap();
+    for (int i = 0; i < C::NSLOT; i++) {
+      mbar_init(&full[i], C::N_P * 32);
+      mbar_init(&empty[i], 2);
+    }
+    for (int i = 0; i < C::NACC; i++) {
+      mbar_init(&done[i], 1);
+      mbar_init(&acc_free[i], 128);
+    }
+  }
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const float s_in = scale_for(__uint_as_float(__ldg(a.in_max)));
+  const float sw = __ldg(a.sw);
+
+  // first / last input row that contributes to output row rho (rho = r - dy + P)
+  auto r_first = [&](int rho) { return max(rho - P, 0); };
+  auto r_last = [&](int rho) { return min(rho - P + (F - 1), ih - 1); };
+
+  if (warp >= C::W_P && warp < C::W_P + C::N_P) {
+    // ============================ P: plane producers ==========================================
+    // thread q owns plane entry q = virtual input column X0 - P + q
+    const int q = tid - C::W_P * 32;
+    const long long vin = X0 - P + q;
+    long long base = -1;   // float offset of (sample, row 0, x, channel 0), -1 = zero column
+    if (q < C::PW && vin >= 0 && vin < vw) {
+      const int smp = (int)(vin / slot_w), x = (int)(vin - (long long)smp * slot_w);
+      if (x < iw) base = (((long long)smp * ih) * iw + x) * C::CIN;
+    }
+    const long long row_stride = (long long)iw * C::CIN;
+    uint8_t* my = smem_raw + C::oSlots + q * 16;
+    float4 v[4];
+    auto load = [&](int r, int c) {
+      if (base >= 0) {
+        const float4* p = reinterpret_cast<const float4*>(a.in + base + r * row_stride + c * 16);
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = __ldg(p + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load(0, 0);
+    int it = 0;
+    for (int r = 0; r < ih; r++) {
+      for (int c = 0; c < C::NSLICE; c++, it++) {
+        const int slot = it % C::NSLOT;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          split_h2(v[j].x * s_in, v[j].y * s_in, hi[2 * j], lo[2 * j]);
+          split_h2(v[j].z * s_in, v[j].w * s_in, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        // the loads of the next slice fly while this thread waits for its slot
+        {
+          int nr = r, nc = c + 1;
+          if (nc == C::NSLICE) { nc = 0; nr++; }
+          if (nr < ih) load(nr, nc);
+        }
+        if (it >= C::NSLOT) mbar_wait(&empty[slot], (uint32_t)(((it / C::NSLOT) - 1) & 1));
+        if (q < C::PW) {
+          uint8_t* s = my + slot * C::SLOT_BYTES;
+          *reinterpret_cast<uint4*>(s) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(s + C::PB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(s + 2 * C::PB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(s + 3 * C::PB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&full[slot]);
+      }
+    }
+  } else if (warp >= C::W_I) {
+    // ============================ I0 / I1: MMA issuers ========================================
+    const int me = warp - C::W_I;                       // owns output rows of this parity
+    const uint32_t idesc = make_idesc_f16(C::M, C::COUT);
+    const uint32_t sW = smem_u32(smem_raw + C::oW);
+    const uint32_t sS = smem_u32(smem_raw + C::oSlots);
+    auto adesc = [](uint32_t addr) -> uint64_t {        // K-major, LBO = plane stride, SBO = 128
+      return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((C::PB >> 4) & 0x3FFF) << 16) |
+             ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    };
+    auto wdesc = [](uint32_t addr) -> uint64_t {        // canonical K-major image
+      return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+             ((uint64_t)((C::W_SBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+    };
+    constexpr uint32_t W_LO = (uint32_t)(C::COUT / 8) * C::W_SBO;   // first W_lo row group
+    int it = 0;
+    for (int r = 0; r < ih; r++) {
+      for (int c = 0; c < C::NSLICE; c++, it++) {
+        const int slot = it % C::NSLOT;
+        mbar_wait(&full[slot], (uint32_t)((it / C::NSLOT) & 1));
+        tcgen05_fence_after();
+        const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
+        bool issued = false;
+#pragma unroll 1
+        for (int dy = 0; dy < F; dy++) {
+          const int rho = r - dy + P;
+          if (rho < 0 || rho >= oh || (rho & 1) != me) continue;
+          const int acc = rho % C::NACC;
+          const bool first = (r == r_first(rho)) && c == 0;
+          if (first && rho >= C::NACC) {                 // the accumulator's previous row has left
+            mbar_wait(&acc_free[acc], (uint32_t)(((rho / C::NACC) - 1) & 1));
+            tcgen05_fence_after();
+          }
+          const uint32_t d = tmem + (uint32_t)(acc * C::COUT);
+          if (elect_one()) {
+#pragma unroll
+            for (int dx = 0; dx < F; dx++) {
+              // K-step (tap, slice): 16 halves = 2 core matrices of the image
+              const uint32_t wk = sW + (uint32_t)(((dy * F + dx) * C::CIN + c * 16) / 8) * 128u;
+              const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
+              const uint64_t dwh = wdesc(wk), dwl = wdesc(wk + W_LO);
+              mma_f16_ss(d, dah, dwh, idesc, (first && dx == 0) ? 0u : 1u);
+              mma_f16_ss(d, dah, dwl, idesc, 1u);
+              mma_f16_ss(d, dal, dwh, idesc, 1u);
+            }
+            if (r == r_last(rho) && c == C::NSLICE - 1) mma_commit(&done[acc]);
+          }
+          __syncwarp();
+          issued = true;
+        }
+        if (elect_one()) {
+          if (issued) mma_commit(&empty[slot]);
+          else mbar_arrive(&empty[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================ E: epilogue =================================================
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int m = (warp & 3) * 32 + lane;
+    const long long vout = X0 + m;
+    long long obase = -1;   // float offset of (sample, row 0, x, channel 0) of the output
+    if (vout < vw) {
+      const int smp = (int)(vout / slot_w), x = (int)(vout - (long long)smp * slot_w);
+      if (x < ow) obase = (((long long)smp * oh) * ow + x) * C::COUT;
+    }
+    const long long orow = (long long)ow * C::COUT;
+    const float cs = 1.f / (s_in * sw);
+    const float* sB = reinterpret_cast<const float*>(smem_raw + C::oBias);
+    for (int rho = 0; rho < oh; rho++) {
+      const int acc = rho % C::NACC;
+      mbar_wait(&done[acc], (uint32_t)((rho / C::NACC) & 1));
+      tcgen05_fence_after();
+      float v[C::COUT];
+#pragma unroll
+      for (int g = 0; g < C::COUT / 16; g++)
+        tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::COUT + g * 16), v + g * 16);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&acc_free[acc]);
+      if (obase < 0) continue;
+      float4* o = reinterpret_cast<float4*>(a.out + obase + rho * orow);
+      if (C::MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < C::COUT / 4; j++)
+          o[j] = make_float4(fmaxf(fmaf(v[4 * j], cs, sB[4 * j]), 0.f),
+                             fmaxf(fmaf(v[4 * j + 1], cs, sB[4 * j + 1]), 0.f),
+                             fmaxf(fmaf(v[4 * j + 2], cs, sB[4 * j + 2]), 0.f),
+                             fmaxf(fmaf(v[4 * j + 3], cs, sB[4 * j + 3]), 0.f));
+      } else {
+        const float4* mk = reinterpret_cast<const float4*>(a.aux + obase + rho * orow);
+#pragma unroll
+        for (int j = 0; j < C::COUT / 4; j++) {
+          const float4 g = __ldg(mk + j);
+          o[j] = make_float4(g.x > 0.f ? v[4 * j] * cs : 0.f, g.y > 0.f ? v[4 * j + 1] * cs : 0.f,
+                             g.z > 0.f ? v[4 * j + 2] * cs : 0.f, g.w > 0.f ? v[4 * j + 3] * cs : 0.f);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+using FwdCfg = Cfg<64, 32, 0>;
+using D1Cfg = Cfg<32, 64, 1>;
+
+inline bool supported(int n1, int n2, int f1, int f2, int f3) {
+  (void)f1; (void)f3;
+  return n1 == 64 && n2 == 32 && f2 == F;
+}
+
+// the packed weight images of `w2`, cached per context while w2 is untouched (see
+// srcnn_ctx::c5_*); `cacheable` as for the fused inference operand image
+inline int prepare(srcnn_ctx* ctx, const float* w2, bool cacheable, const Images** out) {
+  if (!ctx->c5_images) SRCNN_CUDA(cudaMalloc(&ctx->c5_images, sizeof(Images)));
+  if (!(cacheable && ctx->c5_valid && ctx->c5_key == w2)) {
+    prepare_kernel<<<16, 256, 0, ctx->stream>>>(w2, reinterpret_cast<Images*>(ctx->c5_images));
+    ctx->launch_count++;
+    ctx->c5_valid = cacheable;
+    ctx->c5_key = w2;
+  }
+  *out = reinterpret_cast<const Images*>(ctx->c5_images);
+  return SRCNN_OK;
+}
+
+// max |x| of n floats (n % 4 == 0, 16-byte aligned) into *slot (zeroed here)
+inline int absmax(srcnn_ctx* ctx, const float* x, size_t n, unsigned* slot) {
+  SRCNN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned), ctx->stream));
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)ctx->sm_count * 8);
+  absmax_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(
+      reinterpret_cast<const float4*>(x), n4, slot);
+  ctx->launch_count++;
+  return SRCNN_OK;
+}
+
+template <class C>
+inline int launch(srcnn_ctx* ctx, const Args& a) {
+  SRCNN_TRY(ensure_func_setup(ctx, conv5_tc_kernel<C>, C::SMEM_BYTES));
+  const long long vw = (long long)a.S * a.w1;
+  const long long strips = (vw + C::M - 1) / C::M;
+  if (strips > 0x7fffffffLL) return fail(SRCNN_EINVAL, "chunk too large for one conv5 launch");
+  conv5_tc_kernel<C><<<(unsigned)strips, C::NT, C::SMEM_BYTES, ctx->stream>>>(a);
+  return SRCNN_OK;
+}
+
+}  // namespace c5
+}  // namespace srcnn

@@ -14,6 +14,8 @@
 #include "deltas_tc.cuh"
 #include "wgrad_tc.cuh"
 #include "wgrad1_fused_tc.cuh"
+#include "conv5_tc.cuh"
+#include "wgrad5_tc.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -89,6 +91,56 @@ inline bool forward_layer(srcnn_ctx* ctx, const float* in, float* out, const flo
   return train::n1_forward(ctx, in, out, W, B, k, n, f, relu, in_w, in_h, S);
 }
 
+// ---- 9-5-5 layer 2 on the tensor cores (conv5_tc.cuh) ----------------------------------------
+// The virtual-image kernels want enough strips of 128 columns to fill the GPU: batches of
+// patch-sized samples (training / validation chunks).  Returns 1 when launched, 0 when the
+// shape is left to the other kernels, < 0 on error.
+inline bool conv5_shape_ok(srcnn_ctx* ctx, int w1, int h1, int S) {
+  static const bool off = std::getenv("SRCNN_C5_IMPL") && std::strcmp(std::getenv("SRCNN_C5_IMPL"), "simt") == 0;
+  if (off || !ctx->wgrad_tc) return false;
+  const long long vw = (long long)S * w1;
+  return w1 >= c5::F && h1 >= c5::F && w1 <= 1024 && h1 <= 4096 && vw >= 32 * 128 &&
+         (long long)S * w1 * h1 * 64 < (1LL << 40);
+}
+inline int conv5_maxes(srcnn_ctx* ctx, c5::Maxes** out) {
+  if (!ctx->c5_maxes) SRCNN_CUDA(cudaMalloc(&ctx->c5_maxes, sizeof(c5::Maxes)));
+  *out = reinterpret_cast<c5::Maxes*>(ctx->c5_maxes);
+  return SRCNN_OK;
+}
+inline int conv5_forward(srcnn_ctx* ctx, const float* in, float* out, const float* W, const float* B,
+                         int k, int n, int f, bool relu, int in_w, int in_h, int S, srcnn_mem wh,
+                         bool cacheable) {
+  if (!(k == 64 && n == 32 && f == c5::F && relu) || !conv5_shape_ok(ctx, in_w, in_h, S)) return 0;
+  if (!aligned16(in) || !aligned16(out)) return 0;
+  const c5::Images* img;
+  ctx->c5_h = wh;
+  SRCNN_TRY(c5::prepare(ctx, W, cacheable, &img));
+  c5::Maxes* mx;
+  SRCNN_TRY(conv5_maxes(ctx, &mx));
+  SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * in_w * in_h * 64, &mx->out1));
+  ctx->c5_max_out1_of = in;
+  c5::Args a{in, B, out, img->fwd, &img->sw, &mx->out1, S, in_w, in_h};
+  SRCNN_TRY(c5::launch<c5::FwdCfg>(ctx, a));
+  return 1;
+}
+// layer-1 deltas below the 5x5 layer 2: target / layer_output are out1-shaped [S][oh][ow][64]
+inline int conv5_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
+                        const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S,
+                        srcnn_mem wh, bool cacheable) {
+  if (!(n_curr == 64 && n_next == 32 && f_next == c5::F) || !conv5_shape_ok(ctx, ow, oh, S)) return 0;
+  if (!aligned16(dn) || !aligned16(lo) || !aligned16(target)) return 0;
+  const c5::Images* img;
+  ctx->c5_h = wh;
+  SRCNN_TRY(c5::prepare(ctx, W, cacheable, &img));
+  c5::Maxes* mx;
+  SRCNN_TRY(conv5_maxes(ctx, &mx));
+  SRCNN_TRY(c5::absmax(ctx, dn, (size_t)S * (ow - 4) * (oh - 4) * 32, &mx->d2));
+  ctx->c5_max_d2_of = dn;
+  c5::Args a{dn, lo, target, img->d1, &img->sw, &mx->d2, S, ow, oh};
+  SRCNN_TRY(c5::launch<c5::D1Cfg>(ctx, a));
+  return 1;
+}
+
 inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
                    const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S) {
   if (ctx->deltas_tc &&
@@ -98,14 +150,26 @@ inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* targ
   return train::n1_deltas(ctx, dn, lo, target, W, n_curr, f_next, n_next, ow, oh, S);
 }
 
-// returns 1 when it launched, 0 when not handled, <0 on error
+// returns 1 when it launched, 0 when not handled, <0 on error.  `maxes_known`: the |x| maxima of
+// `in` (an out1) and `d` (a d2) are already in the context's c5::Maxes (the chunk entries compute
+// them for the layer-2 forward / layer-1 deltas of the same tensors)
 inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float* gw, float* gb,
-                         int n, int k, int f, int ow, int oh, int S) {
+                         int n, int k, int f, int ow, int oh, int S, bool maxes_known = false) {
   if (!aligned16(d) || !aligned16(in)) return 0;   // the register-tiled kernels use LDG.128
   if (ctx->wgrad_tc) {   // layer-1 / layer-2 gradients on the tensor cores
     int count = 0;
     int rc = wgtc::wgrad1_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
     if (rc == 0) rc = wgtc::wgrad2_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
+    if (rc == 0 && n == wg5::Cfg::N && k == wg5::Cfg::K && f == wg5::Cfg::F &&
+        conv5_shape_ok(ctx, ow + f - 1, oh + f - 1, S)) {   // the 5x5 layer 2 of 9-5-5
+      c5::Maxes* mx;
+      SRCNN_TRY(conv5_maxes(ctx, &mx));
+      if (!maxes_known) {
+        SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * (ow + f - 1) * (oh + f - 1) * k, &mx->out1));
+        SRCNN_TRY(c5::absmax(ctx, d, (size_t)S * ow * oh * n, &mx->d2));
+      }
+      rc = wg5::wgrad5_tc(ctx, d, in, mx, n, k, f, ow, oh, S, &count);
+    }
     if (rc < 0) return rc;
     if (rc == 1) {
       const int Mw = f * f * k, total = (Mw + 1) * n;

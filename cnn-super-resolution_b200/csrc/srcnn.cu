@@ -120,6 +120,8 @@ int srcnn_ctx_destroy(srcnn_ctx* ctx) {
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
   if (ctx->splitk_scratch) cudaFree(ctx->splitk_scratch);
   if (ctx->gather_tab) cudaFree(ctx->gather_tab);
+  if (ctx->c5_images) cudaFree(ctx->c5_images);
+  if (ctx->c5_maxes) cudaFree(ctx->c5_maxes);
   if (ctx->band_in) cudaFree(ctx->band_in);
   if (ctx->band_out) cudaFree(ctx->band_out);
   for (int i = 0; i < 2; i++) {
@@ -391,6 +393,15 @@ int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W
   SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f * f * k * n, &pW, "weights"));
   SRCNN_TRY(resolve(ctx, B, sizeof(float) * (size_t)n, &pB, "bias"));
   LaunchScope scope(ctx, SRCNN_K_FORWARD);
+  {
+    const Allocation* wa = ctx->get(W);
+    const int rc5 = fast::conv5_forward(ctx, pin, pout, pW, pB, k, n, f, !skip_relu, in_w, in_h, S,
+                                        W, wa && wa->owned && !wa->exposed);
+    if (rc5 < 0) return rc5;
+    if (rc5 > 0) {
+      return check_launch("forward(conv5 tc)");   // (absmax / image kernels count themselves)
+    }
+  }
   if (fast::forward_layer(ctx, pin, pout, pW, pB, k, n, f, !skip_relu, in_w, in_h, S))
     return check_launch("forward(fast)");
   generic::FwdArgs a{pin, pout, pW, pB, k, n, f, skip_relu ? 0 : 1, in_w, in_h, ow, oh, S};
@@ -455,6 +466,13 @@ int srcnn_deltas(srcnn_ctx* ctx, srcnn_mem deltas_next, srcnn_mem layer_output,
   ctx->note_write(target);
   SRCNN_TRY(resolve(ctx, W, sizeof(float) * (size_t)f_next * f_next * n_curr * n_next, &pW, "next layer weights"));
   LaunchScope scope(ctx, SRCNN_K_DELTAS);
+  {
+    const Allocation* wa = ctx->get(W);
+    const int rc5 = fast::conv5_deltas(ctx, pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h,
+                                       S, W, wa && wa->owned && !wa->exposed);
+    if (rc5 < 0) return rc5;
+    if (rc5 > 0) return check_launch("deltas(conv5 tc)");
+  }
   if (fast::deltas(ctx, pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h, S))
     return check_launch("deltas(fast)");
   generic::DeltaArgs a{pdn, plo, pt, pW, n_curr, f_next, n_next, out_w, out_h, nw, nh, S};
@@ -479,7 +497,9 @@ int srcnn_backpropagate(srcnn_ctx* ctx, srcnn_mem deltas, srcnn_mem layer_input,
   ctx->note_write(grad_w);
   ctx->note_write(grad_b);
   LaunchScope scope(ctx, SRCNN_K_BACKPROPAGATE, 2);
-  int rc_fast = fast::backpropagate(ctx, pd, pin, pgw, pgb, n, k, f, out_w, out_h, S);
+  int rc_fast = fast::backpropagate(ctx, pd, pin, pgw, pgb, n, k, f, out_w, out_h, S,
+                                    ctx->c5_maxes_known && ctx->c5_max_out1_of == pin &&
+                                        ctx->c5_max_d2_of == pd);
   if (rc_fast < 0) return rc_fast;
   if (rc_fast > 0) return check_launch("backpropagate(fast)");
   const int Mw = f * f * k, M = Mw + 1;
@@ -653,6 +673,7 @@ int srcnn_invalidate_params(srcnn_ctx* ctx) {
   SRCNN_ENTER(ctx);
   ctx->write_gen++;
   ctx->hp_cache_valid = false;
+  ctx->c5_valid = false;
   return SRCNN_OK;
 }
 
@@ -1082,6 +1103,13 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
                    int S, const Work& wk) {
   const Dims d = net_dims(net, w, h);
   int rc = SRCNN_OK;
+  // 9-5-5: the maxima the layer-2 forward and the layer-1 deltas measure (conv5_tc.cuh) stay
+  // valid for the layer-2 gradient of the same chunk
+  ctx->c5_max_out1_of = ctx->c5_max_d2_of = nullptr;
+  struct KnownScope {
+    srcnn_ctx* c;
+    ~KnownScope() { c->c5_maxes_known = false; }
+  } known_scope{ctx};
   // forward, keeping the activations (ConfigBasedDataPipeline.cpp:200-241)
   int fused_fwd = 0;
   if (fast::fused_train_supported(ctx, net->n1, net->n2, net->f1, net->f2, net->f3))
@@ -1105,7 +1133,9 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
   if (!fused_b1 && rc == SRCNN_OK) rc = srcnn_deltas(ctx, wk.d2, wk.out1, wk.d1, net->w[1], net->n1, net->f2, net->n2, d.w1, d.h1, S);
   // gradients (ConfigBasedDataPipeline.cpp:287-320)
   if (!fused_b3 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d3, wk.out2, net->grad_w[2], net->grad_b[2], 1, net->n2, net->f3, d.w3, d.h3, S);
+  ctx->c5_maxes_known = ctx->c5_max_out1_of != nullptr && ctx->c5_max_d2_of != nullptr;
   if (rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d2, wk.out1, net->grad_w[1], net->grad_b[1], net->n2, net->n1, net->f2, d.w2, d.h2, S);
+  ctx->c5_maxes_known = false;
   if (!fused_b1 && rc == SRCNN_OK) rc = srcnn_backpropagate(ctx, wk.d1, in, net->grad_w[0], net->grad_b[0], net->n1, 1, net->f1, d.w1, d.h1, S);
   return rc;
 }

@@ -185,11 +185,41 @@ def test_deltas_vs_oracle(ctx, port, shape):
                                port.deltas(dn, lo, W, nc, fn, nn, ow, oh, S), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("w1,h1,S", [(25, 25, 170), (30, 19, 150), (25, 25, 333)])
+def test_conv5_tensor_core_kernels_vs_oracle(ctx, port, w1, h1, S):
+    """The 9-5-5 network's layer 2 on the tensor cores (conv5_tc.cuh): forward 64 -> 32 and the
+    layer-1 deltas, as virtual-image implicit GEMMs with FP16-split operands, at sample counts
+    that take that path (>= 32 strips of 128 columns).  reference:
+    src/kernel/layer_uber_kernel.cl:36-96, src/kernel/layer_deltas.cl:42-127."""
+    rng = np.random.default_rng(1000 * w1 + S)
+    port.set_num_threads(len(os.sched_getaffinity(0)))
+    k, n, f = 64, 32, 5
+    x = np.maximum(rng.normal(0, 1, (S, h1, w1, k)), 0).astype(np.float32)       # an out1: >= 0
+    W = rng.normal(0, 1.0 / np.sqrt(f * f * k), f * f * k * n).astype(np.float32)
+    B = rng.normal(0, 0.1, n).astype(np.float32)
+    n0 = ctx.launch_count()
+    got = gpu_forward(ctx, x, W, B, k, n, f, False, w1, h1, S)
+    assert ctx.launch_count() - n0 >= 2, "the tensor-core path (absmax + contraction) did not run"
+    np.testing.assert_allclose(got, port.forward(x, W, B, k, n, f, False, w1, h1, S),
+                               rtol=RTOL, atol=ATOL)
+    # deltas of layer 1 from the deltas of layer 2 (tiny values, like real ones)
+    dn = (rng.normal(0, 1, (S, h1 - 4, w1 - 4, n)) * 3e-4).astype(np.float32)
+    n0 = ctx.launch_count()
+    got = gpu_deltas(ctx, dn, x, W, k, f, n, w1, h1, S)
+    assert ctx.launch_count() - n0 >= 2, "the tensor-core path (absmax + contraction) did not run"
+    exp = port.deltas(dn, x, W, k, f, n, w1, h1, S)
+    np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL * 3e-4)
+    assert np.abs(exp).max() > 1e-5
+
+
 BP_SHAPES = [
     # n, k, f, out_w, out_h, S
     (64, 1, 9, 25, 25, 5), (32, 64, 1, 25, 25, 5), (1, 32, 5, 21, 21, 5), (32, 64, 5, 21, 21, 2),
     (128, 1, 9, 12, 9, 2), (64, 128, 1, 10, 10, 2), (16, 32, 1, 8, 8, 3),
     (4, 3, 3, 5, 4, 3), (3, 2, 3, 3, 3, 1), (1, 1, 1, 1, 1, 1), (70, 3, 1, 9, 2, 2),
+    # the 5x5 layer 2 of 9-5-5 at sample counts that take the MN-major tensor-core kernel
+    # (wgrad5_tc.cuh)
+    (32, 64, 5, 21, 21, 170), (32, 64, 5, 26, 15, 150),
 ]
 
 
@@ -197,6 +227,7 @@ BP_SHAPES = [
 def test_backpropagate_vs_oracle(ctx, port, shape):
     n, k, f, ow, oh, S = shape
     rng = np.random.default_rng(hash(shape) % 2**32)
+    port.set_num_threads(len(os.sched_getaffinity(0)))
     d = rng.normal(0, 1, (S, oh, ow, n)).astype(np.float32)
     li = rng.normal(0, 1, (S, oh + f - 1, ow + f - 1, k)).astype(np.float32)
     gw0 = rng.normal(0, 1, f * f * k * n).astype(np.float32)

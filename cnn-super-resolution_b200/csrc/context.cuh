@@ -113,6 +113,7 @@ struct srcnn_ctx {
   const void* c5_max_out1_of = nullptr;
   const void* c5_max_d2_of = nullptr;
   bool c5_maxes_known = false;
+  const void* c5_l1_max_of = nullptr;   // out1 whose maximum the layer-1-only kernel recorded
   // per-context (= per-device) one-time kernel setup: opt-in dynamic shared memory sizes and
   // occupancy queries, keyed by the kernel's address.  cudaFuncSetAttribute is per DEVICE, so a
   // process-wide flag would leave a second context on another GPU unconfigured.

@@ -47,18 +47,20 @@ namespace c5 {
 
 // per-chunk device scalars: bit patterns of max |x| (non-negative floats order like unsigned)
 struct Maxes {
-  unsigned out1, d2;
+  unsigned out1, d2, in;
 };
 
 // |x| maximum of a tensor, as an unsigned bit pattern (atomicMax); `out` must be zeroed first
 __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, size_t n4,
-                                                     unsigned* out) {
+                                                     size_t n, unsigned* out) {
   float m = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(x + i);
     m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
+  if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4)   // the last n % 4 floats
+    m = fmaxf(m, fabsf(__ldg(reinterpret_cast<const float*>(x) + 4 * n4 + threadIdx.x)));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
@@ -300,34 +302,53 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
         mbar_wait(&full[slot], (uint32_t)((it / C::NSLOT) & 1));
         tcgen05_fence_after();
         const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
-        bool issued = false;
+        // the output rows of this issuer that input row r feeds: at most 3 of the 5 taps dy
+        int nrow = 0;
+        uint32_t acc_d[3], w_dy[3];
+        bool first_k[3], last_k[3];
+        int acc_i[3];
 #pragma unroll 1
         for (int dy = 0; dy < F; dy++) {
           const int rho = r - dy + P;
           if (rho < 0 || rho >= oh || (rho & 1) != me) continue;
           const int acc = rho % C::NACC;
           const bool first = (r == r_first(rho)) && c == 0;
-          if (first && rho >= C::NACC) {                 // the accumulator's previous row has left
+          if (first && rho >= C::NACC)                  // the accumulator's previous row has left
             mbar_wait(&acc_free[acc], (uint32_t)(((rho / C::NACC) - 1) & 1));
-            tcgen05_fence_after();
-          }
-          const uint32_t d = tmem + (uint32_t)(acc * C::COUT);
-          if (elect_one()) {
-#pragma unroll
-            for (int dx = 0; dx < F; dx++) {
-              // K-step (tap, slice): 16 halves = 2 core matrices of the image
-              const uint32_t wk = sW + (uint32_t)(((dy * F + dx) * C::CIN + c * 16) / 8) * 128u;
-              const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
-              const uint64_t dwh = wdesc(wk), dwl = wdesc(wk + W_LO);
-              mma_f16_ss(d, dah, dwh, idesc, (first && dx == 0) ? 0u : 1u);
-              mma_f16_ss(d, dah, dwl, idesc, 1u);
-              mma_f16_ss(d, dal, dwh, idesc, 1u);
-            }
-            if (r == r_last(rho) && c == C::NSLICE - 1) mma_commit(&done[acc]);
-          }
-          __syncwarp();
-          issued = true;
+          acc_i[nrow] = acc;
+          acc_d[nrow] = tmem + (uint32_t)(acc * C::COUT);
+          // first K-step (tap (dy, 0), slice c) of the weight image: 16 halves = 2 core matrices
+          w_dy[nrow] = sW + (uint32_t)(((dy * F) * C::CIN + c * 16) / 8) * 128u;
+          first_k[nrow] = first;
+          last_k[nrow] = (r == r_last(rho)) && c == C::NSLICE - 1;
+          nrow++;
         }
+        tcgen05_fence_after();
+        const bool issued = nrow > 0;
+        if (issued && elect_one()) {
+          // consecutive MMAs go to DIFFERENT accumulators: back-to-back MMAs into one accumulator
+          // serialise on its read-modify-write (measured: 63-83 cycles per MMA instead of 40-48)
+#pragma unroll
+          for (int dx = 0; dx < F; dx++) {
+            const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
+            constexpr uint32_t W_DX = (uint32_t)(C::CIN / 8) * 128u;   // next tap of the image
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                if (k < nrow) {
+                  const uint32_t wk = w_dy[k] + dx * W_DX + (p == 1 ? W_LO : 0u);
+                  mma_f16_ss(acc_d[k], p == 2 ? dal : dah, wdesc(wk), idesc,
+                             (first_k[k] && dx == 0 && p == 0) ? 0u : 1u);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            if (k < nrow && last_k[k]) mma_commit(&done[acc_i[k]]);
+        }
+        __syncwarp();
         if (elect_one()) {
           if (issued) mma_commit(&empty[slot]);
           else mbar_arrive(&empty[slot]);
@@ -407,13 +428,13 @@ inline int prepare(srcnn_ctx* ctx, const float* w2, bool cacheable, const Images
   return SRCNN_OK;
 }
 
-// max |x| of n floats (n % 4 == 0, 16-byte aligned) into *slot (zeroed here)
+// max |x| of n floats (16-byte aligned) into *slot (zeroed here)
 inline int absmax(srcnn_ctx* ctx, const float* x, size_t n, unsigned* slot) {
   SRCNN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned), ctx->stream));
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)ctx->sm_count * 8);
   absmax_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(
-      reinterpret_cast<const float4*>(x), n4, slot);
+      reinterpret_cast<const float4*>(x), n4, n, slot);
   ctx->launch_count++;
   return SRCNN_OK;
 }

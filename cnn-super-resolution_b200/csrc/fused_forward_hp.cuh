@@ -96,6 +96,7 @@ struct ScaleVals {
   float c3;       // 1 / (s2 * sw3):  D3 -> Q
   float inv_s1, inv_s2;
   int ok;         // 1: the input is inside the FP16 domain, this kernel runs; 0: the TF32 one
+  float in_lim;   // |input| must stay below this (64 unless the scale was derived from the data)
 };
 // what hp_prepare_kernel leaves for the main kernel: the scales and the ready-made shared-memory
 // image of the B operands (scaled, split, in the canonical K-major layout) and scaled biases, so
@@ -189,7 +190,11 @@ __device__ __forceinline__ float pow2_scale(float bound) {   // 2^14 / pow2ceil(
   frexpf(bound, &e);                 // bound = f * 2^e, f in [0.5, 1)
   return ldexpf(1.f, 14 - e);
 }
-__global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* sc) {
+// `in_max` (may be null): bit pattern of the largest |input| of the launch, measured on the
+// device -- the input scale then follows the data (no domain restriction, no fallback); used by
+// the layer-1-only launches, where a.pw2 / a.pw3 are null.
+__global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* sc,
+                                                         const unsigned* in_max = nullptr) {
   // the parameters are staged in shared memory with coalesced loads first: the column sums
   // below would otherwise be chains of dependent global loads (13 us instead of ~3)
   __shared__ float sw1[Cfg::F1 * Cfg::F1 * Cfg::N1];   // |W1| [tap][n]
@@ -212,14 +217,27 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
     sw1[i] = w;
     v1 = fmaxf(v1, w);
   }
+  const bool l1only = a.pw2 == nullptr;
   for (int i = tid; i < Cfg::N1 * Cfg::N2; i += 256) {
-    const float w = fabsf(__ldg(a.pw2 + i));
+    const float w = l1only ? 0.f : fabsf(__ldg(a.pw2 + i));
     sw2[i] = w;
     v2 = fmaxf(v2, w);
   }
-  for (int i = tid; i < Cfg::QP * Cfg::N2; i += 256) v3 = fmaxf(v3, fabsf(__ldg(a.pw3 + i)));
+  if (!l1only)
+    for (int i = tid; i < Cfg::QP * Cfg::N2; i += 256) v3 = fmaxf(v3, fabsf(__ldg(a.pw3 + i)));
   const float b1v = tid < Cfg::N1 ? fabsf(__ldg(a.pb1 + tid)) : 0.f;
-  const float b2v = tid < Cfg::N2 ? fabsf(__ldg(a.pb2 + tid)) : 0.f;
+  const float b2v = (tid < Cfg::N2 && !l1only) ? fabsf(__ldg(a.pb2 + tid)) : 0.f;
+  // input range: 64 (fixed: a row-band partition then reproduces the single launch bit for
+  // bit), or the power of two above the measured maximum
+  float in_lim = kInMax;
+  if (in_max) {
+    const float mx = __uint_as_float(__ldg(in_max));
+    if (mx > 0.f && mx < 1e30f) {
+      int e;
+      frexpf(mx, &e);
+      in_lim = ldexpf(1.f, e);      // > mx
+    }
+  }
   const float m1 = block_max(v1);
   const float m2 = block_max(v2);
   const float m3 = block_max(v3);
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
       s1 += sw1[(t + 1) * Cfg::N1 + tid];
       s2 += sw1[(t + 2) * Cfg::N1 + tid];
     }
-    v = (s0 + s1 + s2) * kInMax + b1v;
+    v = (s0 + s1 + s2) * in_lim + b1v;
   }
   const float bound1 = block_max(v);
   v = 0.f;
@@ -248,7 +266,8 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
   __shared__ ScaleVals sv;
   if (tid == 0) {
     ScaleVals s;
-    s.sx = 512.f;   // 64 * 512 = 2^15
+    s.sx = 32768.f / in_lim;   // in_lim * sx = 2^15 (512 for the fixed range of 64)
+    s.in_lim = in_lim;
     s.sw1 = pow2_scale(m1);
     s.sw2 = pow2_scale(m2);
     s.sw3 = pow2_scale(m3);
@@ -280,6 +299,10 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
     split_h(t >= 0 ? __ldg(a.pw1 + t * C::N1 + (n & (C::N1 - 1))) * sv.sw1 : 0.f, hi, lo);
     gW1[kmajor16(n, k, C::K1)] = __ushort_as_half(n < C::N1 ? hi : lo);
   }
+  if (l1only) {
+    for (int i = gtid; i < C::N1; i += gn) gB1[i] = __ldg(a.pb1 + i) * sv.s1;
+    return;
+  }
   for (int i = gtid; i < 2 * C::N2 * C::K2; i += gn) {
     const int n = i / C::K2, k = i % C::K2;
     unsigned short hi, lo;
@@ -298,7 +321,10 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(fused::Args a, Scales* 
 }
 
 // ---------------------------------------------------------------------------- main kernel ----
-template <bool BATCH>
+// L1ONLY (with BATCH): only layer 1 runs and out1 is its result -- the forward of the first
+// layer of a 9-5-5 training chunk (a.w3 / a.h3 / rpc are those of the 9-1-5 geometry: one tile
+// per out1 row).  The layer-2/3 roles idle; E1 releases D1 itself (bar2) and records max |out1|.
+template <bool BATCH, bool L1ONLY = false>
 __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Args a, int rpc,
                                                                       BatchExt bx,
                                                                       const Scales* scales,
@@ -336,7 +362,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   // pad entries of the planes are read by the tensor core (times a zero weight): keep them finite
   for (int i = tid; i < 2 * (C::RO + C::RH) * C::PB / 4; i += C::NT)
     reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
-  const float b3 = __ldg(a.pb3);
+  const float b3 = L1ONLY ? 0.f : __ldg(a.pb3);
 
   if (warp == 0) tmem_alloc(&tmem_slot, C::TMEM_COLS);
   if (tid == 0) {
@@ -348,7 +374,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     for (int i = 0; i < 2; i++) {
       mbar_init(&bar1[i], 1);
       mbar_init(&a2_full[i], C::N_E1 * 32);
-      mbar_init(&bar2[i], 1);
+      mbar_init(&bar2[i], L1ONLY ? C::N_E1 * 32 : 1);
       mbar_init(&a3_full[i], 128);
       mbar_init(&bar3[i], 1);
       mbar_init(&d3_free[i], 128);
@@ -395,8 +421,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     };
     // the domain check happens where a value is consumed, never where it is loaded: the loads
     // of the next two rows stay in flight across a tile (HBM latency > one tile period)
+    const float in_lim = sc.in_lim * 0.999f;
     auto in_domain = [&](float x) {
-      if (!(fabsf(x) < kInMax * 0.999f)) *fallback = 1;   // outside the FP16 domain (or NaN)
+      if (!(fabsf(x) < in_lim)) *fallback = 1;   // outside the FP16 domain (or NaN)
     };
     unsigned short hh[7], hl[7];   // rows r-7 .. r-1 of this column
     {
@@ -496,6 +523,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       __syncwarp();
       PL_EV(t, 1)
     }
+  } else if (L1ONLY && warp >= C::W_E2) {
+    // layer-1-only launch: the layer-2 / layer-3 roles have nothing to do
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
     const uint32_t idesc_hi = make_idesc_f16(C::M, 2 * C::N2);
@@ -561,6 +590,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     const int w1_row = bx.pw - (C::F1 - 1);
     float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + warp * (32 * C::SP);
+    float act_max = 0.f;   // L1ONLY: largest scaled activation this thread stored
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
       if (warp == 0) PL_EV(b, 2)
@@ -574,6 +604,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
       }
       tmem_ld_wait();
+      if (L1ONLY) {                 // D1[b&1] may be overwritten by MMA-1(b+2)
+        tcgen05_fence_before();
+        mbar_arrive(&bar2[b & 1]);
+      }
 #pragma unroll
       for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
         const int g = g0 + gl;
@@ -582,11 +616,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
 #pragma unroll
         for (int j = 0; j < 16; j++)
           act[j] = fmaxf(fmaf(va[gl][j] + vb[gl][j], sc.c1s, sB1[g * 16 + j]), 0.f);
+        if (L1ONLY) {
+          if (pix1 >= 0) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-        const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
-        tmem_st8u(d1 + col, hi);
-        tmem_st8u(d1 + C::N1 + col, lo);
+            for (int j = 0; j < 16; j++) act_max = fmaxf(act_max, act[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
+          const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
+          tmem_st8u(d1 + col, hi);
+          tmem_st8u(d1 + C::N1 + col, lo);
+        }
         if (keep1) {
           float4* q = reinterpret_cast<float4*>(st1 + lane * C::SP + gl * 16);
 #pragma unroll
@@ -595,9 +636,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
                                act[4 * j + 2] * sc.inv_s1, act[4 * j + 3] * sc.inv_s1);
         }
       }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&a2_full[b & 1]);
+      if (!L1ONLY) {
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&a2_full[b & 1]);
+      }
       if (keep1) {
         // 8 lanes per pixel: every store instruction writes four full 128-byte lines (one
         // 64-byte run per thread touched 32 lines per instruction and bound the whole kernel)
@@ -614,6 +657,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         __syncwarp();
       }
       if (warp == 0) PL_EV(b, 3)
+    }
+    if (L1ONLY && bx.out1_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) act_max = fmaxf(act_max, __shfl_xor_sync(0xffffffffu, act_max, o));
+      if (lane == 0 && act_max > 0.f) atomicMax(bx.out1_max, __float_as_uint(act_max * sc.inv_s1));
     }
   } else if (warp < C::W_E3) {
     // ============================ E2: A3 = split(relu(out2) * s2), in place ================
@@ -759,6 +807,9 @@ inline int configure() {
   SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)Cfg::SMEM_BYTES_KEEP));
+  SRCNN_CUDA(cudaFuncSetAttribute(forward_fused_hp_kernel<true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::SMEM_BYTES_KEEP));
   return SRCNN_OK;
 }
 
@@ -829,6 +880,35 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
     fused_pl::forward_fused_pl_kernel<false>
         <<<grid, fused_pl::Cfg::NT, fused_pl::Cfg::SMEM_BYTES, ctx->stream>>>(a, rpc, bx);
   }
+  return SRCNN_OK;
+}
+
+// Layer 1 alone (9x9, 1 -> 64, ReLU) of a batch of S samples of pw x ph pixels, out1 kept: the
+// first layer of a 9-5-5 training chunk.  `in_max` holds the measured max |input| (the operand
+// scale follows it: no input-range restriction), `out1_max` receives max |out1| (zeroed here).
+inline int launch_l1only(srcnn_ctx* ctx, const float* in, float* out1, const float* w1,
+                         const float* b1, int pw, int ph, int S, const unsigned* in_max,
+                         unsigned* out1_max) {
+  Scales* slot;
+  unsigned* ws;
+  SRCNN_TRY(scale_slot(ctx, &slot, &ws));
+  const int pad = Cfg::F1 + Cfg::F3 - 2;   // geometry of the 9-1-5 kernel: one tile per out1 row
+  fused::Args v{in, nullptr, w1, b1, nullptr, nullptr, nullptr, nullptr, S * pw, ph, S * pw - pad, ph - pad};
+  hp_prepare_kernel<<<8, 256, 0, ctx->stream>>>(v, slot, in_max);
+  int* fallback = reinterpret_cast<int*>(ws);
+  SRCNN_CUDA(cudaMemsetAsync(fallback, 0, sizeof(int), ctx->stream));
+  SRCNN_CUDA(cudaMemsetAsync(out1_max, 0, sizeof(unsigned), ctx->stream));
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  BatchExt bx{};
+  bx.out1 = out1;
+  bx.S = S;
+  bx.pw = pw;
+  bx.ph = ph;
+  bx.out1_max = out1_max;
+  const int rpc = fused_pl::rows_per_cta(v.w3, v.h3, 1, sms);
+  dim3 grid((v.w3 + Cfg::OW3 - 1) / Cfg::OW3, (v.h3 + rpc - 1) / rpc, 1);
+  forward_fused_hp_kernel<true, true>
+      <<<grid, Cfg::NT, Cfg::SMEM_BYTES_KEEP, ctx->stream>>>(v, rpc, bx, slot, fallback);
   return SRCNN_OK;
 }
 

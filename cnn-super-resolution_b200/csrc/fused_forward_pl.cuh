@@ -165,6 +165,9 @@ struct BatchExt {
   // when set: run only if *gate != 0 (the FP16-split kernel of fused_forward_hp.cuh found the
   // input outside its domain and left the launch to this kernel)
   const int* gate;
+  // layer-1-only launches of the FP16-split kernel (9-5-5 training forward): |out1| maximum,
+  // as an unsigned bit pattern (atomicMax), for the layer-2 kernel's operand scale
+  unsigned* out1_max;
 };
 
 template <bool BATCH>

@@ -109,7 +109,7 @@ inline int conv5_maxes(srcnn_ctx* ctx, c5::Maxes** out) {
 }
 inline int conv5_forward(srcnn_ctx* ctx, const float* in, float* out, const float* W, const float* B,
                          int k, int n, int f, bool relu, int in_w, int in_h, int S, srcnn_mem wh,
-                         bool cacheable) {
+                         bool cacheable, bool max_known = false) {
   if (!(k == 64 && n == 32 && f == c5::F && relu) || !conv5_shape_ok(ctx, in_w, in_h, S)) return 0;
   if (!aligned16(in) || !aligned16(out)) return 0;
   const c5::Images* img;
@@ -117,12 +117,28 @@ inline int conv5_forward(srcnn_ctx* ctx, const float* in, float* out, const floa
   SRCNN_TRY(c5::prepare(ctx, W, cacheable, &img));
   c5::Maxes* mx;
   SRCNN_TRY(conv5_maxes(ctx, &mx));
-  SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * in_w * in_h * 64, &mx->out1));
+  if (!max_known) SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * in_w * in_h * 64, &mx->out1));
   ctx->c5_max_out1_of = in;
   c5::Args a{in, B, out, img->fwd, &img->sw, &mx->out1, S, in_w, in_h};
   SRCNN_TRY(c5::launch<c5::FwdCfg>(ctx, a));
   return 1;
 }
+// layer 1 of a 9-5-5 training chunk through the FP16-split tensor-core kernel in its
+// layer-1-only mode; leaves max |out1| in the context's c5::Maxes.  Returns 1 when launched.
+inline int conv5_layer1(srcnn_ctx* ctx, const float* in, float* out1, const float* w1,
+                        const float* b1, int n1, int f1, int w, int h, int S) {
+  if (ctx->fused_impl != 4 || n1 != fused_hp::Cfg::N1 || f1 != fused_hp::Cfg::F1) return 0;
+  if (!conv5_shape_ok(ctx, w - f1 + 1, h - f1 + 1, S)) return 0;
+  if (w > 512 || (long long)S * w >= (1LL << 30) || (long long)S * w * h >= (1LL << 31)) return 0;
+  if (!aligned16(in) || !aligned16(out1)) return 0;
+  c5::Maxes* mx;
+  SRCNN_TRY(conv5_maxes(ctx, &mx));
+  SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * w * h, &mx->in));
+  SRCNN_TRY(fused_hp::launch_l1only(ctx, in, out1, w1, b1, w, h, S, &mx->in, &mx->out1));
+  ctx->launch_count += 2;
+  return 1;
+}
+
 // layer-1 deltas below the 5x5 layer 2: target / layer_output are out1-shaped [S][oh][ow][64]
 inline int conv5_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* target,
                         const float* W, int n_curr, int f_next, int n_next, int ow, int oh, int S,

@@ -396,7 +396,8 @@ int srcnn_forward_layer(srcnn_ctx* ctx, srcnn_mem in, srcnn_mem out, srcnn_mem W
   {
     const Allocation* wa = ctx->get(W);
     const int rc5 = fast::conv5_forward(ctx, pin, pout, pW, pB, k, n, f, !skip_relu, in_w, in_h, S,
-                                        W, wa && wa->owned && !wa->exposed);
+                                        W, wa && wa->owned && !wa->exposed,
+                                        ctx->c5_l1_max_of == pin);
     if (rc5 < 0) return rc5;
     if (rc5 > 0) {
       return check_launch("forward(conv5 tc)");   // (absmax / image kernels count themselves)
@@ -1115,8 +1116,31 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
   if (fast::fused_train_supported(ctx, net->n1, net->n2, net->f1, net->f2, net->f3))
     rc = forward_train_fused_entry(ctx, net, in, wk, w, h, S, &fused_fwd);
   if (!fused_fwd) {
-    if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, in, wk.out1, net->w[0], net->b[0], 1, net->n1, net->f1, 0, w, h, S);
+    // 9-5-5: layer 1 through the FP16-split tensor-core kernel in its layer-1-only mode (it also
+    // records max |out1| for the layer-2 kernel), layer 2 through conv5_tc
+    int l1_tc = 0;
+    ctx->c5_l1_max_of = nullptr;
+    if (rc == SRCNN_OK && c5::supported(net->n1, net->n2, net->f1, net->f2, net->f3)) {
+      const float *pin, *w1, *b1;
+      float* o1;
+      rc = resolve(ctx, in, sizeof(float) * (size_t)S * w * h, &pin, "input luma");
+      if (rc == SRCNN_OK) rc = resolve(ctx, wk.out1, sizeof(float) * (size_t)S * d.w1 * d.h1 * net->n1, &o1, "out1");
+      if (rc == SRCNN_OK) rc = resolve(ctx, net->w[0], sizeof(float) * (size_t)net->f1 * net->f1 * net->n1, &w1, "w1");
+      if (rc == SRCNN_OK) rc = resolve(ctx, net->b[0], sizeof(float) * (size_t)net->n1, &b1, "b1");
+      if (rc == SRCNN_OK) {
+        LaunchScope scope(ctx, SRCNN_K_FORWARD, 2);
+        l1_tc = fast::conv5_layer1(ctx, pin, o1, w1, b1, net->n1, net->f1, w, h, S);
+        if (l1_tc < 0) rc = l1_tc;
+        if (l1_tc <= 0) scope.n_launches = 0;
+        if (l1_tc > 0) {
+          rc = check_launch("forward(layer 1, tc)");
+          ctx->c5_l1_max_of = o1;
+        }
+      }
+    }
+    if (l1_tc <= 0 && rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, in, wk.out1, net->w[0], net->b[0], 1, net->n1, net->f1, 0, w, h, S);
     if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out1, wk.out2, net->w[1], net->b[1], net->n1, net->n2, net->f2, 0, d.w1, d.h1, S);
+    ctx->c5_l1_max_of = nullptr;
     if (rc == SRCNN_OK) rc = srcnn_forward_layer(ctx, wk.out2, wk.out3, net->w[2], net->b[2], net->n2, 1, net->f3, 1, d.w2, d.h2, S);
   }
   // last-layer delta, layer-2 deltas and layer-3 gradients share one pass over out2 when the

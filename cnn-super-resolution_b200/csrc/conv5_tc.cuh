@@ -86,13 +86,19 @@ struct Cfg {
   static constexpr int PB = PW * 16;                  // bytes per plane
   static constexpr int SLOT_BYTES = 4 * PB;           // hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1
   static constexpr int NSLOT = 3, NACC = 7;
+  // STACK: A_hi x [W_hi ; W_lo] as ONE N = 2*COUT instruction (its two halves land in separate
+  // accumulator columns, the epilogue adds them) + A_lo x W_hi: two A-tile fetches per K-step
+  // instead of three.  The A tile (128 rows at a 16-byte shifted base: every 128-byte core matrix
+  // straddles two shared-memory lines) is the expensive operand.  Needs 2*COUT columns per row.
+  static constexpr bool STACK = 2 * NACC * COUT <= 512;
+  static constexpr int ACCW = STACK ? 2 * COUT : COUT;
   static constexpr int W_BYTES = 2 * COUT * KT * 2;   // [W_hi rows ; W_lo rows][KT] halves
   static constexpr int W_SBO = 128 * (KT / 8);        // bytes between 8-row groups of the image
   static constexpr int oW = 0, oSlots = W_BYTES, oBias = oSlots + NSLOT * SLOT_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)oBias + COUT * 4;
   static constexpr int W_E = 0, W_P = 4, N_P = 5, W_I = W_P + N_P, NT = (W_I + 2) * 32;
-  static constexpr uint32_t TMEM_COLS = NACC * COUT <= 256 ? 256 : 512;
-  static_assert(NACC * COUT <= 512, "accumulators must fit tensor memory");
+  static constexpr uint32_t TMEM_COLS = NACC * ACCW <= 256 ? 256 : 512;
+  static_assert(NACC * ACCW <= 512, "accumulators must fit tensor memory");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0, "channel counts");
   static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory");
 };
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     // ============================ I0 / I1: MMA issuers ========================================
     const int me = warp - C::W_I;                       // owns output rows of this parity
     const uint32_t idesc = make_idesc_f16(C::M, C::COUT);
+    const uint32_t idesc2 = make_idesc_f16(C::M, 2 * C::COUT);   // stacked [W_hi ; W_lo]
     const uint32_t sW = smem_u32(smem_raw + C::oW);
     const uint32_t sS = smem_u32(smem_raw + C::oSlots);
     auto adesc = [](uint32_t addr) -> uint64_t {        // K-major, LBO = plane stride, SBO = 128
@@ -302,53 +309,42 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
         mbar_wait(&full[slot], (uint32_t)((it / C::NSLOT) & 1));
         tcgen05_fence_after();
         const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
-        // the output rows of this issuer that input row r feeds: at most 3 of the 5 taps dy
-        int nrow = 0;
-        uint32_t acc_d[3], w_dy[3];
-        bool first_k[3], last_k[3];
-        int acc_i[3];
+        // MMAs into one accumulator stay consecutive: interleaving the rows of a slice across
+        // accumulators measured 30-40 % SLOWER (r2c: 829 vs 599 us forward, 580 vs 475 us deltas)
+        bool issued = false;
 #pragma unroll 1
         for (int dy = 0; dy < F; dy++) {
           const int rho = r - dy + P;
           if (rho < 0 || rho >= oh || (rho & 1) != me) continue;
           const int acc = rho % C::NACC;
           const bool first = (r == r_first(rho)) && c == 0;
-          if (first && rho >= C::NACC)                  // the accumulator's previous row has left
+          if (first && rho >= C::NACC) {                 // the accumulator's previous row has left
             mbar_wait(&acc_free[acc], (uint32_t)(((rho / C::NACC) - 1) & 1));
-          acc_i[nrow] = acc;
-          acc_d[nrow] = tmem + (uint32_t)(acc * C::COUT);
-          // first K-step (tap (dy, 0), slice c) of the weight image: 16 halves = 2 core matrices
-          w_dy[nrow] = sW + (uint32_t)(((dy * F) * C::CIN + c * 16) / 8) * 128u;
-          first_k[nrow] = first;
-          last_k[nrow] = (r == r_last(rho)) && c == C::NSLICE - 1;
-          nrow++;
-        }
-        tcgen05_fence_after();
-        const bool issued = nrow > 0;
-        if (issued && elect_one()) {
-          // consecutive MMAs go to DIFFERENT accumulators: back-to-back MMAs into one accumulator
-          // serialise on its read-modify-write (measured: 63-83 cycles per MMA instead of 40-48)
+            tcgen05_fence_after();
+          }
+          const uint32_t d = tmem + (uint32_t)(acc * C::ACCW);
+          if (elect_one()) {
 #pragma unroll
-          for (int dx = 0; dx < F; dx++) {
-            const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
-            constexpr uint32_t W_DX = (uint32_t)(C::CIN / 8) * 128u;   // next tap of the image
-#pragma unroll
-            for (int p = 0; p < 3; p++) {
-#pragma unroll
-              for (int k = 0; k < 3; k++) {
-                if (k < nrow) {
-                  const uint32_t wk = w_dy[k] + dx * W_DX + (p == 1 ? W_LO : 0u);
-                  mma_f16_ss(acc_d[k], p == 2 ? dal : dah, wdesc(wk), idesc,
-                             (first_k[k] && dx == 0 && p == 0) ? 0u : 1u);
-                }
+            for (int dx = 0; dx < F; dx++) {
+              // K-step (tap, slice): 16 halves = 2 core matrices of the image
+              const uint32_t wk = sW + (uint32_t)(((dy * F + dx) * C::CIN + c * 16) / 8) * 128u;
+              const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
+              const uint64_t dwh = wdesc(wk), dwl = wdesc(wk + W_LO);
+              const uint32_t fresh = (first && dx == 0) ? 0u : 1u;
+              if (C::STACK) {
+                mma_f16_ss(d, dah, dwh, idesc2, fresh);       // [hi.w_hi | hi.w_lo]
+                mma_f16_ss(d, dal, dwh, idesc, 1u);           // + lo.w_hi
+              } else {
+                mma_f16_ss(d, dah, dwh, idesc, fresh);
+                mma_f16_ss(d, dah, dwl, idesc, 1u);
+                mma_f16_ss(d, dal, dwh, idesc, 1u);
               }
             }
+            if (r == r_last(rho) && c == C::NSLICE - 1) mma_commit(&done[acc]);
           }
-#pragma unroll
-          for (int k = 0; k < 3; k++)
-            if (k < nrow && last_k[k]) mma_commit(&done[acc_i[k]]);
+          __syncwarp();
+          issued = true;
         }
-        __syncwarp();
         if (elect_one()) {
           if (issued) mma_commit(&empty[slot]);
           else mbar_arrive(&empty[slot]);
@@ -376,7 +372,16 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       float v[C::COUT];
 #pragma unroll
       for (int g = 0; g < C::COUT / 16; g++)
-        tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::COUT + g * 16), v + g * 16);
+        tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::ACCW + g * 16), v + g * 16);
+      if (C::STACK) {
+        float v2[C::COUT];
+#pragma unroll
+        for (int g = 0; g < C::COUT / 16; g++)
+          tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::ACCW + C::COUT + g * 16), v2 + g * 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < C::COUT; j++) v[j] += v2[j];
+      }
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&acc_free[acc]);

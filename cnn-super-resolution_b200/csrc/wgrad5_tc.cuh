@@ -293,24 +293,20 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad5_tc_kernel(Args a) {
       if (elect_one()) {
         const uint32_t st = sA + stage * C::STAGE;
         const uint32_t ring = (uint32_t)((i % C::RBN) * C::KS * 16);   // entry of local pixel 16 i
-        // product-major order: consecutive MMAs go to different accumulators (back-to-back MMAs
-        // into one accumulator serialise on its read-modify-write)
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-#pragma unroll
-          for (int gi = 0; gi < 4; gi++) {
-            const int g = me + 2 * gi;
-            if (g < C::NG) {
-              const uint32_t set = g == 5 ? 1u : 0u;
-              const uint32_t shift = g < 5 ? (uint32_t)(g * w1) : (g == 5 ? 4u : (uint32_t)(4 * w1 + 4));
-              // ring entry of the first pixel: (16 i + shift) mod ring length; the mirror block
-              // makes the 16-pixel read contiguous
-              const uint32_t e = (ring + shift * 16u) % (uint32_t)(C::RBN * C::KS * 16);
-              const uint64_t ad = desc(st + set * 2 * C::TILE + (p == 2 ? C::TILE : 0), C::KS * 16);
-              const uint64_t bd = desc((p == 1 ? sBl : sBh) + e, C::PLANE);
-              mma_f16_ss(tmem + (uint32_t)(g * C::K), ad, bd, idesc, (i > 0 || p > 0) ? 1u : 0u);
-            }
-          }
+        for (int g = me; g < C::NG; g += 2) {
+          const uint32_t set = g == 5 ? 1u : 0u;
+          const uint32_t shift = g < 5 ? (uint32_t)(g * w1) : (g == 5 ? 4u : (uint32_t)(4 * w1 + 4));
+          // ring entry of the first pixel: (16 i + shift) mod ring length; the mirror block
+          // makes the 16-pixel read contiguous
+          const uint32_t e = (ring + shift * 16u) % (uint32_t)(C::RBN * C::KS * 16);
+          const uint64_t ah = desc(st + set * 2 * C::TILE, C::KS * 16);
+          const uint64_t al = desc(st + set * 2 * C::TILE + C::TILE, C::KS * 16);
+          const uint64_t bh = desc(sBh + e, C::PLANE), bl = desc(sBl + e, C::PLANE);
+          const uint32_t d = tmem + (uint32_t)(g * C::K);
+          mma_f16_ss(d, ah, bh, idesc, i > 0 ? 1u : 0u);
+          mma_f16_ss(d, ah, bl, idesc, 1u);
+          mma_f16_ss(d, al, bh, idesc, 1u);
         }
         mma_commit(&empty_a[stage]);
         mma_commit(&bempty[i % C::RBN]);

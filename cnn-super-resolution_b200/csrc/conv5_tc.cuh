@@ -50,17 +50,24 @@ struct Maxes {
   unsigned out1, d2, in;
 };
 
-// |x| maximum of a tensor, as an unsigned bit pattern (atomicMax); `out` must be zeroed first
-__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, size_t n4,
-                                                     size_t n, unsigned* out) {
+// |x| maximum of a tensor, as an unsigned bit pattern (atomicMax); `out` must be zeroed first.
+// `x` only needs float alignment: up to 3 leading and 3 trailing floats are read singly.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n,
+                                                     unsigned* out) {
+  const size_t head = min(n, (size_t)((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) / 4);
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const size_t n4 = (n - head) / 4;
   float m = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(x + i);
+    const float4 v = __ldg(x4 + i);
     m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4)   // the last n % 4 floats
-    m = fmaxf(m, fabsf(__ldg(reinterpret_cast<const float*>(x) + 4 * n4 + threadIdx.x)));
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < head) m = fmaxf(m, fabsf(__ldg(x + threadIdx.x)));
+    const size_t tail = head + 4 * n4;
+    if (threadIdx.x < n - tail) m = fmaxf(m, fabsf(__ldg(x + tail + threadIdx.x)));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
@@ -433,13 +440,12 @@ inline int prepare(srcnn_ctx* ctx, const float* w2, bool cacheable, const Images
   return SRCNN_OK;
 }
 
-// max |x| of n floats (16-byte aligned) into *slot (zeroed here)
+// max |x| of n floats into *slot (zeroed here)
 inline int absmax(srcnn_ctx* ctx, const float* x, size_t n, unsigned* slot) {
   SRCNN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned), ctx->stream));
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)ctx->sm_count * 8);
-  absmax_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(
-      reinterpret_cast<const float4*>(x), n4, n, slot);
+  absmax_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(x, n, slot);
   ctx->launch_count++;
   return SRCNN_OK;
 }

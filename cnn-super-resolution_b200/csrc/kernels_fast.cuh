@@ -130,7 +130,7 @@ inline int conv5_layer1(srcnn_ctx* ctx, const float* in, float* out1, const floa
   if (ctx->fused_impl != 4 || n1 != fused_hp::Cfg::N1 || f1 != fused_hp::Cfg::F1) return 0;
   if (!conv5_shape_ok(ctx, w - f1 + 1, h - f1 + 1, S)) return 0;
   if (w > 512 || (long long)S * w >= (1LL << 30) || (long long)S * w * h >= (1LL << 31)) return 0;
-  if (!aligned16(in) || !aligned16(out1)) return 0;
+  if (!aligned16(out1)) return 0;   // (the one-channel input is read float by float)
   c5::Maxes* mx;
   SRCNN_TRY(conv5_maxes(ctx, &mx));
   SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * w * h, &mx->in));
@@ -171,7 +171,9 @@ inline bool deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float* targ
 // them for the layer-2 forward / layer-1 deltas of the same tensors)
 inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float* gw, float* gb,
                          int n, int k, int f, int ow, int oh, int S, bool maxes_known = false) {
-  if (!aligned16(d) || !aligned16(in)) return 0;   // the register-tiled kernels use LDG.128
+  // the register-tiled kernels use LDG.128 (a one-channel layer input is read float by float:
+  // sample sets whose size is not a multiple of 4 leave later chunks float-aligned only)
+  if (!aligned16(d) || (k != 1 && !aligned16(in))) return 0;
   if (ctx->wgrad_tc) {   // layer-1 / layer-2 gradients on the tensor cores
     int count = 0;
     int rc = wgtc::wgrad1_tc(ctx, d, in, n, k, f, ow, oh, S, &count);
@@ -195,6 +197,7 @@ inline int backpropagate(srcnn_ctx* ctx, const float* d, const float* in, float*
       return 1;
     }
   }
+  if (!aligned16(in)) return 0;   // the FP32 split-K kernels stage the input with LDG.128
   return train::gradw(ctx, d, in, gw, gb, n, k, f, ow, oh, S);
 }
 

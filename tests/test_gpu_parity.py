@@ -561,6 +561,35 @@ def test_baseline_sized_epochs_vs_committed_reference(ctx, name, route):
         ctx.release(m)
 
 
+@pytest.mark.parametrize("cfg", [(64, 32, 9, 1, 5), (64, 32, 9, 5, 5)])
+def test_chunk_views_need_only_float_alignment(ctx, cfg):
+    """A chunk that starts at a sample offset which is not a multiple of 4 samples is only
+    float-aligned (33*33*4 bytes per sample): it must take the same kernels and give the same bits
+    as the 16-byte aligned copy of the same samples."""
+    rng = np.random.default_rng(77)
+    S, w = 171, 33
+    params = make_params(rng, *cfg)
+    x, gt = patches(rng, S + 1, w, w)
+    per = 4 * w * w
+    big_i, big_g = ctx.upload(x), ctx.upload(gt)
+    results = []
+    for shifted in (False, True):
+        net = pkg.Net(ctx, *cfg, params)
+        work = ctx.alloc(net.train_workspace_bytes(w, w, S))
+        if shifted:   # samples 1..S of the big arrays: a view at +4356 bytes
+            mi = ctx.wrap(ctx.mem_ptr(big_i) + per, S * per)
+            mg = ctx.wrap(ctx.mem_ptr(big_g) + per, S * per)
+        else:
+            mi, mg = ctx.upload(x[1:]), ctx.upload(gt[1:])
+        n0 = ctx.launch_count()
+        net.train_chunk(mi, mg, w, w, S, work)
+        results.append((ctx.launch_count() - n0, net.grads()))
+        ctx.release(work)
+    assert results[0][0] == results[1][0], "the float-aligned view took a different (slower) path"
+    for k in results[0][1]:
+        np.testing.assert_array_equal(results[0][1][k], results[1][1][k], err_msg=k)
+
+
 INFER = [
     # n1, n2, f1, f2, f3, w, h, S
     (64, 32, 9, 1, 5, 256, 256, 1),     # BASELINE config C1

@@ -197,3 +197,107 @@ def test_cnn_cli_training_and_profile_output(tmp_path):
     for k in ("layer_uber_kernel.cl", "layer_deltas.cl", "backpropagate.cl", "update_parameters.cl"):
         assert k in names, r.stdout
     assert sum(int(float(p[1])) for p in prof) > 0
+
+
+def _write_samples(d, rng, n):
+    d.mkdir()
+    for i in range(n):
+        gt = rng.integers(0, 256, (33, 33, 1)).astype(np.uint8).repeat(3, -1)
+        write_ppm(d / ("sample_%d_large.ppm" % i), gt)
+        write_ppm(d / ("sample_%d_small.ppm" % i),
+                  np.clip(gt.astype(int) + rng.integers(-9, 9, gt.shape), 0, 255))
+
+
+@pytest.mark.gpu
+def test_cnn_cli_resume_state(tmp_path):
+    """the parameters file carries an optional "resume" key (9-digit parameters +
+    the momentum state, src/ConfigBasedDataPipeline.cpp:432-465 writes neither).  Training 2
+    epochs in one run == 1 epoch, save, resume, 1 more epoch; without the key (the reference's
+    format) momentum restarts at zero and 6-digit weights differ."""
+    rng = np.random.default_rng(11)
+    d = tmp_path / "samples"
+    _write_samples(d, rng, 4)              # 4 samples: the 20 % validation set is empty
+    cfg = (8, 4, 9, 1, 5)
+    c0 = str(tmp_path / "c0.json")
+    write_config(c0, cfg)
+    env = dict(os.environ, CNN_SR_SEED="3")
+
+    def train(config, out, epochs, extra_env=None):
+        e = dict(env, **(extra_env or {}))
+        r = run([CNN, "train", "-c", config, "-i", str(d), "-o", out, "--epochs", str(epochs)], env=e)
+        assert r.returncode == 0, r.stdout
+        return json.load(open(out)), r.stdout
+
+    init, _ = train(c0, str(tmp_path / "init.json"), 0)       # the seeded random initialisation
+    assert init["epochs"] == 0 and "resume" in init
+    c1 = str(tmp_path / "c1.json")
+    write_config(c1, cfg, str(tmp_path / "init.json"))
+    two, _ = train(c1, str(tmp_path / "two.json"), 2)
+    one, _ = train(c1, str(tmp_path / "one.json"), 1)
+    assert any(abs(v) > 0 for v in one["resume"]["layer1"]["previous_delta_w"])
+    c2 = str(tmp_path / "c2.json")
+    write_config(c2, cfg, str(tmp_path / "one.json"))
+    resumed, log = train(c2, str(tmp_path / "resumed.json"), 1)
+    assert "Resume state found" in log and resumed["epochs"] == 2
+    for l in ("layer1", "layer2", "layer3"):
+        for k in ("weights", "bias", "previous_delta_w", "previous_delta_b"):
+            np.testing.assert_allclose(np.array(resumed["resume"][l][k]), np.array(two["resume"][l][k]),
+                                       rtol=2e-6, atol=1e-9, err_msg="%s %s" % (l, k))
+    # the reference's own format: no resume key -> momentum restarts, result differs
+    plain, _ = train(c1, str(tmp_path / "plain.json"), 1, {"CNN_SR_RESUME_STATE": "0"})
+    assert "resume" not in plain and set(plain) == {"epochs", "layer1", "layer2", "layer3"}
+    c3 = str(tmp_path / "c3.json")
+    write_config(c3, cfg, str(tmp_path / "plain.json"))
+    cold, log = train(c3, str(tmp_path / "cold.json"), 1)
+    assert "Resume state found" not in log
+    a = np.array(cold["resume"]["layer1"]["weights"])
+    b = np.array(two["resume"]["layer1"]["weights"])
+    assert np.abs(a - b).max() > 1e-7
+
+
+@pytest.mark.gpu
+def test_cnn_cli_data_parallel_two_gpus(tmp_path):
+    """`cnn train` on 2 GPUs (CNN_SR_WORLD=2, one process per GPU, NCCL id through
+    CNN_SR_COMM_FILE) must write the same parameters as the 1-GPU run of the same samples."""
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(n))
+    except OSError:
+        pytest.skip("no CUDA runtime")
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(12)
+    d = tmp_path / "samples"
+    _write_samples(d, rng, 12)
+    cfg = (8, 4, 9, 1, 5)
+    c0 = str(tmp_path / "c0.json")
+    write_config(c0, cfg)
+    env = dict(os.environ, CNN_SR_SEED="5")
+    r = run([CNN, "train", "-c", c0, "-i", str(d), "-o", str(tmp_path / "init.json"), "--epochs", "0"], env=env)
+    assert r.returncode == 0, r.stdout
+    c1 = str(tmp_path / "c1.json")
+    write_config(c1, cfg, str(tmp_path / "init.json"))
+    r = run([CNN, "train", "-c", c1, "-i", str(d), "-o", str(tmp_path / "single.json"), "--epochs", "3"], env=env)
+    assert r.returncode == 0, r.stdout
+    procs = []
+    for rank in range(2):
+        e = dict(env, CNN_SR_WORLD="2", CNN_SR_RANK=str(rank), CNN_SR_COMM_FILE=str(tmp_path / "nccl.id"))
+        procs.append(subprocess.Popen([CNN, "train", "-c", c1, "-i", str(d), "-o", str(tmp_path / "dp.json"),
+                                       "--epochs", "3"], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "DATA PARALLEL: rank 0 of 2" in outs[0] and "mean validation error" in outs[0]
+    single, dp = json.load(open(tmp_path / "single.json")), json.load(open(tmp_path / "dp.json"))
+    assert dp["epochs"] == 3
+    for l in ("layer1", "layer2", "layer3"):
+        for k in ("weights", "bias"):
+            np.testing.assert_allclose(np.array(dp["resume"][l][k]), np.array(single["resume"][l][k]),
+                                       rtol=2e-5, atol=1e-9, err_msg="%s %s" % (l, k))
+    v1 = [l for l in r.stdout.splitlines() if "mean validation error" in l]
+    v2 = [l for l in outs[0].splitlines() if "mean validation error" in l]
+    assert len(v1) == len(v2) > 0
+    for a, b in zip(v1, v2):
+        fa, fb = float(a.split("error:")[1].split()[0]), float(b.split("error:")[1].split()[0])
+        assert fa == pytest.approx(fb, rel=1e-4)

@@ -2,7 +2,6 @@
 """e2e timing of srcnn_infer_rows_host on C3 (pinned host buffers, H2D + kernel + D2H)."""
 import os, sys, time
 import numpy as np
-import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg
 pkg = _pkg.load()

@@ -47,7 +47,7 @@ namespace c5 {
 
 // per-chunk device scalars: bit patterns of max |x| (non-negative floats order like unsigned)
 struct Maxes {
-  unsigned out1, d2, in;
+  unsigned out1, d2, in, out2, d3;
 };
 
 // |x| maximum of a tensor, as an unsigned bit pattern (atomicMax); `out` must be zeroed first.
@@ -177,6 +177,7 @@ struct Args {
   const float* sw;       // -> Images::sw
   const unsigned* in_max;      // bit pattern of max |in|
   int S, w1, h1;         // samples, extent of the layer-1 map (25 x 25 for 33 x 33 patches)
+  unsigned* out_max;     // MODE 0, may be null: receives max |out2| (zeroed by the launcher)
 };
 
 template <class C>
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     const long long orow = (long long)ow * C::COUT;
     const float cs = 1.f / (s_in * sw);
     const float* sB = reinterpret_cast<const float*>(smem_raw + C::oBias);
+    float omax = 0.f;
     for (int rho = 0; rho < oh; rho++) {
       const int acc = rho % C::NACC;
       mbar_wait(&done[acc], (uint32_t)((rho / C::NACC) & 1));
@@ -396,11 +398,14 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       float4* o = reinterpret_cast<float4*>(a.out + obase + rho * orow);
       if (C::MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < C::COUT / 4; j++)
-          o[j] = make_float4(fmaxf(fmaf(v[4 * j], cs, sB[4 * j]), 0.f),
-                             fmaxf(fmaf(v[4 * j + 1], cs, sB[4 * j + 1]), 0.f),
-                             fmaxf(fmaf(v[4 * j + 2], cs, sB[4 * j + 2]), 0.f),
-                             fmaxf(fmaf(v[4 * j + 3], cs, sB[4 * j + 3]), 0.f));
+        for (int j = 0; j < C::COUT / 4; j++) {
+          const float4 r = make_float4(fmaxf(fmaf(v[4 * j], cs, sB[4 * j]), 0.f),
+                                       fmaxf(fmaf(v[4 * j + 1], cs, sB[4 * j + 1]), 0.f),
+                                       fmaxf(fmaf(v[4 * j + 2], cs, sB[4 * j + 2]), 0.f),
+                                       fmaxf(fmaf(v[4 * j + 3], cs, sB[4 * j + 3]), 0.f));
+          o[j] = r;
+          omax = fmaxf(fmaxf(omax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
+        }
       } else {
         const float4* mk = reinterpret_cast<const float4*>(a.aux + obase + rho * orow);
 #pragma unroll
@@ -410,6 +415,11 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
                              g.z > 0.f ? v[4 * j + 2] * cs : 0.f, g.w > 0.f ? v[4 * j + 3] * cs : 0.f);
         }
       }
+    }
+    if (C::MODE == 0 && a.out_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+      if (lane == 0 && omax > 0.f) atomicMax(a.out_max, __float_as_uint(omax));
     }
   }
 

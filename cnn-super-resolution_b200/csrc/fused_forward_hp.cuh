@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     const int w2_row = bx.pw - (C::F1 - 1);
     float* st2 = reinterpret_cast<float*>(smem_raw + C::oS2) + (warp - C::W_E2) * (32 * C::SP);
+    float act2_max = 0.f;   // largest scaled out2 value this thread stored
     for (int b = 0; b < n_tiles; b++) {
       mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
       if (warp == C::W_E2) PL_EV(b, 6)
@@ -700,6 +701,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         tmem_st8u(d2 + g * 8, hi);
         tmem_st8u(d2 + C::N2 + g * 8, lo);
         if (keep2) {
+          if (pix2 >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) act2_max = fmaxf(act2_max, act[j]);
+          }
           float4* q = reinterpret_cast<float4*>(st2 + lane * C::SP + g * 16);
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -724,6 +729,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         __syncwarp();
       }
       if (warp == C::W_E2) PL_EV(b, 7)
+    }
+    if (keep2 && bx.out2_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) act2_max = fmaxf(act2_max, __shfl_xor_sync(0xffffffffu, act2_max, o));
+      if (lane == 0 && act2_max > 0.f) atomicMax(bx.out2_max, __float_as_uint(act2_max * sc.inv_s2));
     }
   } else if (warp < C::W_IM) {
     // ============================ E3: Q row -> smem, 25-term gather -> out3 ================
@@ -841,7 +851,7 @@ inline void prepare_into(srcnn_ctx* ctx, const fused::Args& a, void* block) {
 // srcnn_infer_rows_host, or the context's cache); null = prepare here.  The scales are read-only
 // for the kernels; "leave this launch to the TF32 kernel" is a per-launch word of the ring.
 inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float* out1,
-                  float* out2, const Scales* shared = nullptr) {
+                  float* out2, const Scales* shared = nullptr, unsigned* out2_max = nullptr) {
   const Scales* sc = shared;
   Scales* slot;
   unsigned* ws;
@@ -867,6 +877,8 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S, bool batch, float
     bx.S = S;
     bx.pw = a.w;
     bx.ph = a.h;
+    bx.out2_max = out2_max;
+    if (out2_max) SRCNN_CUDA(cudaMemsetAsync(out2_max, 0, sizeof(unsigned), ctx->stream));
     forward_fused_hp_kernel<true>
         <<<grid, Cfg::NT, (out1 || out2) ? Cfg::SMEM_BYTES_KEEP : Cfg::SMEM_BYTES, ctx->stream>>>(
             v, rpc, bx, sc, fallback);

@@ -168,6 +168,8 @@ struct BatchExt {
   // layer-1-only launches of the FP16-split kernel (9-5-5 training forward): |out1| maximum,
   // as an unsigned bit pattern (atomicMax), for the layer-2 kernel's operand scale
   unsigned* out1_max;
+  // training forward (out2 kept): |out2| maximum for the tensor-core backward of layer 3
+  unsigned* out2_max;
 };
 
 template <bool BATCH>
@@ -498,6 +500,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
         o2 = bx.out2 + (((size_t)smp * h2 + R0) * w2 + px) * C::N2;
     }
     const size_t o2_row = (size_t)(bx.pw - (C::F1 - 1)) * C::N2;
+    float act2_max = 0.f;   // largest out2 value this thread stored (training forward)
     PL_T0
     for (int b = 0; b < n_tiles; b++) {
       PL_WAIT(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
@@ -528,6 +531,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
             float4* q = reinterpret_cast<float4*>(o2 + (size_t)b * o2_row + g * 16 + h8 * 8);
             q[0] = make_float4(act[0], act[1], act[2], act[3]);
             q[1] = make_float4(act[4], act[5], act[6], act[7]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) act2_max = fmaxf(act2_max, act[j]);
           }
         }
       }
@@ -535,6 +540,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_pl_kernel(fused::Arg
       tcgen05_fence_before();
       mbar_arrive(&a3_full[b & 1]);
       if (warp == C::W_E2) PL_EV(b, 7)
+    }
+    if (BATCH && bx.out2 && bx.out2_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) act2_max = fmaxf(act2_max, __shfl_xor_sync(0xffffffffu, act2_max, o));
+      if (lane == 0 && act2_max > 0.f) atomicMax(bx.out2_max, __float_as_uint(act2_max));
     }
     PL_REPORT("E2")
   } else if (warp < C::W_IM) {
@@ -666,15 +676,23 @@ inline int launch(srcnn_ctx* ctx, const fused::Args& a, int S) {
 }
 
 // a batch of S samples of pw x ph pixels as one virtual image; out1/out2 may be null
-inline int launch_batch(srcnn_ctx* ctx, const fused::Args& a, int S, float* out1, float* out2) {
+inline int launch_batch(srcnn_ctx* ctx, const fused::Args& a, int S, float* out1, float* out2,
+                        unsigned* out2_max = nullptr) {
   fused::Args v = a;
   const int pad = Cfg::F1 + Cfg::F3 - 2;
   v.w = S * a.w;
   v.w3 = S * a.w - pad;
   const int rpc = rows_per_cta(v.w3, v.h3, 1, ctx->sm_count > 0 ? ctx->sm_count : 148);
   dim3 grid((v.w3 + Cfg::OW3 - 1) / Cfg::OW3, (v.h3 + rpc - 1) / rpc, 1);
-  forward_fused_pl_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
-      v, rpc, BatchExt{out1, out2, S, a.w, a.h});
+  BatchExt bx{};
+  bx.out1 = out1;
+  bx.out2 = out2;
+  bx.S = S;
+  bx.pw = a.w;
+  bx.ph = a.h;
+  bx.out2_max = out2_max;
+  if (out2_max) SRCNN_CUDA(cudaMemsetAsync(out2_max, 0, sizeof(unsigned), ctx->stream));
+  forward_fused_pl_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(v, rpc, bx);
   return SRCNN_OK;
 }
 

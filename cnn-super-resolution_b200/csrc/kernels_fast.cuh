@@ -16,6 +16,7 @@
 #include "wgrad1_fused_tc.cuh"
 #include "conv5_tc.cuh"
 #include "wgrad5_tc.cuh"
+#include "bwd3_tc.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -91,6 +92,32 @@ inline bool forward_layer(srcnn_ctx* ctx, const float* in, float* out, const flo
   return train::n1_forward(ctx, in, out, W, B, k, n, f, relu, in_w, in_h, S);
 }
 
+// ---- backward of the last layer on the tensor cores (bwd3_tc.cuh) ------------------------------
+// d3, d2 and the layer-3 gradient partials of a chunk of patch-sized samples; returns 1 when
+// launched (then max |d2| is in the context's maxima block), 0 when left to the FP32 kernel
+inline int conv5_maxes(srcnn_ctx* ctx, c5::Maxes** out);
+inline int backward3_tc(srcnn_ctx* ctx, const float* gt, const float* out3, const float* out2,
+                        const float* W3, float* d3, float* d2, float* gw, float* gb, int k, int f,
+                        int gt_w, int gt_h, int w3, int h3, int S) {
+  static const bool off = std::getenv("SRCNN_B3_IMPL") && std::strcmp(std::getenv("SRCNN_B3_IMPL"), "simt") == 0;
+  if (off || !ctx->wgrad_tc || !b3tc::supported(k, f)) return 0;
+  const int ow = w3 + f - 1, oh = h3 + f - 1;
+  if ((long long)S * ow < 32 * 128 || ow > 1024 || oh > 4096) return 0;   // batches of patches
+  if (!aligned16(out2) || !aligned16(d2)) return 0;
+  c5::Maxes* mx;
+  SRCNN_TRY(conv5_maxes(ctx, &mx));
+  int count = 0;
+  const int rc = b3tc::bwd3_tc(ctx, gt, out3, out2, W3, d3, d2, mx, ctx->c5_fresh_out2 == out2, k, f,
+                               gt_w, gt_h, w3, h3, S, &count);
+  if (rc != 1) return rc;
+  ctx->c5_fresh_d2 = d2;
+  const int Mw = f * f * k;
+  train::partial_reduce_kernel<<<(Mw + 1 + train::RED_OUT - 1) / train::RED_OUT,
+                                 train::RED_OUT * train::RED_WARPS, 0, ctx->stream>>>(
+      (const float*)ctx->splitk_scratch, gw, gb, Mw, 1, count);
+  return 1;
+}
+
 // ---- 9-5-5 layer 2 on the tensor cores (conv5_tc.cuh) ----------------------------------------
 // The virtual-image kernels want enough strips of 128 columns to fill the GPU: batches of
 // patch-sized samples (training / validation chunks).  Returns 1 when launched, 0 when the
@@ -119,8 +146,10 @@ inline int conv5_forward(srcnn_ctx* ctx, const float* in, float* out, const floa
   SRCNN_TRY(conv5_maxes(ctx, &mx));
   if (!max_known) SRCNN_TRY(c5::absmax(ctx, in, (size_t)S * in_w * in_h * 64, &mx->out1));
   ctx->c5_max_out1_of = in;
-  c5::Args a{in, B, out, img->fwd, &img->sw, &mx->out1, S, in_w, in_h};
+  SRCNN_CUDA(cudaMemsetAsync(&mx->out2, 0, sizeof(unsigned), ctx->stream));
+  c5::Args a{in, B, out, img->fwd, &img->sw, &mx->out1, S, in_w, in_h, &mx->out2};
   SRCNN_TRY(c5::launch<c5::FwdCfg>(ctx, a));
+  ctx->c5_fresh_out2 = out;   // max |out2| recorded by the epilogue
   return 1;
 }
 // layer 1 of a 9-5-5 training chunk through the FP16-split tensor-core kernel in its
@@ -150,9 +179,10 @@ inline int conv5_deltas(srcnn_ctx* ctx, const float* dn, const float* lo, float*
   SRCNN_TRY(c5::prepare(ctx, W, cacheable, &img));
   c5::Maxes* mx;
   SRCNN_TRY(conv5_maxes(ctx, &mx));
-  SRCNN_TRY(c5::absmax(ctx, dn, (size_t)S * (ow - 4) * (oh - 4) * 32, &mx->d2));
+  if (ctx->c5_fresh_d2 != dn)   // (the tensor-core backward of layer 3 records it)
+    SRCNN_TRY(c5::absmax(ctx, dn, (size_t)S * (ow - 4) * (oh - 4) * 32, &mx->d2));
   ctx->c5_max_d2_of = dn;
-  c5::Args a{dn, lo, target, img->d1, &img->sw, &mx->d2, S, ow, oh};
+  c5::Args a{dn, lo, target, img->d1, &img->sw, &mx->d2, S, ow, oh, nullptr};
   SRCNN_TRY(c5::launch<c5::D1Cfg>(ctx, a));
   return 1;
 }
@@ -328,7 +358,7 @@ inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, i
                                const float* in, float* out1, float* out2, float* out3,
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w3, const float* b3, int in_w, int in_h, int S,
-                               const void* scales = nullptr) {
+                               const void* scales = nullptr, unsigned* out2_max = nullptr) {
   if (ctx->fused_impl < 3 || !fused_pl::supported(n1, n2, f1, f2, f3)) return 0;
   if ((long long)S * in_w >= (1LL << 30)) return 0;
   if ((long long)S * in_w * in_h >= (1LL << 31)) return 0;   // 32-bit pixel indices of out1 / out2
@@ -336,8 +366,8 @@ inline int forward_train_fused(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, i
                 in_h - (f1 + f2 + f3 - 3)};
   const int rc = ctx->fused_impl == 4
                      ? fused_hp::launch(ctx, a, S, true, out1, out2,
-                                        static_cast<const fused_hp::Scales*>(scales))
-                     : fused_pl::launch_batch(ctx, a, S, out1, out2);
+                                        static_cast<const fused_hp::Scales*>(scales), out2_max)
+                     : fused_pl::launch_batch(ctx, a, S, out1, out2, out2_max);
   return rc == SRCNN_OK ? 1 : rc;
 }
 

@@ -765,10 +765,11 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   int sub_r0[kMaxSub + 1] = {0};
   {
     // shares ramp up from a small first sub-band and down to a small last one: 1,2,3,..,3,2,1
-    // capped at 4 units; the exposed head upload / tail download shrink with them
+    // capped at 2 units (round-2 sweep, profiles/r2g_e2e_subband_sweep.txt: cap 2 / 4 / 8 at 16
+    // sub-bands: 1.69 / 1.77 / 1.86 ms); the exposed head upload / tail download shrink with them
     float unit[kMaxSub], total = 0.f;
     for (int i = 0; i < n_sub; i++) {
-      static const int kRampCap = std::getenv("SRCNN_E2E_RAMPCAP") ? std::atoi(std::getenv("SRCNN_E2E_RAMPCAP")) : 4;
+      static const int kRampCap = std::getenv("SRCNN_E2E_RAMPCAP") ? std::atoi(std::getenv("SRCNN_E2E_RAMPCAP")) : 2;
       unit[i] = (float)std::min(std::min(i + 1, n_sub - i), std::max(kRampCap, 1));
       total += unit[i];
     }
@@ -1037,6 +1038,15 @@ int backward3_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem gt, co
   SRCNN_TRY(resolve(ctx, net->grad_w[2], sizeof(float) * (size_t)net->f3 * net->f3 * net->n2, &gw, "grad_w3"));
   SRCNN_TRY(resolve(ctx, net->grad_b[2], sizeof(float), &gb, "grad_b3"));
   LaunchScope scope(ctx, SRCNN_K_BACKPROPAGATE, 2);
+  {   // tensor cores first (batches of patches, 32 channels); 3 launches: d3, main, reduce
+    const int rtc = fast::backward3_tc(ctx, pgt, o3, o2, w3, pd3, pd2, gw, gb, net->n2, net->f3, w, h,
+                                       d.w3, d.h3, S);
+    if (rtc < 0) return rtc;
+    if (rtc > 0) {
+      *launched = 1;
+      return check_launch("bwd3_tc");
+    }
+  }
   const int rc = train::bwd3_fused(ctx, pgt, o3, o2, w3, pd3, pd2, gw, gb, net->n2, net->f3, w, h,
                                    d.w3, d.h3, S);
   if (rc < 0) return rc;
@@ -1089,9 +1099,13 @@ int forward_train_fused_entry(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in
   const void* scales = nullptr;
   SRCNN_TRY(net_prepare(ctx, net, w1, b1, w2, b2, w3, b3, &scales));
   LaunchScope scope(ctx, SRCNN_K_FORWARD_FUSED, fast::fused_launches(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, scales != nullptr));
+  c5::Maxes* mx;
+  SRCNN_TRY(fast::conv5_maxes(ctx, &mx));
   const int rc = fast::forward_train_fused(ctx, net->n1, net->n2, net->f1, net->f2, net->f3, pin,
-                                           o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S, scales);
+                                           o1, o2, o3, w1, b1, w2, b2, w3, b3, w, h, S, scales,
+                                           &mx->out2);
   if (rc < 0) return rc;
+  if (rc > 0) ctx->c5_fresh_out2 = o2;   // max |out2| recorded for the layer-3 backward
   *launched = rc;
   if (!rc) scope.n_launches = 0;
   return rc ? check_launch("forward_train_fused") : SRCNN_OK;
@@ -1107,6 +1121,7 @@ int train_chunk_on(srcnn_ctx* ctx, const srcnn_net* net, srcnn_mem in, srcnn_mem
   // 9-5-5: the maxima the layer-2 forward and the layer-1 deltas measure (conv5_tc.cuh) stay
   // valid for the layer-2 gradient of the same chunk
   ctx->c5_max_out1_of = ctx->c5_max_d2_of = nullptr;
+  ctx->c5_fresh_out2 = ctx->c5_fresh_d2 = nullptr;
   struct KnownScope {
     srcnn_ctx* c;
     ~KnownScope() { c->c5_maxes_known = false; }

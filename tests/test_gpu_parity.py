@@ -383,6 +383,11 @@ NETS = [
     # patches over several 124-column strips, 1x1 outputs, and tall samples (several row bands)
     (64, 32, 9, 1, 5, 40, 29, 7), (64, 32, 9, 1, 5, 33, 33, 37), (64, 32, 9, 1, 5, 13, 13, 5),
     (64, 32, 9, 1, 5, 20, 150, 3),
+    # sample counts that take the tensor-core kernels of the backward pass as bench.py's chunks
+    # do: bwd3_tc (>= 32 strips of out2 columns), and for 9-5-5 the layer-1-only forward,
+    # conv5_tc (forward, layer-1 deltas) and wgrad5_tc
+    (64, 32, 9, 1, 5, 33, 33, 170), (64, 32, 9, 5, 5, 33, 33, 200), (64, 32, 9, 1, 5, 40, 29, 140),
+    (64, 32, 9, 5, 5, 36, 31, 180),
 ]
 
 
@@ -392,6 +397,7 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
     gradient tensors against the oracle."""
     n1, n2, f1, f2, f3, w, h, S = cfg
     rng = np.random.default_rng(sum(cfg))
+    port.set_num_threads(len(os.sched_getaffinity(0)))
     params = make_params(rng, n1, n2, f1, f2, f3)
     x, gt = patches(rng, S, w, h)
     on = NetState(n1, n2, f1, f2, f3, params)

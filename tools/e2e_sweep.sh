@@ -9,3 +9,4 @@ for sb in 6 8 10 12 16 20 24; do
   done
 done
 echo -n "graph off, 16/4: "; SRCNN_E2E_GRAPH=0 python tools/e2e_infer.py | tail -1
+tools/probe/mn16_probe | tail -4

@@ -7,6 +7,8 @@
 //   2. can an MN-major operand be combined with a K-major one
 //   3. does a 16-byte shifted base address shift the K (pixel) index by one
 //   4. where do the rows of an M = 64 accumulator live in tensor memory
+//   5. may the M groups of an MN-major operand OVERLAP (SBO = 16: group g = the same one-channel
+//      "oct" plane shifted by g entries -- the Hankel structure of a one-channel im2col matrix)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o mn16_probe mn16_probe.cu
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -52,6 +54,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* A, const __hal
   for (int i = tid; i < 128 * KP; i += 128) { sA[i] = __float2half(0.f); sB[i] = __float2half(0.f); }
   __syncthreads();
   // A is given as [M][KT] row-major, element (m, k) stored at K row (k + shift) of the planes
+  if (variant == 2) {
+    // overlapping groups: ONE plane P[kk][e] = A[e][kk] (rows 0..7 of A are the plane); logical
+    // A'[m = 8 g + e][k] = P[k + g][e]
+    for (int i = tid; i < 8 * KP; i += 128) {
+      const int kk = i / 8, e = i % 8;
+      sA[kk * 8 + e] = kk < KT ? A[e * KT + kk] : __float2half(0.f);
+    }
+  } else
   for (int i = tid; i < M * KT; i += 128) {
     const int m = i / KT, k = i % KT;
     if (a_mn) sA[(m / 8) * (KP * 8) + (k + shift) * 8 + (m & 7)] = A[i];
@@ -73,11 +83,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* A, const __hal
     const uint32_t idesc = idesc_f16(M, N, a_mn, b_mn);
     const uint32_t gs = KP * 16;   // bytes between groups of 8 M (or N) elements
     for (int ks = 0; ks < KT / 16; ks++) {
-      const uint32_t lbo = variant == 0 ? 128 : gs, sbo = variant == 0 ? gs : 128;
+      const uint32_t lbo = variant == 1 ? gs : 128, sbo = variant == 0 ? gs : (variant == 1 ? 128 : 16);
       // MN-major: one K-step = 16 K rows = 256 bytes along the plane; K-major: 2 core matrices
       const uint64_t ad = a_mn ? make_desc_kmajor(sA, (ks * 16 + shift) * 16, lbo, sbo)
                                : make_desc_kmajor(sA, ks * 256, 128, 128 * (KT / 8));
-      const uint64_t bd = b_mn ? make_desc_kmajor(sB, ks * 16 * 16, lbo, sbo)
+      const uint64_t bd = b_mn ? make_desc_kmajor(sB, ks * 16 * 16, variant == 1 ? gs : 128, variant == 1 ? 128 : gs)
                                : make_desc_kmajor(sB, ks * 256, 128, 128 * (KT / 8));
       mma_f16(tmem, ad, bd, idesc, ks > 0);
     }
@@ -125,6 +135,9 @@ int main() {
       {64, 0, 0, 0, 0, "M=64 K-major (lane map)"},
       {64, 1, 1, 0, 0, "M=64 MN-major LBO=128 SBO=group (lane map)"},
       {64, 1, 1, 1, 0, "M=64 MN-major LBO=group SBO=128 (lane map)"},
+      {64, 1, 1, 2, 0, "M=64 MN-major A with OVERLAPPING groups (SBO=16), MN-major B"},
+      {64, 1, 0, 2, 0, "M=64 MN-major A with OVERLAPPING groups (SBO=16), K-major B"},
+      {128, 1, 1, 2, 0, "M=128 MN-major A with OVERLAPPING groups (SBO=16), MN-major B"},
   };
   for (const Case& c : cases) {
     cudaMemset(dD, 0, D.size() * 4);
@@ -139,6 +152,25 @@ int main() {
         for (int k = 0; k < KT; k++) r += (double)Af[m * KT + k] * Bf[n * KT + k];
         ref[(size_t)m * N + n] = r;
       }
+    if (c.variant == 2) {
+      // reference: A'[8 g + e][k] = A[e][k + g] (zero beyond KT)
+      double err = 0;
+      int lanes_ok = 0;
+      for (int m = 0; m < c.M; m++) {
+        const int g = m / 8, e = m % 8;
+        const int lane = c.M == 128 ? m : (m / 16) * 32 + m % 16;
+        double rowerr = 0;
+        for (int n = 0; n < N; n++) {
+          double r = 0;
+          for (int k = 0; k + g < KT && k < KT; k++) r += (double)Af[e * KT + k + g] * Bf[n * KT + k];
+          rowerr = fmax(rowerr, fabs(D[lane * N + n] - r));
+        }
+        err = fmax(err, rowerr);
+        lanes_ok += rowerr < 1e-3;
+      }
+      printf("%-70s max err %.3e (%d of %d rows match) %s\n", c.what, err, lanes_ok, c.M, err < 1e-3 ? "PASS" : "fail");
+      continue;
+    }
     if (c.M == 128) {
       double err = 0;
       for (int i = 0; i < 128 * N; i++) err = fmax(err, fabs(D[i] - ref[i]));

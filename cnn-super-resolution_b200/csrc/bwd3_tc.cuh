@@ -188,13 +188,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
 #pragma unroll
     for (int r = 0; r < 7; r++) hh[r] = hl[r] = 0;
     uint8_t* my = smem_raw + C::oP + q * 16;
-    float v = (base >= 0 && h3 > 0) ? __ldg(a.d3 + base) : 0.f;
+    auto ld3 = [&](int j) -> float {
+      return (base >= 0 && j < h3) ? __ldg(a.d3 + base + (long long)j * w3) : 0.f;
+    };
+    float v = ld3(0), v1 = ld3(1), v2 = ld3(2);   // three rows of d3 in flight
     for (int j = 0; j < oh; j++) {
       const int slot = j % C::RP;
       unsigned short nh, nl;
       split_h(v * s_d, nh, nl);
       if (own) gb += v;
-      const float vnext = (base >= 0 && j + 1 < h3) ? __ldg(a.d3 + base + (long long)(j + 1) * w3) : 0.f;
+      const float v3 = ld3(j + 3);
       if (j >= C::RP) mbar_wait(&pfree[slot], (uint32_t)(((j / C::RP) - 1) & 1));
       if (q < C::PW) {
         uint8_t* s = my + slot * C::P_SLOT;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
       hh[6] = nh; hl[6] = nl;
       fence_proxy_async();
       mbar_arrive(&pfull[slot]);
-      v = vnext;
+      v = v1; v1 = v2; v2 = v3;
     }
     // bias gradient of this CTA: lanes, then the 5 producer warps in order
 #pragma unroll
@@ -225,20 +228,30 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
       base = (((long long)smp * oh) * ow + x) * C::N + half * 16;
     }
     const long long row = (long long)ow * C::N;
-    float4 v[4];
-    auto load = [&](int j) {
-      if (base >= 0) {
+    // three rows of loads in flight per thread (48 KB per SM): one row ahead left the HBM latency
+    // exposed on every row (r2h: the producers' first use of a loaded value was the top stall)
+    constexpr int DEPTH = 3;
+    float4 vq[DEPTH][4];
+    auto load = [&](int j, float4 (&dst)[4]) {
+      if (base >= 0 && j < oh) {
         const float4* p = reinterpret_cast<const float4*>(a.out2 + base + j * row);
 #pragma unroll
-        for (int c = 0; c < 4; c++) v[c] = __ldg(p + c);
+        for (int c = 0; c < 4; c++) dst[c] = __ldg(p + c);
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; c++) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 4; c++) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    load(0);
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) load(d, vq[d]);
     uint8_t* my = smem_raw + C::oQ + (2 * half) * C::GP + m * 16;
-    for (int j = 0; j < oh; j++) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < oh; j0 += DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      const int j = j0 + d;
+      if (j >= oh) break;
+      float4 (&v)[4] = vq[d];
       const int slot = j % C::RQ;
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
         split_h2(v[c].x * s_o, v[c].y * s_o, hi[2 * c], lo[2 * c]);
         split_h2(v[c].z * s_o, v[c].w * s_o, hi[2 * c + 1], lo[2 * c + 1]);
       }
-      if (j + 1 < oh) load(j + 1);
+      load(j + DEPTH, vq[d]);
       if (j >= C::RQ) mbar_wait(&qfree[slot], (uint32_t)(((j / C::RQ) - 1) & 1));
       uint8_t* s = my + slot * C::Q_SLOT;
       *reinterpret_cast<uint4*>(s) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -255,6 +268,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
       *reinterpret_cast<uint4*>(s + 5 * C::GP) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       fence_proxy_async();
       mbar_arrive(&qfull[slot]);
+    }
     }
   } else if (warp == C::W_I) {
     // ============================ I0: d2 = d3 (*) W3 ===========================================
@@ -331,6 +345,17 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
     const long long row = (long long)ow * C::N;
     const float cs = 1.f / (s_d * s_w);
     float dmax = 0.f;
+    // the ReLU' mask (this pixel's out2 row, an L2 hit behind the Q producers) is fetched one
+    // row ahead of the accumulator it is applied to
+    float4 g[8];
+    auto load_mask = [&](int j) {
+      if (obase >= 0 && j < oh) {
+        const float4* mk = reinterpret_cast<const float4*>(a.out2 + obase + j * row);
+#pragma unroll
+        for (int c = 0; c < 8; c++) g[c] = __ldg(mk + c);
+      }
+    };
+    load_mask(0);
     for (int j = 0; j < oh; j++) {
       mbar_wait(&d2_done[j & 1], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
@@ -344,19 +369,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
       tcgen05_fence_before();
       mbar_arrive(&d2_free[j & 1]);
       if (obase < 0) continue;
-      const float4* mk = reinterpret_cast<const float4*>(a.out2 + obase + j * row);
       float4* o = reinterpret_cast<float4*>(a.d2 + obase + j * row);
 #pragma unroll
       for (int c = 0; c < 8; c++) {
-        const float4 g = __ldg(mk + c);
         float4 r;
-        r.x = g.x > 0.f ? (v[4 * c] + w[4 * c]) * cs : 0.f;
-        r.y = g.y > 0.f ? (v[4 * c + 1] + w[4 * c + 1]) * cs : 0.f;
-        r.z = g.z > 0.f ? (v[4 * c + 2] + w[4 * c + 2]) * cs : 0.f;
-        r.w = g.w > 0.f ? (v[4 * c + 3] + w[4 * c + 3]) * cs : 0.f;
+        r.x = g[c].x > 0.f ? (v[4 * c] + w[4 * c]) * cs : 0.f;
+        r.y = g[c].y > 0.f ? (v[4 * c + 1] + w[4 * c + 1]) * cs : 0.f;
+        r.z = g[c].z > 0.f ? (v[4 * c + 2] + w[4 * c + 2]) * cs : 0.f;
+        r.w = g[c].w > 0.f ? (v[4 * c + 3] + w[4 * c + 3]) * cs : 0.f;
         o[c] = r;
         dmax = fmaxf(fmaxf(dmax, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
       }
+      load_mask(j + 1);   // in flight while the next accumulator completes
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));

@@ -429,8 +429,12 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
         np.testing.assert_allclose(got[name], exp, rtol=RTOL, atol=ATOL, err_msg=name)
     g = net.grads()
     for l in range(3):
-        np.testing.assert_allclose(g["w%d" % (l + 1)], on.gw[l], rtol=RTOL, atol=1e-4, err_msg="gw%d" % l)
-        np.testing.assert_allclose(g["b%d" % (l + 1)], on.gb[l], rtol=RTOL, atol=1e-4, err_msg="gb%d" % l)
+        # sums over S * pixels terms: the absolute floor follows the size of the tensor's entries
+        # (a near-cancelling entry of a gradient whose other entries are ~500 is good to ~1e-6 of
+        # those, not to 1e-4 absolute)
+        for key, exp in (("w%d" % (l + 1), on.gw[l]), ("b%d" % (l + 1), on.gb[l])):
+            np.testing.assert_allclose(g[key], exp, rtol=RTOL, atol=1e-4 + 2e-6 * float(np.abs(exp).max()),
+                                       err_msg="g" + key)
 
 
 def test_layer1_deltas_fused_and_separate_agree(ctx, port):

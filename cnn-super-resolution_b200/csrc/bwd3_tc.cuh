@@ -46,12 +46,17 @@ struct Cfg {
   static constexpr int M = 128;                        // out2 pixels per strip row
   static constexpr int PW = 136, PB = PW * 16;         // oct plane: entries, bytes
   static constexpr int RP = 4, P_SLOT = 2 * PB;        // plane ring: hi plane + lo plane
-  static constexpr int GP = M * 16;                    // one 8-channel group plane of out2: 2 KB
+  // one 8-channel group plane of out2: 128 entries of 16 bytes + 32 bytes of padding, so that the
+  // four planes a quarter-warp of producers writes to start 8 banks apart
+  static constexpr int GP = M * 16 + 32;
   static constexpr int RQ = 3, Q_SLOT = 8 * GP;        // out2 ring: hi groups 0..3, lo groups 4..7
   static constexpr int KW = 48;                        // K of the d2 GEMM (3 steps of 16)
   static constexpr int W_BYTES = 2 * N * KW * 2;       // [W_hi 32 rows; W_lo 32 rows][48] halves
+  static constexpr int SP = 36;                        // floats per staged d2 pixel (128 B + pad)
   static constexpr int oP = 0, oQ = oP + RP * P_SLOT, oW = oQ + RQ * Q_SLOT;
-  static constexpr size_t SMEM_BYTES = (size_t)oW + W_BYTES;
+  static constexpr int oMask = oW + W_BYTES;           // [RQ][M] ReLU' masks of the out2 rows
+  static constexpr int oStage = oMask + RQ * M * 4;    // 4 epilogue warps x 32 pixels x SP floats
+  static constexpr size_t SMEM_BYTES = (size_t)oStage + 4 * 32 * SP * 4;
   static constexpr int W_E = 0, W_P = 4, N_P = 5, W_Q = W_P + N_P, N_Q = 8, W_I = W_Q + N_Q,
                        NT = (W_I + 2) * 32;
   static constexpr uint32_t cD2 = 0, cGW = 128, TMEM_COLS = 256;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
     }
     for (int i = 0; i < C::RQ; i++) {
       mbar_init(&qfull[i], C::N_Q * 32);
-      mbar_init(&qfree[i], 1);
+      mbar_init(&qfree[i], 1 + 128);   // the gradient MMAs + the epilogue's mask readers
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&d2_done[i], 1);
@@ -219,56 +224,81 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
     if (lane == 0) s_gb[warp - C::W_P] = gb;
   } else if (warp >= C::W_Q && warp < C::W_Q + C::N_Q) {
     // ============================ Q: out2 row -> MN-major planes ===============================
-    // thread = (pixel m, 16-channel half)
-    const int t = tid - C::W_Q * 32, m = t >> 1, half = t & 1;
-    const long long vm = X0 + m;
-    long long base = -1;
-    if (vm < vw) {
-      const int smp = (int)(vm / ow), x = (int)(vm - (long long)smp * ow);
-      base = (((long long)smp * oh) * ow + x) * C::N + half * 16;
+    // thread = (8-channel group g, pixels m0 and m0 + 64): a warp's lanes read consecutive
+    // 32-byte pieces (8 pixels x 128 bytes per instruction pair; a thread-per-pixel mapping
+    // touched 16-32 lines per load and kept the L1 pipe at 83 %, r2i)
+    const int t = tid - C::W_Q * 32, g = t & 3, m0 = t >> 2;
+    long long base[2];
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+      const long long vm = X0 + m0 + 64 * it;
+      base[it] = -1;
+      if (vm < vw) {
+        const int smp = (int)(vm / ow), x = (int)(vm - (long long)smp * ow);
+        base[it] = (((long long)smp * oh) * ow + x) * C::N + g * 8;
+      }
     }
     const long long row = (long long)ow * C::N;
     // three rows of loads in flight per thread (48 KB per SM): one row ahead left the HBM latency
-    // exposed on every row (r2h: the producers' first use of a loaded value was the top stall)
+    // exposed on every row
     constexpr int DEPTH = 3;
     float4 vq[DEPTH][4];
     auto load = [&](int j, float4 (&dst)[4]) {
-      if (base >= 0 && j < oh) {
-        const float4* p = reinterpret_cast<const float4*>(a.out2 + base + j * row);
 #pragma unroll
-        for (int c = 0; c < 4; c++) dst[c] = __ldg(p + c);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; c++) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 2; it++) {
+        if (base[it] >= 0 && j < oh) {
+          const float4* p = reinterpret_cast<const float4*>(a.out2 + base[it] + j * row);
+          dst[2 * it] = __ldg(p);
+          dst[2 * it + 1] = __ldg(p + 1);
+        } else {
+          dst[2 * it] = dst[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
 #pragma unroll
     for (int d = 0; d < DEPTH; d++) load(d, vq[d]);
-    uint8_t* my = smem_raw + C::oQ + (2 * half) * C::GP + m * 16;
+    uint8_t* my = smem_raw + C::oQ + g * C::GP + m0 * 16;
+    uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + C::oMask);
 #pragma unroll 1
     for (int j0 = 0; j0 < oh; j0 += DEPTH) {
 #pragma unroll
-    for (int d = 0; d < DEPTH; d++) {
-      const int j = j0 + d;
-      if (j >= oh) break;
-      float4 (&v)[4] = vq[d];
-      const int slot = j % C::RQ;
-      uint32_t hi[8], lo[8];
+      for (int d = 0; d < DEPTH; d++) {
+        const int j = j0 + d;
+        if (j < oh) {
+          const int slot = j % C::RQ;
+          uint32_t hi[8], lo[8], bits[2];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        split_h2(v[c].x * s_o, v[c].y * s_o, hi[2 * c], lo[2 * c]);
-        split_h2(v[c].z * s_o, v[c].w * s_o, hi[2 * c + 1], lo[2 * c + 1]);
+          for (int c = 0; c < 4; c++) {
+            const float4 v = vq[d][c];
+            split_h2(v.x * s_o, v.y * s_o, hi[2 * c], lo[2 * c]);
+            split_h2(v.z * s_o, v.w * s_o, hi[2 * c + 1], lo[2 * c + 1]);
+          }
+#pragma unroll
+          for (int it = 0; it < 2; it++) {   // ReLU' mask bits of this thread's 8 channels
+            const float4 p = vq[d][2 * it], q = vq[d][2 * it + 1];
+            uint32_t b = (p.x > 0.f ? 1u : 0u) | (p.y > 0.f ? 2u : 0u) | (p.z > 0.f ? 4u : 0u) |
+                         (p.w > 0.f ? 8u : 0u) | (q.x > 0.f ? 16u : 0u) | (q.y > 0.f ? 32u : 0u) |
+                         (q.z > 0.f ? 64u : 0u) | (q.w > 0.f ? 128u : 0u);
+            b <<= 8 * g;
+            b |= __shfl_xor_sync(0xffffffffu, b, 1);
+            b |= __shfl_xor_sync(0xffffffffu, b, 2);
+            bits[it] = b;                       // all 32 channels of the pixel
+          }
+          load(j + DEPTH, vq[d]);
+          if (j >= C::RQ) mbar_wait(&qfree[slot], (uint32_t)(((j / C::RQ) - 1) & 1));
+          uint8_t* sq = my + slot * C::Q_SLOT;
+          *reinterpret_cast<uint4*>(sq) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sq + 4 * C::GP) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(sq + 64 * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(sq + 4 * C::GP + 64 * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          if (g == 0) {
+            smask[slot * C::M + m0] = bits[0];
+            smask[slot * C::M + m0 + 64] = bits[1];
+          }
+          fence_proxy_async();
+          mbar_arrive(&qfull[slot]);
+        }
       }
-      load(j + DEPTH, vq[d]);
-      if (j >= C::RQ) mbar_wait(&qfree[slot], (uint32_t)(((j / C::RQ) - 1) & 1));
-      uint8_t* s = my + slot * C::Q_SLOT;
-      *reinterpret_cast<uint4*>(s) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(s + C::GP) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      *reinterpret_cast<uint4*>(s + 4 * C::GP) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(s + 5 * C::GP) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-      fence_proxy_async();
-      mbar_arrive(&qfull[slot]);
-    }
     }
   } else if (warp == C::W_I) {
     // ============================ I0: d2 = d3 (*) W3 ===========================================
@@ -345,17 +375,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
     const long long row = (long long)ow * C::N;
     const float cs = 1.f / (s_d * s_w);
     float dmax = 0.f;
-    // the ReLU' mask (this pixel's out2 row, an L2 hit behind the Q producers) is fetched one
-    // row ahead of the accumulator it is applied to
-    float4 g[8];
-    auto load_mask = [&](int j) {
-      if (obase >= 0 && j < oh) {
-        const float4* mk = reinterpret_cast<const float4*>(a.out2 + obase + j * row);
-#pragma unroll
-        for (int c = 0; c < 8; c++) g[c] = __ldg(mk + c);
-      }
-    };
-    load_mask(0);
+    const uint32_t* smask = reinterpret_cast<const uint32_t*>(smem_raw + C::oMask);
+    float* st = reinterpret_cast<float*>(smem_raw + C::oStage) + warp * (32 * C::SP);
     for (int j = 0; j < oh; j++) {
       mbar_wait(&d2_done[j & 1], (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
@@ -368,19 +389,34 @@ __global__ void __launch_bounds__(Cfg::NT, 1) bwd3_tc_kernel(Args a) {
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&d2_free[j & 1]);
-      if (obase < 0) continue;
-      float4* o = reinterpret_cast<float4*>(a.d2 + obase + j * row);
+      // ReLU' mask of this pixel's out2 row (bit n = out2[n] > 0), written by the Q producers;
+      // the accumulator can only be complete after the row's planes were full
+      const int qs = j % C::RQ;
+      mbar_wait(&qfull[qs], (uint32_t)((j / C::RQ) & 1));   // (the d2 MMAs do not depend on Q)
+      const uint32_t bits = smask[qs * C::M + m];
+      mbar_arrive(&qfree[qs]);
+      // stage the 32 pixels of this warp, then 8 lanes per pixel: every store instruction writes
+      // four full 128-byte lines
+      float4* own = reinterpret_cast<float4*>(st + lane * C::SP);
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         float4 r;
-        r.x = g[c].x > 0.f ? (v[4 * c] + w[4 * c]) * cs : 0.f;
-        r.y = g[c].y > 0.f ? (v[4 * c + 1] + w[4 * c + 1]) * cs : 0.f;
-        r.z = g[c].z > 0.f ? (v[4 * c + 2] + w[4 * c + 2]) * cs : 0.f;
-        r.w = g[c].w > 0.f ? (v[4 * c + 3] + w[4 * c + 3]) * cs : 0.f;
-        o[c] = r;
+        r.x = (bits >> (4 * c)) & 1u ? (v[4 * c] + w[4 * c]) * cs : 0.f;
+        r.y = (bits >> (4 * c + 1)) & 1u ? (v[4 * c + 1] + w[4 * c + 1]) * cs : 0.f;
+        r.z = (bits >> (4 * c + 2)) & 1u ? (v[4 * c + 2] + w[4 * c + 2]) * cs : 0.f;
+        r.w = (bits >> (4 * c + 3)) & 1u ? (v[4 * c + 3] + w[4 * c + 3]) * cs : 0.f;
+        own[c] = r;
         dmax = fmaxf(fmaxf(dmax, fmaxf(fabsf(r.x), fabsf(r.y))), fmaxf(fabsf(r.z), fabsf(r.w)));
       }
-      load_mask(j + 1);   // in flight while the next accumulator completes
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const int pp = it * 4 + (lane >> 3), ck = lane & 7;
+        const long long ob = __shfl_sync(0xffffffffu, obase, pp);
+        const float4 r = *reinterpret_cast<const float4*>(st + pp * C::SP + ck * 4);
+        if (ob >= 0) *reinterpret_cast<float4*>(a.d2 + ob + j * row + ck * 4) = r;
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));

@@ -170,6 +170,32 @@ class ClockSampler:
         return self.summary()
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the cores of its GPU's NUMA node BEFORE the pinned buffers are allocated
+    (first touch puts their pages on that node): with 8 ranks copying at once, buffers on the far
+    socket share the inter-socket link.  Best effort; returns the node or None."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id",
+                                       "--format=csv,noheader"], text=True).strip().lower()
+        # nvidia-smi prints an 8-digit domain (00000000:1b:00.0), sysfs uses 4 digits
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def synthetic_params(cfg, seed=1234):
     from helpers import make_params
     rng = np.random.default_rng(seed + cfg[0] + 7 * cfg[3])
@@ -300,6 +326,7 @@ def run_ours(args, rank, world, local_rank, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
@@ -607,6 +634,7 @@ def run_ours(args, rank, world, local_rank, wl):
     # frame workloads are long tensor-bound runs that can sit at the 1000 W power cap)
     line["clocks"] = wclocks.get("c3") if wclocks.get("c3", {}).get("samples") else clocks
     line["clocks_whole_run"] = clocks
+    line["config"]["numa_node_rank0"] = numa_node
 
     for key, name, metric in (("c2", "train", "srcnn_915_train_patches_per_s"),
                               ("c4", "train_c4", "srcnn_955_train_patches_per_s")):

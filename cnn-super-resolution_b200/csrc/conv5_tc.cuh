@@ -78,7 +78,7 @@ __host__ __device__ __forceinline__ float scale_for(float mx) {
   if (!(mx > 0.f) || !(mx < 1e30f)) return 1.f;
   int e;
   frexpf(mx, &e);   // mx = f * 2^e, f in [0.5, 1)
-  return ldexpf(1.f, 14 - e);
+  return ldexpf(1.f, min(14 - e, 100));   // (a tensor of denormal-sized values keeps a finite scale)
 }
 
 constexpr int F = 5, T = F * F;

@@ -758,9 +758,10 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
   // 18: 1.78, 20 (cap 3): 1.79, 24: 1.83, 32: 1.96; ramp cap 3 / 5 / 6 at 16: 1.78 / 1.83 / 1.79.
   static const int kSubDefault = std::getenv("SRCNN_E2E_SUBBANDS") ? std::atoi(std::getenv("SRCNN_E2E_SUBBANDS")) : 16;
   // bands of a multi-GPU partition are pipelined too (an 8-way split of C3 leaves 511 rows per
-  // rank): about one sub-band per 128 output rows, at most the default count
+  // rank, and with 8 ranks copying at once each gets ~18 GB/s of the host's pinned-copy rate, so
+  // the copies dominate even more): about one sub-band per 64 output rows, at most the default
   int n_sub = band_out_h >= 256
-                  ? std::min(std::min(std::max(kSubDefault, 2), kMaxSub), std::max(2, band_out_h / 128))
+                  ? std::min(std::min(std::max(kSubDefault, 2), kMaxSub), std::max(2, band_out_h / 64))
                   : 1;
   int sub_r0[kMaxSub + 1] = {0};
   {

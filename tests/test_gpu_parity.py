@@ -887,3 +887,108 @@ def test_host_row_pipeline_replay(ctx, port):
     np.testing.assert_array_equal(out2, single_launch(x)[40:])
     ctx.release(mi)
     ctx.release(mo)
+
+
+def test_exposed_parameters_are_never_cached(ctx, port):
+    """a parameter buffer whose raw pointer left the device layer (srcnn_mem_ptr) can
+    be written behind its back -- here by a device copy through a WRAPPED alias, which the
+    write tracking cannot attribute to the parameter handle.  Such a buffer must not be served
+    from the operand cache; srcnn_invalidate_params covers writers that never took the pointer
+    through this context."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    w, h = 150, 40
+    rng = np.random.default_rng(78)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    x = luma_image(rng, h, w)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    mi, mo = ctx.upload(x), ctx.alloc(4 * w3 * h3)
+
+    def run():
+        net.forward_fused(mi, mo, w, h, 1)
+        return ctx.read(mo, (1, h3, w3))
+
+    def expect(p):
+        _, _, e3 = port.net_forward(NetState(n1, n2, f1, f2, f3, p), x, w, h, 1)
+        return e3
+
+    assert float(np.abs(run() - expect(params)).max()) <= 1e-4
+    run()                                   # cached now
+    # write w2 through an alias of its raw pointer
+    p2 = dict(params)
+    p2["w2"] = (params["w2"] * 0.25).astype(np.float32)
+    alias = ctx.wrap(ctx.mem_ptr(net.c.w[1]), 4 * p2["w2"].size)   # mem_ptr marks w2 as exposed
+    src = ctx.upload(p2["w2"])
+    ctx.copy(src, alias)
+    assert float(np.abs(run() - expect(p2)).max()) <= 1e-4
+    # and once more through the alias: still followed
+    p3 = dict(p2)
+    p3["w2"] = (params["w2"] * 2.0).astype(np.float32)
+    ctx.write(src, p3["w2"])
+    ctx.copy(src, alias)
+    assert float(np.abs(run() - expect(p3)).max()) <= 1e-4
+    ctx.invalidate_params()                 # harmless on top
+    assert float(np.abs(run() - expect(p3)).max()) <= 1e-4
+
+
+def test_gather_and_frames_host_entries(ctx, port):
+    """srcnn_gather (the sample gather of execute_batch as one launch) and
+    srcnn_infer_frames_host (many frames through a ring of device slots: upload / forward /
+    download overlap) against their definitions."""
+    rng = np.random.default_rng(91)
+    # gather: 37 buffers of 33*33 floats (a size that is not a multiple of 16 bytes)
+    n, per = 37, 33 * 33
+    parts = [rng.normal(0, 1, per).astype(np.float32) for _ in range(n)]
+    handles = [ctx.upload(p) for p in parts]
+    dst = ctx.alloc(4 * per * n)
+    ctx.gather(handles[::-1], 4 * per, dst)
+    np.testing.assert_array_equal(ctx.read(dst, (n, per)), np.stack(parts[::-1]))
+    with pytest.raises(pkg.SrcnnError):
+        ctx.gather(handles, 4 * per, ctx.alloc(4 * per * (n - 1)))      # destination too small
+    with pytest.raises(pkg.SrcnnError):
+        ctx.gather(handles, 4 * per + 2, dst)                           # not a multiple of 4
+    # frames: both tensor-core networks, more frames than one group, ragged last group
+    for (n1, n2, wf, hf, nf, group) in ((128, 64, 160, 90, 7, 3), (64, 32, 96, 80, 5, 2)):
+        os.environ["SRCNN_FRAMES_GROUP"] = str(group)   # read once per process: first value wins
+        params = make_params(rng, n1, n2, 9, 1, 5)
+        net = pkg.Net(ctx, n1, n2, 9, 1, 5, params)
+        frames = np.stack([luma_image(rng, hf, wf) for _ in range(nf)])
+        hin, hout = pkg.PinnedBuffer((nf, hf, wf)), pkg.PinnedBuffer((nf, hf - 12, wf - 12))
+        hin.array[:] = frames
+        hout.array[:] = -1
+        net.infer_frames_host(hin.array, wf, hf, hout.array)
+        mi, mo = ctx.upload(frames), ctx.alloc(4 * nf * (hf - 12) * (wf - 12))
+        net.forward_fused(mi, mo, wf, hf, nf)
+        np.testing.assert_array_equal(hout.array, ctx.read(mo, (nf, hf - 12, wf - 12)))
+        _, _, e3 = port.net_forward(NetState(n1, n2, 9, 1, 5, params), frames, wf, hf, nf)
+        assert float(np.abs(hout.array - e3).max()) <= 1e-4
+        # a second call on the same buffers (ring state carried over correctly)
+        hin.array[:] = frames[::-1]
+        net.infer_frames_host(hin.array, wf, hf, hout.array)
+        np.testing.assert_allclose(hout.array, e3[::-1], atol=1e-4, rtol=0)
+
+
+def test_communicator_entries_on_one_rank(ctx):
+    """The multi-GPU entries on a single rank: a world of 1 joins, sums are no-ops, misuse is
+    reported (the 2..8-GPU behaviour is in tests/test_dp_gpu.py)."""
+    c = pkg.Context(0)
+    try:
+        assert c.comm_info() == (0, 1)
+        buf = c.upload(np.arange(8, dtype=np.float32))
+        c.allreduce_sum(buf, 8)                      # no communicator: sum over one rank
+        c.broadcast(buf, 8, 0)
+        uid = pkg.Context.comm_unique_id()
+        assert len(uid) == 128
+        with pytest.raises(pkg.SrcnnError):
+            c.comm_init(1, 1, uid)                   # rank outside the world
+        c.comm_init(0, 1, uid)
+        with pytest.raises(pkg.SrcnnError):
+            c.comm_init(0, 1, uid)                   # already joined
+        c.allreduce_sum(buf, 8)
+        np.testing.assert_array_equal(c.read(buf, (8,)), np.arange(8, dtype=np.float32))
+        with pytest.raises(pkg.SrcnnError):
+            c.allreduce_sum(buf, 9)                  # outside the buffer
+        c.comm_destroy()
+        assert c.comm_info() == (0, 1)
+    finally:
+        c.close()

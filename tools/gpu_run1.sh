@@ -11,10 +11,10 @@ timeout 60 tools/probe/mn16_probe > gpurun_out/${T}_mn16.log 2>&1; echo "probe r
 cat gpurun_out/${T}_mn16.log
 timeout 1200 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc $?"
 tail -3 gpurun_out/${T}_bench.err
-timeout 300 python tools/profile_targets.py c3 c2 c5 > gpurun_out/${T}_plain.log 2>&1 && \
+timeout 300 python tools/profile_targets.py c3 c2 c4 c5 > gpurun_out/${T}_plain.log 2>&1 && \
 timeout 1200 ncu --set full --clock-control none --import-source on \
-  -k regex:'forward_fused_hp|bwd3_fused|wgrad1_fused_tc|wgrad2_tc' \
-  -o gpurun_out/${T}_prof -f python tools/profile_targets.py c3 c2 c5 > gpurun_out/${T}_ncu.log 2>&1
+  -k regex:'forward_fused_hp|bwd3_tc_kernel|wgrad1_fused_tc|wgrad2_tc|conv5_tc_kernel|wgrad5' \
+  -o gpurun_out/${T}_prof -f python tools/profile_targets.py c3 c2 c4 c5 > gpurun_out/${T}_ncu.log 2>&1
 echo "ncu full rc $?"
 timeout 300 python bench.py --steps 2 --warmup 3 --workloads c3,c2 --no-cpu-baseline > gpurun_out/${T}_plain2.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \

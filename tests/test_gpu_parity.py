@@ -992,3 +992,49 @@ def test_communicator_entries_on_one_rank(ctx):
         assert c.comm_info() == (0, 1)
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,S", [((64, 32, 9, 1, 5), 150), ((64, 32, 9, 5, 5), 197),
+                                   ((64, 32, 9, 5, 5), 333), ((128, 64, 9, 1, 5), 40)])
+def test_no_writes_outside_the_callers_buffers(ctx, cfg, S):
+    """Every buffer of a training chunk and of a fused inference call is a view into ONE arena
+    with 64 KB of sentinel bytes on both sides: the tensor-core kernels (full-line staged stores,
+    virtual-image tiles that hang over the last sample, the workspace carve-up of
+    srcnn_train_workspace_bytes) must leave every sentinel byte alone.  (compute-sanitizer is
+    closed on this pool; this is the bounds check we can run.)"""
+    rng = np.random.default_rng(5)
+    w = 33
+    GAP = 64 * 1024
+    net0 = pkg.Net(ctx, *cfg, make_params(rng, *cfg))
+    sizes = {"in": 4 * S * w * w, "gt": 4 * S * w * w,   # ground truth is full size (centre crop)
+             "work": net0.train_workspace_bytes(w, w, S), "grads": 4 * net0.grad_count,
+             "out": 4 * S * (w - net0.padding) ** 2}
+    offs, total = {}, GAP
+    for k, n in sizes.items():
+        offs[k] = total
+        total += (n + 255) // 256 * 256 + GAP
+    arena = ctx.alloc(total)
+    ctx.write(arena, np.full(total, 0xA5, np.uint8))
+    base = ctx.mem_ptr(arena)
+    view = {k: ctx.wrap(base + offs[k], sizes[k]) for k in sizes}
+    x, gt = patches(rng, S, w, w)
+    ctx.write(view["in"], x)
+    ctx.write(view["gt"], gt)
+    ctx.write(view["grads"], np.zeros(net0.grad_count, np.float32))
+    net = pkg.Net(ctx, *cfg, make_params(rng, *cfg), grad_flat=view["grads"])
+    net.train_chunk(view["in"], view["gt"], w, w, S, view["work"])
+    net.train_chunk(view["in"], view["gt"], w, w, S, view["work"])
+    if net.fused_supported():
+        net.forward_fused(view["in"], view["out"], w, w, S)
+    ctx.block()
+    after = ctx.read(arena, (total,), np.uint8)
+    inside = np.zeros(total, bool)
+    for k in sizes:
+        inside[offs[k]:offs[k] + sizes[k]] = True
+    bad = np.flatnonzero(~inside & (after != 0xA5))
+    assert bad.size == 0, "bytes written outside the buffers: first at arena offset %d (%s)" % (
+        bad[0], {k: (offs[k], sizes[k]) for k in sizes})
+    assert all(np.isfinite(g).all() for g in net.grads().values())
+    np.testing.assert_array_equal(ctx.read(view["in"], x.shape), x)   # inputs are read-only
+    np.testing.assert_array_equal(ctx.read(view["gt"], gt.shape), gt)

@@ -635,7 +635,7 @@ def run_ours(args, rank, world, local_rank, wl):
         achieved_tf = alg_flop / (c["ms"] / 1e3) / 1e12
         impl = os.environ.get("SRCNN_FUSED_IMPL", "hp")
         split = 6.0 if impl == "pl" else 3.0
-        traffic, traffic_src = ncu_traffic("forward_fused_hp_kernel<0>")
+        traffic, traffic_src = ncu_traffic("forward_fused_hp_kernel<0, 0>")
         if impl == "simt":
             roofline = {"kernel": "forward_fused_kernel (FP32 SIMT)", "bound": "hbm",
                         "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -66,8 +66,17 @@ def main():
         return v * mult.get(unit, 1)
 
     for name, r in last.items():
-        m = re.match(r"^(?:void\s+)?([\w:]+(?:<.*?>)?)", name)
-        short = (m.group(1) if m else name).replace("srcnn::", "")
+        short = re.sub(r"^void\s+", "", name).replace("srcnn::", "")
+        short = short[:short.index("(")] if "(" in short.replace("(bool)", "") else short
+        short = re.sub(r"\(bool\)([01])", r"\1", short)
+        depth, cut = 0, len(short)      # up to the end of the (nested) template argument list
+        for i, ch in enumerate(short):
+            depth += ch == "<"
+            depth -= ch == ">"
+            if ch == "(" and depth == 0:
+                cut = i
+                break
+        short = short[:cut]
         out.append("")
         out.append("== %s" % short)
         for k in KEEP:
@@ -77,7 +86,7 @@ def main():
         if rd is not None and wr is not None:
             rb = to_bytes(rd, units[col["dram__bytes_read.sum"]])
             wb = to_bytes(wr, units[col["dram__bytes_write.sum"]])
-            key = re.sub(r"^.*::", "", short)
+            key = re.sub(r"\b\w+::", "", short)      # drop every namespace qualifier
             key = re.sub(r"<\(bool\)([01])>", r"<\1>", key)
             traffic[key] = {"dram_bytes": rb + wb, "dram_read": rb, "dram_write": wb,
                             "source": "profiles/%s_ncu_summary.txt" % tag}

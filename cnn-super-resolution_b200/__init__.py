@@ -101,6 +101,7 @@ _SIGS = {
     "srcnn_forward_fused_supported": (_i, [C.POINTER(CNet)]),
     "srcnn_forward_fused": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64, _u64]),
     "srcnn_infer_rows_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _i, _vp]),
+    "srcnn_infer_rows_host_async": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _i, _vp]),
     "srcnn_infer_frames_host": (_i, [_vp, C.POINTER(CNet), _vp, _i, _i, _i, _vp]),
     "srcnn_train_chunk": (_i, [_vp, C.POINTER(CNet), _u64, _u64, _i, _i, _i, _u64]),
     "srcnn_train_chunks_host": (_i, [_vp, C.POINTER(CNet), _vp, _vp, _i, _i, _i, _i, _u64]),
@@ -413,11 +414,13 @@ class Net:
         _check(self.ctx.L.srcnn_forward_fused(self.ctx.h, C.byref(self.c), inp, out, w, h, S,
                                               scratch1, scratch2))
 
-    def infer_rows_host(self, host_in, w, h, row0, row1, host_out):
-        """host_in: full [h][w] float32 image; host_out: array whose first row is output row row0."""
+    def infer_rows_host(self, host_in, w, h, row0, row1, host_out, block=True):
+        """host_in: full [h][w] float32 image; host_out: array whose first row is output row row0.
+        block=False queues the call (two can be in flight); Context.block() completes them."""
         assert host_in.dtype == np.float32 and host_out.dtype == np.float32
-        _check(self.ctx.L.srcnn_infer_rows_host(self.ctx.h, C.byref(self.c), _np_ptr(host_in), w,
-                                                h, row0, row1, _np_ptr(host_out)))
+        fn = self.ctx.L.srcnn_infer_rows_host if block else self.ctx.L.srcnn_infer_rows_host_async
+        _check(fn(self.ctx.h, C.byref(self.c), _np_ptr(host_in), w, h, row0, row1,
+                  _np_ptr(host_out)))
 
     def infer_frames_host(self, host_in, w, h, host_out):
         """host_in: [n][h][w] float32 frames; host_out: [n][h3][w3].  Upload / forward / download

@@ -140,6 +140,21 @@ struct srcnn_ctx {
   unsigned long long e2e_key[20] = {};
   unsigned e2e_graph_launches = 0;
   cudaEvent_t ev_join[2] = {};
+  // srcnn_infer_rows_host_async: two lanes, each with its own stream, staging and graph, used
+  // alternately, so that the tail (download) of one call overlaps the head (upload, first
+  // launches) of the next.  lanes_busy: work may be in flight on a lane stream.
+  struct RowsLane {
+    cudaStream_t stream = nullptr;
+    void* in = nullptr;
+    void* out = nullptr;
+    size_t in_bytes = 0, out_bytes = 0;
+    cudaGraphExec_t graph = nullptr;
+    unsigned long long key[20] = {};
+    unsigned graph_launches = 0;
+  } lanes[2];
+  unsigned lane_next = 0;
+  bool lanes_busy = false;
+  cudaEvent_t lane_ev = nullptr;
   static constexpr int kEvents = 32;
   cudaEvent_t ev_in[kEvents] = {}, ev_k[kEvents] = {};
   cudaEvent_t ev_d[4] = {};   // download-finished events of srcnn_infer_frames_host's ring
@@ -153,9 +168,24 @@ struct srcnn_ctx {
   static constexpr size_t kRedScratchBytes = 64 * 1024;
 
   // a device-layer call is about to write the allocation behind `h`
+  // waits for the calls srcnn_infer_rows_host_async has in flight
+  cudaError_t drain_lanes() {
+    if (!lanes_busy) return cudaSuccess;
+    lanes_busy = false;
+    for (RowsLane& l : lanes)
+      if (l.stream) {
+        const cudaError_t e = cudaStreamSynchronize(l.stream);
+        if (e != cudaSuccess) return e;
+      }
+    return cudaSuccess;
+  }
+
   void note_write(srcnn_mem h) {
     for (int i = 0; i < 6; i++)
-      if (hp_cache_valid && hp_cache_h[i] == h) write_gen++;
+      if (hp_cache_valid && hp_cache_h[i] == h) {
+        write_gen++;
+        drain_lanes();   // an asynchronous inference may still be reading these parameters
+      }
     if (c5_valid && c5_h == h) c5_valid = false;
   }
 

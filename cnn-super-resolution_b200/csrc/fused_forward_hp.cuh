@@ -830,7 +830,7 @@ inline bool supported(int n1, int n2, int f1, int f2, int f3) {
 // the per-context ring of scale blocks: launches on different streams (the pipelined
 // host-buffer inference) must not share one
 inline int scale_slot(srcnn_ctx* ctx, Scales** sc, unsigned** ws) {
-  constexpr int kSlots = 32;
+  constexpr int kSlots = 128;   // three captured pipelines of 16-32 launches keep theirs
   if (!ctx->hp_scales) {
     SRCNN_CUDA(cudaMalloc(&ctx->hp_scales, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));
     SRCNN_CUDA(cudaMemset(ctx->hp_scales, 0, kSlots * (sizeof(Scales) + 2 * sizeof(unsigned))));

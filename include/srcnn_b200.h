@@ -217,6 +217,16 @@ int srcnn_forward_fused_supported(const srcnn_net* net);
  * result is in host_out on return.  Pinned host buffers give the PCIe rate; pageable ones work. */
 int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in, int in_w,
                           int in_h, int out_row0, int out_row1, float* host_out);
+/* The same call, NON-BLOCKING: the reference's read_buffer(..., block = false) followed by
+ * Context::block() (src/opencl/Context.cpp:255-276, 120-126).  Returns once the work is queued;
+ * host_out is complete (and host_in may be rewritten) after srcnn_block(ctx) or after the next
+ * blocking device-layer call on the parameters.  Two calls can be in flight: consecutive calls
+ * alternate between two lanes (stream + staging + graph each), so that for a STREAM of images
+ * the download of image i overlaps the upload and the first launches of image i+1 -- the
+ * throughput tends to max(H2D, compute, D2H) per image instead of one call's head + tail on top.
+ * Calls in flight must not share host_out.  Pinned host buffers are required for the overlap. */
+int srcnn_infer_rows_host_async(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in,
+                                int in_w, int in_h, int out_row0, int out_row1, float* host_out);
 
 /* ConfigBasedDataPipeline::forward(sample) for MANY frames (src/ConfigBasedDataPipeline.cpp:
  * 114-126 is called once per image by src/Main_cl.cpp:217-239): `n_frames` luma frames of

@@ -1038,3 +1038,52 @@ def test_no_writes_outside_the_callers_buffers(ctx, cfg, S):
     assert all(np.isfinite(g).all() for g in net.grads().values())
     np.testing.assert_array_equal(ctx.read(view["in"], x.shape), x)   # inputs are read-only
     np.testing.assert_array_equal(ctx.read(view["gt"], gt.shape), gt)
+
+
+@pytest.mark.gpu
+def test_host_row_pipeline_async_stream_of_images(ctx, port):
+    """srcnn_infer_rows_host_async: a stream of images through the two lanes (several calls queued
+    before one Context.block()) gives, image by image, the bits of the blocking call; a parameter
+    write between two calls waits for the calls in flight and is seen by the next one; small bands
+    (single launch) and the blocking call in between work too."""
+    n1, n2, f1, f2, f3 = 64, 32, 9, 1, 5
+    w, h = 180, 700
+    rng = np.random.default_rng(31)
+    params = make_params(rng, n1, n2, f1, f2, f3)
+    net = pkg.Net(ctx, n1, n2, f1, f2, f3, params)
+    (_, _), (_, _), (w3, h3) = net.out_dims(w, h)
+    n_img = 5
+    hin = [pkg.PinnedBuffer((h, w)) for _ in range(n_img)]
+    hout = [pkg.PinnedBuffer((h3, w3)) for _ in range(n_img)]
+    ref = pkg.PinnedBuffer((h3, w3))
+    expect = []
+    for b in hin:
+        b.array[:] = luma_image(rng, h, w)
+        net.infer_rows_host(b.array, w, h, 0, h3, ref.array)
+        expect.append(ref.array.copy())
+    for rep in range(2):                  # first pass captures both lanes, second replays them
+        for o in hout:
+            o.array[:] = -1.0
+        for i in range(n_img):
+            net.infer_rows_host(hin[i].array, w, h, 0, h3, hout[i].array, block=False)
+        ctx.block()
+        for i in range(n_img):
+            np.testing.assert_array_equal(hout[i].array, expect[i], err_msg="image %d" % i)
+    # parameter write with two calls in flight, then one more call: old, old, new parameters
+    net.infer_rows_host(hin[0].array, w, h, 0, h3, hout[0].array, block=False)
+    net.infer_rows_host(hin[1].array, w, h, 0, h3, hout[1].array, block=False)
+    ctx.write(net.c.w[1], (params["w2"] * 0.5).astype(np.float32))
+    net.infer_rows_host(hin[2].array, w, h, 0, h3, hout[2].array, block=False)
+    ctx.block()
+    np.testing.assert_array_equal(hout[0].array, expect[0])
+    np.testing.assert_array_equal(hout[1].array, expect[1])
+    net.infer_rows_host(hin[2].array, w, h, 0, h3, ref.array)      # blocking, new parameters
+    assert not np.array_equal(ref.array, expect[2])
+    np.testing.assert_array_equal(hout[2].array, ref.array)
+    # a band below the pipelining threshold (one launch), asynchronous, then a blocking call
+    small = pkg.PinnedBuffer((100, w3))
+    net.infer_rows_host(hin[3].array, w, h, 50, 150, small.array, block=False)
+    net.infer_rows_host(hin[3].array, w, h, 0, h3, ref.array)      # drains the lanes first
+    np.testing.assert_array_equal(small.array, ref.array[50:150])
+    for b in hin + hout + [ref, small]:
+        b.free()

@@ -151,9 +151,11 @@ struct srcnn_ctx {
     cudaGraphExec_t graph = nullptr;
     unsigned long long key[20] = {};
     unsigned graph_launches = 0;
+    srcnn_mem params[6] = {};   // the parameter buffers the lane's call in flight reads
   } lanes[2];
   unsigned lane_next = 0;
   bool lanes_busy = false;
+
   cudaEvent_t lane_ev = nullptr;
   static constexpr int kEvents = 32;
   cudaEvent_t ev_in[kEvents] = {}, ev_k[kEvents] = {};
@@ -181,11 +183,14 @@ struct srcnn_ctx {
   }
 
   void note_write(srcnn_mem h) {
+    if (lanes_busy)
+      for (int i = 0; i < 12; i++)
+        if (lanes[i / 6].params[i % 6] == h) {
+          drain_lanes();   // an asynchronous inference is still reading these parameters
+          break;
+        }
     for (int i = 0; i < 6; i++)
-      if (hp_cache_valid && hp_cache_h[i] == h) {
-        write_gen++;
-        drain_lanes();   // an asynchronous inference may still be reading these parameters
-      }
+      if (hp_cache_valid && hp_cache_h[i] == h) write_gen++;
     if (c5_valid && c5_h == h) c5_valid = false;
   }
 

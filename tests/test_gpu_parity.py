@@ -19,6 +19,14 @@ from oracle.loader import NetState
 pytestmark = pytest.mark.gpu
 pkg = _pkg.load()
 
+# A/B switches of the library (README "Environment switches"): the whole file can be run under
+# any of them as a check of the fallback kernels; the few tests that assert WHICH kernel ran are
+# skipped then.
+SWITCHED = [k for k in ("SRCNN_FUSED_IMPL", "SRCNN_C5_IMPL", "SRCNN_B3_IMPL", "SRCNN_GW_IMPL",
+                        "SRCNN_D1_IMPL") if os.environ.get(k)]
+default_paths_only = pytest.mark.skipif(bool(SWITCHED), reason="asserts the default kernel "
+                                        "selection; %s is set" % ", ".join(SWITCHED))
+
 RTOL, ATOL = 1e-4, 1e-5
 
 
@@ -185,6 +193,7 @@ def test_deltas_vs_oracle(ctx, port, shape):
                                port.deltas(dn, lo, W, nc, fn, nn, ow, oh, S), rtol=RTOL, atol=ATOL)
 
 
+@default_paths_only
 @pytest.mark.parametrize("w1,h1,S", [(25, 25, 170), (30, 19, 150), (25, 25, 333)])
 def test_conv5_tensor_core_kernels_vs_oracle(ctx, port, w1, h1, S):
     """The 9-5-5 network's layer 2 on the tensor cores (conv5_tc.cuh): forward 64 -> 32 and the
@@ -437,6 +446,7 @@ def test_train_chunk_vs_oracle(ctx, port, cfg):
                                        err_msg="g" + key)
 
 
+@default_paths_only
 def test_layer1_deltas_fused_and_separate_agree(ctx, port):
     """The layer-1 deltas normally live inside the layer-1 gradient kernel; with
     SRCNN_D1_IMPL=separate they are materialised by their own launch.  Same gradients either
@@ -571,6 +581,7 @@ def test_baseline_sized_epochs_vs_committed_reference(ctx, name, route):
         ctx.release(m)
 
 
+@default_paths_only
 @pytest.mark.parametrize("cfg", [(64, 32, 9, 1, 5), (64, 32, 9, 5, 5)])
 def test_chunk_views_need_only_float_alignment(ctx, cfg):
     """A chunk that starts at a sample offset which is not a multiple of 4 samples is only

@@ -270,6 +270,9 @@ inline int fused_prepare(srcnn_ctx* ctx, int n1, int n2, int f1, int f2, int f3,
     *out = ctx->hp_cache;
     return SRCNN_OK;
   }
+  // the image is about to be rewritten: calls srcnn_infer_rows_host_async still has in flight
+  // (for other parameters) read it
+  SRCNN_CUDA(ctx->drain_lanes());
   if (!ctx->hp_cache) {
     constexpr size_t bytes = sizeof(fused_hpw::Scales) > sizeof(fused_hp::Scales)
                                  ? sizeof(fused_hpw::Scales) : sizeof(fused_hp::Scales);

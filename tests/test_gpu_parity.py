@@ -1091,6 +1091,19 @@ def test_host_row_pipeline_async_stream_of_images(ctx, port):
     net.infer_rows_host(hin[2].array, w, h, 0, h3, ref.array)      # blocking, new parameters
     assert not np.array_equal(ref.array, expect[2])
     np.testing.assert_array_equal(hout[2].array, ref.array)
+    # two different networks in flight: a write to the first one's parameters waits for it too
+    params_b = make_params(np.random.default_rng(32), n1, n2, f1, f2, f3)
+    net_b = pkg.Net(ctx, n1, n2, f1, f2, f3, params_b)
+    net_b.infer_rows_host(hin[4].array, w, h, 0, h3, ref.array)
+    expect_b = ref.array.copy()
+    net.infer_rows_host(hin[0].array, w, h, 0, h3, ref.array)
+    expect_a = ref.array.copy()
+    net.infer_rows_host(hin[0].array, w, h, 0, h3, hout[0].array, block=False)
+    net_b.infer_rows_host(hin[4].array, w, h, 0, h3, hout[4].array, block=False)
+    ctx.write(net.c.b[0], np.zeros(n1, np.float32))        # first net, two calls ago
+    ctx.block()
+    np.testing.assert_array_equal(hout[0].array, expect_a)
+    np.testing.assert_array_equal(hout[4].array, expect_b)
     # a band below the pipelining threshold (one launch), asynchronous, then a blocking call
     small = pkg.PinnedBuffer((100, w3))
     net.infer_rows_host(hin[3].array, w, h, 50, 150, small.array, block=False)

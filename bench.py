@@ -719,6 +719,29 @@ def run_ours(args, rank, world, local_rank, wl):
                 "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": hbm_peak,
                         "frac": achieved_gbs / hbm_peak,
                         "algorithmic_bytes_per_launch": alg_bytes}}
+            if split == 3.0 and world == 1:
+                # what the MMA operand traffic of the scheme allows (profiles/r2zb_cta2_probe.txt):
+                # per 128-pixel tile 6 x (67 + 51) cycles of shared-memory operand fetch for layer
+                # 1 and 12 x 60 cycles of TMEM operand reads for layers 2 and 3
+                strips, rows = -(-(IMG - 12) // 124), IMG - 12
+                sms = torch.cuda.get_device_properties(0).multi_processor_count
+                best = None     # the launcher's band-height rule (fused_forward_pl.cuh: rows_per_cta)
+                for nb in range(1, min(512, rows) + 1):
+                    r = -(-rows // nb)
+                    cost = -(-(strips * -(-rows // r)) // sms) * (r + 4 + 8)
+                    if best is None or cost < best[0]:
+                        best = (cost, r)
+                bands = -(-rows // best[1])
+                tiles_per_sm = strips * (rows + 4 * bands) / sms
+                mhz = (wclocks.get("c3") or {}).get("sm_mhz") or 1965.0
+                cyc = c["ms"] * 1e-3 * mhz * 1e6 / tiles_per_sm
+                roofline["mma_operand_model"] = {
+                    "cycles_per_tile_model": 6 * (67 + 51) + 12 * 60, "cycles_per_tile": cyc,
+                    "frac": (6 * (67 + 51) + 12 * 60) / cyc, "tiles_per_sm": tiles_per_sm,
+                    "source": "profiles/r2zb_cta2_probe.txt, profiles/r2w_fused_kernel_sensitivity.txt",
+                    "note": "the kernel's tile period against the measured cost of its 24 MMA "
+                            "instructions per tile (operand fetch: shared memory 128 B/clk, TMEM "
+                            "64 B/clk); launch and prologue time is inside cycles_per_tile"}
         line.update({"value": mpix, "ms_per_step": c["ms"], "gpu_launches": int(c["launches"]),
                      "roofline": roofline,
                      "e2e": {"value": e2e_mpix, "unit": "MPix/s", "ms_per_step": c["e2e_ms"],

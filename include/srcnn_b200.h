@@ -224,7 +224,9 @@ int srcnn_infer_rows_host(srcnn_ctx* ctx, const srcnn_net* net, const float* hos
  * alternate between two lanes (stream + staging + graph each), so that for a STREAM of images
  * the download of image i overlaps the upload and the first launches of image i+1 -- the
  * throughput tends to max(H2D, compute, D2H) per image instead of one call's head + tail on top.
- * Calls in flight must not share host_out.  Pinned host buffers are required for the overlap. */
+ * Calls in flight must not share host_out.  Pinned host buffers are required for the overlap.
+ * A device-layer write to the network's parameters, or a call with other parameters, first waits
+ * for the calls in flight; in profile mode (and with SRCNN_E2E_GRAPH=0) the call is blocking. */
 int srcnn_infer_rows_host_async(srcnn_ctx* ctx, const srcnn_net* net, const float* host_in,
                                 int in_w, int in_h, int out_row0, int out_row1, float* host_out);
 

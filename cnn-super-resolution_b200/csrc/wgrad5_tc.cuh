@@ -45,7 +45,10 @@ struct Cfg {
   static constexpr int KS = 16;                         // pixels per K-step (one f16 MMA)
   static constexpr int RBN = 32;                        // ring blocks of 16 pixels
   static constexpr int RPX = RBN * KS + KS;             // plane entries: ring + mirror block
-  static constexpr int PLANE = RPX * 16;                // bytes per 8-channel plane
+  // bytes per 8-channel plane, + 16: the four plane pairs a quarter-warp of PB threads writes
+  // then start 32 bytes apart modulo 128 (all in the same banks without it: 16 instead of 4
+  // wavefronts per store, profiles/r2s)
+  static constexpr int PLANE = RPX * 16 + 16;
   static constexpr int oBh = 0, oBl = oBh + 8 * PLANE;  // out1 hi / lo: 8 planes each
   static constexpr int NSTAGE = 3;
   static constexpr int TILE = 16 * KS * 16;             // one A tile: 16 groups x 16 px x 16 B
@@ -122,6 +125,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad5_tc_kernel(Args a) {
   if (warp < C::N_PA) {
     // ============================ PA: the 8 shifted copies of the d2 tile ======================
     // thread = (set, copy j, pixel kk, 16-channel half): value d2pad[Q0 + 16 i + kk - lag]
+    // (the channel half in lane bit 0 costs the stores a 2-way bank conflict -- the two
+    // destinations are 512 bytes apart -- but keeps a quarter-warp's loads within 4 lines; with the
+    // pixel in the low bits the stores are conflict-free and the chunk's gradients 10 % SLOWER)
     const int set = tid >> 7, j = (tid >> 5) & 3, kk = (tid >> 1) & 15, half = tid & 1;
     const int lag = set == 0 ? j : j * w1;
     // first K-step whose pixel is not before Q0, and that pixel's (sample, y, x)

@@ -247,25 +247,38 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
 
   if (warp >= C::W_P && warp < C::W_P + C::N_P) {
     // ============================ P: plane producers ==========================================
-    // thread q owns plane entry q = virtual input column X0 - P + q
-    const int q = tid - C::W_P * 32;
-    const long long vin = X0 - P + q;
-    long long base = -1;   // float offset of (sample, row 0, x, channel 0), -1 = zero column
-    if (q < C::PW && vin >= 0 && vin < vw) {
-      const int smp = (int)(vin / slot_w), x = (int)(vin - (long long)smp * slot_w);
-      if (x < iw) base = (((long long)smp * ih) * iw + x) * C::CIN;
+    // item = (plane entry q = virtual input column X0 - P + q, 8-channel chunk ch of the slice);
+    // a thread owns items t and t + 160.  Two lanes per pixel: a quarter-warp's 16-byte loads
+    // fall into 4 lines (one lane per pixel with the whole 64-byte slice: 8 lines per quarter
+    // and 32 per instruction -- the L1 pipe these kernels are bound by counts lines)
+    const int t = tid - C::W_P * 32;
+    long long base[2];       // float offset of (sample, row 0, x, channel 8 ch), -1 = zero column
+    uint8_t* my[2];
+    bool live[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int item = t + k * (C::N_P * 32), q = item >> 1, ch = item & 1;
+      const long long vin = X0 - P + q;
+      base[k] = -1;
+      live[k] = q < C::PW;
+      if (q < C::PW && vin >= 0 && vin < vw) {
+        const int smp = (int)(vin / slot_w), x = (int)(vin - (long long)smp * slot_w);
+        if (x < iw) base[k] = (((long long)smp * ih) * iw + x) * C::CIN + ch * 8;
+      }
+      my[k] = smem_raw + C::oSlots + ch * C::PB + q * 16;
     }
     const long long row_stride = (long long)iw * C::CIN;
-    uint8_t* my = smem_raw + C::oSlots + q * 16;
-    float4 v[4];
+    float4 v[2][2];
     auto load = [&](int r, int c) {
-      if (base >= 0) {
-        const float4* p = reinterpret_cast<const float4*>(a.in + base + r * row_stride + c * 16);
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = __ldg(p + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 2; k++) {
+        if (base[k] >= 0) {
+          const float4* p = reinterpret_cast<const float4*>(a.in + base[k] + r * row_stride + c * 16);
+          v[k][0] = __ldg(p);
+          v[k][1] = __ldg(p + 1);
+        } else {
+          v[k][0] = v[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     load(0, 0);
@@ -273,12 +286,14 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     for (int r = 0; r < ih; r++) {
       for (int c = 0; c < C::NSLICE; c++, it++) {
         const int slot = it % C::NSLOT;
-        uint32_t hi[8], lo[8];
+        uint32_t hi[2][4], lo[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          split_h2(v[j].x * s_in, v[j].y * s_in, hi[2 * j], lo[2 * j]);
-          split_h2(v[j].z * s_in, v[j].w * s_in, hi[2 * j + 1], lo[2 * j + 1]);
-        }
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            split_h2(v[k][j].x * s_in, v[k][j].y * s_in, hi[k][2 * j], lo[k][2 * j]);
+            split_h2(v[k][j].z * s_in, v[k][j].w * s_in, hi[k][2 * j + 1], lo[k][2 * j + 1]);
+          }
         // the loads of the next slice fly while this thread waits for its slot
         {
           int nr = r, nc = c + 1;
@@ -286,13 +301,13 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
           if (nr < ih) load(nr, nc);
         }
         if (it >= C::NSLOT) mbar_wait(&empty[slot], (uint32_t)(((it / C::NSLOT) - 1) & 1));
-        if (q < C::PW) {
-          uint8_t* s = my + slot * C::SLOT_BYTES;
-          *reinterpret_cast<uint4*>(s) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(s + C::PB) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(s + 2 * C::PB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(s + 3 * C::PB) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+          if (live[k]) {
+            uint8_t* sdst = my[k] + slot * C::SLOT_BYTES;
+            *reinterpret_cast<uint4*>(sdst) = make_uint4(hi[k][0], hi[k][1], hi[k][2], hi[k][3]);
+            *reinterpret_cast<uint4*>(sdst + 2 * C::PB) = make_uint4(lo[k][0], lo[k][1], lo[k][2], lo[k][3]);
+          }
         fence_proxy_async();
         mbar_arrive(&full[slot]);
       }

@@ -52,8 +52,20 @@ struct Cfg {
 #ifndef HP_N_E1
 #define HP_N_E1 8
 #endif
-  static constexpr int W_E1 = 0, N_E1 = HP_N_E1, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4,
-                       N_IM = 5, W_I1 = W_IM + N_IM, W_I2 = W_I1 + 1, W_I3 = W_I2 + 1;
+  // role -> warp ids.  Every E role needs warp % 4 = its TMEM lane quarter, so E blocks start at
+  // multiples of 4; the plane producers are 4 + 1 warps (IMA: columns 0..127, IMB: 128..143).
+#ifndef HP_ORDER
+#define HP_ORDER 0
+#endif
+  static constexpr int N_E1 = HP_N_E1, N_IM = 5;
+#if HP_ORDER == 0
+  static constexpr int W_E1 = 0, W_E2 = N_E1, W_E3 = W_E2 + 4, W_IM = W_E3 + 4, N_IMA = 5, W_IMB = -1;
+#elif HP_ORDER == 1
+  static constexpr int W_IM = 0, N_IMA = 4, W_E1 = 4, W_E2 = W_E1 + N_E1, W_E3 = W_E2 + 4, W_IMB = W_E3 + 4;
+#else
+  static constexpr int W_IM = 0, N_IMA = 4, W_E3 = 4, W_E2 = 8, W_E1 = 12, W_IMB = W_E1 + N_E1;
+#endif
+  static constexpr int W_I1 = N_E1 + 8 + N_IM, W_I2 = W_I1 + 1, W_I3 = W_I2 + 1;
   static constexpr int NT = (W_I3 + 1) * 32;
   static constexpr int E1_CHUNKS = (N1 / 16) / (N_E1 / 4);   // 16-channel chunks per E1 warp
   static constexpr int IM_THREADS = N_IM * 32;
@@ -85,6 +97,33 @@ struct Cfg {
   //   D2: [0,32), [32,64)                       ->  A3: [0,16) hi pairs, [32,48) lo pairs
   //   D3: [0,32), [32,64) (25 taps of 32 used)
   static constexpr uint32_t cD1 = 0, cD2 = 256, cD3 = 384;
+  // layers 2 and 3 with ONE accumulator: three N = n instructions per K-step (hi.w_hi, hi.w_lo,
+  // lo.w_hi -- the low halves are unscaled, so the three products share a scale) instead of a
+  // stacked N = 2n one + an N = n one.  The tensor pipe pays ~5 cycles more per K-step (A from
+  // tensor memory: 20.5 cycles at N = 32, 36 at N = 64, tools/probe/ts_probe.cu); E2 / E3 lose
+  // the addition of the two accumulator halves and half their tensor-memory loads.
+#ifndef HP_ACC1_23
+#define HP_ACC1_23 0
+#endif
+  static constexpr bool ACC1_23 = HP_ACC1_23 != 0;
+  static constexpr uint32_t A3LO = ACC1_23 ? 16 : N2;   // column of A3's low half pairs
+  // A2 in its OWN tensor-memory columns (needs the single-accumulator layers 2 / 3 to fit):
+  // D1[b&1] is free again as soon as E1 has LOADED it, not after E1 has converted it and MMA-2
+  // has read the result -- the loop MMA-1(b) -> E1(b) -> MMA-2(b) -> MMA-1(b+2) over the two D1
+  // buffers was the tile period (tools/hp_prof.py: I1 waited 530 of 1 900 cycles per tile for it)
+#ifndef HP_A2SEP
+#define HP_A2SEP 0
+#endif
+  static constexpr bool A2SEP = HP_A2SEP != 0;
+  static_assert(!A2SEP || ACC1_23, "separate A2 columns need the single-accumulator layers");
+  static constexpr uint32_t cA2 = A2SEP ? 256 : cD1, sA2 = A2SEP ? 64 : 128;   // base, stride
+  static constexpr uint32_t cD2x = A2SEP ? 384 : cD2, sD2 = A2SEP ? 32 : 64;
+  static constexpr uint32_t cD3x = A2SEP ? 448 : cD3, sD3 = A2SEP ? 32 : 64;
+  // column of chunk g's (16 channels) hi pairs inside an A2 buffer, and offset of the lo pairs
+  __host__ __device__ static constexpr uint32_t a2col(uint32_t g) {
+    return A2SEP ? 8u * g : 32u * (g >> 1) + 8u * (g & 1);
+  }
+  static constexpr uint32_t A2LO = A2SEP ? 32 : N1;
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr int BAR_E3 = 1;
 };
@@ -177,6 +216,15 @@ using fused_pl::tmem_ld16_nowait;
 using fused_pl::tmem_ld_wait;
 using tc::mbar_arrive;
 using tc::named_bar_sync;
+
+#ifdef HP_PROF
+// kernel-development aid: per-warp cycles spent blocked at each hand-off of CTA (1,1,0), read
+// back with srcnn_debug_hp_prof (tools/hp_prof.py); no printf, no per-tile stores
+__device__ unsigned hp_prof[32][4];
+#define HPW(i, ...) { const unsigned _t = (unsigned)clock(); __VA_ARGS__; _hw[i] += (unsigned)clock() - _t; }
+#else
+#define HPW(i, ...) { __VA_ARGS__; }
+#endif
 
 // ---------------------------------------------------------------------------- prepare --------
 // Derives the scales from the parameters (every CTA of a small grid, redundantly) and packs the
@@ -343,7 +391,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
   float* sB1 = reinterpret_cast<float*>(smem_raw + C::oB1);
   float* sB2 = reinterpret_cast<float*>(smem_raw + C::oB2);
   float* sQs = reinterpret_cast<float*>(smem_raw + C::oQs);
-  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2],
+  __shared__ __align__(8) uint64_t p_full[4], p_free[4], bar1[2], a2_full[2], bar2[2], d1_free[2],
       a3_full[2], bar3[2], d3_free[2];
   __shared__ uint32_t tmem_slot;
 
@@ -374,7 +422,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     for (int i = 0; i < 2; i++) {
       mbar_init(&bar1[i], 1);
       mbar_init(&a2_full[i], C::N_E1 * 32);
-      mbar_init(&bar2[i], L1ONLY ? C::N_E1 * 32 : 1);
+      mbar_init(&bar2[i], (L1ONLY && !C::A2SEP) ? C::N_E1 * 32 : 1);
+      mbar_init(&d1_free[i], C::N_E1 * 32);
       mbar_init(&a3_full[i], 128);
       mbar_init(&bar3[i], 1);
       mbar_init(&d3_free[i], 128);
@@ -388,13 +437,21 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
 
   const int rows_here = min(rpc, a.h3 - R0);
   const int n_tiles = rows_here + (C::F3 - 1);   // out2 rows R0 .. R0+rows_here+3
+#ifdef HP_PROF
+  unsigned _hw[3] = {0u, 0u, 0u};
+  const unsigned _hstart = (unsigned)clock();
+#endif
 
-  if (warp >= C::W_IM && warp < C::W_IM + C::N_IM) {
+  const bool is_im = (warp >= C::W_IM && warp < C::W_IM + C::N_IMA) || warp == C::W_IMB;
+  const bool is_e1 = warp >= C::W_E1 && warp < C::W_E1 + C::N_E1;
+  const bool is_e2 = warp >= C::W_E2 && warp < C::W_E2 + 4;
+  const bool is_e3 = warp >= C::W_E3 && warp < C::W_E3 + 4;
+  if (is_im) {
     // ============================ IM: plane producers =====================================
     // thread c owns plane column c (image column X0+c): per input row r it writes
     // H8(r)[c] = in[r][c..c+7] and O(r-7)[c] = (in[r-7..r][c]); the 7 older rows of the column
     // live in registers as halves.
-    const int c = tid - C::W_IM * 32;
+    const int c = warp == C::W_IMB ? C::N_IMA * 32 + lane : tid - C::W_IM * 32;
     const bool active = c < C::PW;
     const int gx = X0 + c;
     uint8_t* pOh = smem_raw + C::oOh + c * 16;
@@ -465,7 +522,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         split_h2(v[2 * e] * sc.sx, v[2 * e + 1] * sc.sx, ph[e], pl[e]);
       const unsigned short nh = (unsigned short)(ph[0] & 0xffffu), nl = (unsigned short)(pl[0] & 0xffffu);
       // H8(b+8) replaces H8(b+4) (MMA-1(b-4)), O(b+1) replaces O(b-3) (MMA-1(b-3))
-      if (b >= 3) mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1));
+      if (b >= 3) HPW(0, mbar_wait(&p_free[(b - 3) & 3], (uint32_t)(((b - 3) >> 2) & 1)))
       if (active) {
         const int sh = b & (C::RH - 1), so = (b + 1) & (C::RO - 1);
         *reinterpret_cast<uint4*>(pHh + sh * C::PB) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -496,14 +553,17 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
              ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     };
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1));
+      HPW(0, mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1)))
       // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
-      if (t >= 2) mbar_wait(&bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      if (t >= 2) HPW(1, mbar_wait(C::A2SEP ? &d1_free[t & 1] : &bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
       const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
       const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
       const uint32_t sh = (uint32_t)(t & (C::RH - 1)) * C::PB;
       PL_EV(t, 0)
+#ifdef HP_PROF
+      const unsigned _tb = (unsigned)clock();
+#endif
       if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < C::KS1; s++) {
@@ -521,9 +581,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         mma_commit(&p_free[t & 3]);
       }
       __syncwarp();
+#ifdef HP_PROF
+      _hw[2] += (unsigned)clock() - _tb;
+#endif
       PL_EV(t, 1)
     }
-  } else if (L1ONLY && warp >= C::W_E2) {
+  } else if (L1ONLY && !is_e1) {
     // layer-1-only launch: the layer-2 / layer-3 roles have nothing to do
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
@@ -531,23 +594,37 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::N2);
     const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1));
+      HPW(0, mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1)))
       // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
-      if (t >= 2) mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      if (t >= 2) HPW(1, mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
-      const uint32_t a2 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
-      const uint32_t d2 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
+      const uint32_t a2 = tmem + C::cA2 + C::sA2 * (uint32_t)(t & 1);
+      const uint32_t d2 = tmem + C::cD2x + C::sD2 * (uint32_t)(t & 1);
       PL_EV(t, 4)
+#ifdef HP_PROF
+      const unsigned _tb = (unsigned)clock();
+#endif
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K2 / 16; ks++) {
-          const uint32_t col = 32u * (ks >> 1) + 8u * (ks & 1);   // a2col(ks)
-          mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_f16_ts(d2 + C::N2, a2 + C::N1 + col, wdesc + 16 * ks, idesc_lo, 1);
+          const uint32_t col = C::a2col((uint32_t)ks);
+          if (C::ACC1_23) {
+            // rows 32.. of sW2 (the low halves) start 4 row groups = 4 * 128 * K2/8 bytes in
+            constexpr uint64_t kLo = (4 * 128 * (C::K2 / 8)) >> 4;
+            mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_lo, ks > 0);
+            mma_f16_ts(d2, a2 + col, wdesc + kLo + 16 * ks, idesc_lo, 1);
+            mma_f16_ts(d2, a2 + C::A2LO + col, wdesc + 16 * ks, idesc_lo, 1);
+          } else {
+            mma_f16_ts(d2, a2 + col, wdesc + 16 * ks, idesc_hi, ks > 0);
+            mma_f16_ts(d2 + C::N2, a2 + C::A2LO + col, wdesc + 16 * ks, idesc_lo, 1);
+          }
         }
         mma_commit(&bar2[t & 1]);
       }
       __syncwarp();
+#ifdef HP_PROF
+      _hw[2] += (unsigned)clock() - _tb;
+#endif
       PL_EV(t, 5)
     }
   } else if (warp == C::W_I3) {
@@ -556,30 +633,43 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::NT3);
     const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::K3 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1));
-      if (t >= 2) mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1));
+      HPW(0, mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1)))
+      if (t >= 2) HPW(1, mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
-      const uint32_t a3 = tmem + C::cD2 + 64u * (uint32_t)(t & 1);
-      const uint32_t d3 = tmem + C::cD3 + 64u * (uint32_t)(t & 1);
+      const uint32_t a3 = tmem + C::cD2x + C::sD2 * (uint32_t)(t & 1);
+      const uint32_t d3 = tmem + C::cD3x + C::sD3 * (uint32_t)(t & 1);
       PL_EV(t, 8)
+#ifdef HP_PROF
+      const unsigned _tb = (unsigned)clock();
+#endif
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < C::K3 / 16; ks++) {
-          mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
-          mma_f16_ts(d3 + C::NT3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          if (C::ACC1_23) {
+            constexpr uint64_t kLo = (4 * 128 * (C::K3 / 8)) >> 4;   // rows 32.. of sW3
+            mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_lo, ks > 0);
+            mma_f16_ts(d3, a3 + ks * 8, wdesc + kLo + 16 * ks, idesc_lo, 1);
+            mma_f16_ts(d3, a3 + C::A3LO + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          } else {
+            mma_f16_ts(d3, a3 + ks * 8, wdesc + 16 * ks, idesc_hi, ks > 0);
+            mma_f16_ts(d3 + C::NT3, a3 + C::N2 + ks * 8, wdesc + 16 * ks, idesc_lo, 1);
+          }
         }
         mma_commit(&bar3[t & 1]);
       }
       __syncwarp();
+#ifdef HP_PROF
+      _hw[2] += (unsigned)clock() - _tb;
+#endif
       PL_EV(t, 9)
     }
-  } else if (warp < C::W_E1 + C::N_E1) {
+  } else if (is_e1) {
     // ============================ E1: A2 = split(relu(out1) * s1), in place ================
     // warp w: TMEM lane quarter w&3, chunks g0 .. g0+E1_CHUNKS-1 of 16 channels.  Chunk g reads
     // D1 columns [16g,16g+16) and [64+16g, ..), then writes its hi pairs to a2col(g) and its lo
     // pairs to 64 + a2col(g): columns this warp has consumed
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int g0 = (warp >> 2) * C::E1_CHUNKS;
+    const int g0 = ((warp - C::W_E1) >> 2) * C::E1_CHUNKS;
     // out1 (training): pixel index of this lane's pixel in tile 0, -1 = not an out1 pixel
     int pix1 = -1;
     const bool keep1 = BATCH && bx.out1 != nullptr;
@@ -589,11 +679,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       if (m < C::OW3 && vx < a.w && px < w1) pix1 = (smp * h1 + R0) * w1 + px;
     }
     const int w1_row = bx.pw - (C::F1 - 1);
-    float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + warp * (32 * C::SP);
+    float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + (warp - C::W_E1) * (32 * C::SP);
     float act_max = 0.f;   // L1ONLY: largest scaled activation this thread stored
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-1(b) done
-      if (warp == 0) PL_EV(b, 2)
+      HPW(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
+      if (warp == C::W_E1) PL_EV(b, 2)
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
       // all loads of this warp's chunks first (one TMEM round trip), then the conversions
@@ -604,10 +694,15 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
       }
       tmem_ld_wait();
-      if (L1ONLY) {                 // D1[b&1] may be overwritten by MMA-1(b+2)
+      if (L1ONLY || C::A2SEP) {     // D1[b&1] may be overwritten by MMA-1(b+2)
         tcgen05_fence_before();
-        mbar_arrive(&bar2[b & 1]);
+        mbar_arrive(C::A2SEP ? &d1_free[b & 1] : &bar2[b & 1]);
       }
+      if (C::A2SEP && !L1ONLY && b >= 2) {   // A2[b&1] is still being read until MMA-2(b-2) is done
+        mbar_wait(&bar2[b & 1], (uint32_t)(((b - 2) >> 1) & 1));
+        tcgen05_fence_after();
+      }
+      const uint32_t a2w = tmem + lane_base + C::cA2 + C::sA2 * (uint32_t)(b & 1);
 #pragma unroll
       for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
         const int g = g0 + gl;
@@ -624,9 +719,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         } else {
 #pragma unroll
           for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
-          const uint32_t col = 32u * (uint32_t)(g >> 1) + 8u * (uint32_t)(g & 1);
-          tmem_st8u(d1 + col, hi);
-          tmem_st8u(d1 + C::N1 + col, lo);
+          const uint32_t col = C::a2col((uint32_t)g);
+          tmem_st8u(a2w + col, hi);
+          tmem_st8u(a2w + C::A2LO + col, lo);
         }
         if (keep1) {
           float4* q = reinterpret_cast<float4*>(st1 + lane * C::SP + gl * 16);
@@ -656,14 +751,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         }
         __syncwarp();
       }
-      if (warp == 0) PL_EV(b, 3)
+      if (warp == C::W_E1) PL_EV(b, 3)
     }
     if (L1ONLY && bx.out1_max) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) act_max = fmaxf(act_max, __shfl_xor_sync(0xffffffffu, act_max, o));
       if (lane == 0 && act_max > 0.f) atomicMax(bx.out1_max, __float_as_uint(act_max * sc.inv_s1));
     }
-  } else if (warp < C::W_E3) {
+  } else if (is_e2) {
     // ============================ E2: A3 = split(relu(out2) * s2), in place ================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int pix2 = -1;
@@ -677,16 +772,16 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     float* st2 = reinterpret_cast<float*>(smem_raw + C::oS2) + (warp - C::W_E2) * (32 * C::SP);
     float act2_max = 0.f;   // largest scaled out2 value this thread stored
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-2(b) done
+      HPW(0, mbar_wait(&bar2[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-2(b) done
       if (warp == C::W_E2) PL_EV(b, 6)
       tcgen05_fence_after();
-      const uint32_t d2 = tmem + lane_base + C::cD2 + 64u * (uint32_t)(b & 1);
+      const uint32_t d2 = tmem + lane_base + C::cD2x + C::sD2 * (uint32_t)(b & 1);
       // all loads first (one TMEM round trip), then the conversions
-      float va[2][16], vb[2][16];
+      float va[2][16], vb[C::ACC1_23 ? 1 : 2][16];
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         tmem_ld16_nowait(d2 + g * 16, va[g]);
-        tmem_ld16_nowait(d2 + C::N2 + g * 16, vb[g]);
+        if (!C::ACC1_23) tmem_ld16_nowait(d2 + C::N2 + g * 16, vb[C::ACC1_23 ? 0 : g]);
       }
       tmem_ld_wait();
 #pragma unroll
@@ -695,11 +790,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         float act[16];
 #pragma unroll
         for (int j = 0; j < 16; j++)
-          act[j] = fmaxf(fmaf(va[g][j] + vb[g][j], sc.c2s, sB2[g * 16 + j]), 0.f);
+          act[j] = fmaxf(fmaf(C::ACC1_23 ? va[g][j] : va[g][j] + vb[C::ACC1_23 ? 0 : g][j], sc.c2s,
+                              sB2[g * 16 + j]), 0.f);
 #pragma unroll
         for (int j = 0; j < 8; j++) split_h2(act[2 * j], act[2 * j + 1], hi[j], lo[j]);
         tmem_st8u(d2 + g * 8, hi);
-        tmem_st8u(d2 + C::N2 + g * 8, lo);
+        tmem_st8u(d2 + C::A3LO + g * 8, lo);
         if (keep2) {
           if (pix2 >= 0) {
 #pragma unroll
@@ -735,7 +831,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       for (int o = 16; o > 0; o >>= 1) act2_max = fmaxf(act2_max, __shfl_xor_sync(0xffffffffu, act2_max, o));
       if (lane == 0 && act2_max > 0.f) atomicMax(bx.out2_max, __float_as_uint(act2_max * sc.inv_s2));
     }
-  } else if (warp < C::W_IM) {
+  } else if (is_e3) {
     // ============================ E3: Q row -> smem, 25-term gather -> out3 ================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int x = (warp & 3) * 32 + lane;
@@ -751,22 +847,24 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int b = 0; b < n_tiles; b++) {
-      mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1));       // MMA-3(b) done
+      HPW(0, mbar_wait(&bar3[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-3(b) done
       if (warp == C::W_E3) PL_EV(b, 10)
       tcgen05_fence_after();
-      const uint32_t d3 = tmem + lane_base + C::cD3 + 64u * (uint32_t)(b & 1);
-      float v[32], w[32];
+      const uint32_t d3 = tmem + lane_base + C::cD3x + C::sD3 * (uint32_t)(b & 1);
+      float v[32], w[C::ACC1_23 ? 1 : 32];
       tmem_ld16_nowait(d3, v);
       tmem_ld16_nowait(d3 + 16, v + 16);
-      tmem_ld16_nowait(d3 + 32, w);
-      tmem_ld16_nowait(d3 + 48, w + 16);
+      if (!C::ACC1_23) {
+        tmem_ld16_nowait(d3 + 32, w);
+        tmem_ld16_nowait(d3 + 48, w + (C::ACC1_23 ? 0 : 16));
+      }
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);
 #pragma unroll
-      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = v[j] + w[j];
-      named_bar_sync(C::BAR_E3, 128);                          // Q row visible to its neighbours
+      for (int j = 0; j < C::QP; j++) qs[x * C::QP + j] = C::ACC1_23 ? v[j] : v[j] + w[C::ACC1_23 ? 0 : j];
+      HPW(1, named_bar_sync(C::BAR_E3, 128))                          // Q row visible to its neighbours
       float r[C::F3];
       if (x < C::OW3) {
 #pragma unroll
@@ -794,6 +892,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     }
   }
 
+#ifdef HP_PROF
+  if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && lane == 0) {
+    hp_prof[warp][0] = (unsigned)clock() - _hstart;
+    hp_prof[warp][1] = _hw[0];
+    hp_prof[warp][2] = _hw[1];
+    hp_prof[warp][3] = _hw[2];
+  }
+#endif
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);

@@ -679,6 +679,15 @@ struct TableScope {
 };
 }  // namespace
 
+#ifdef HP_PROF
+// kernel-development aid (never in the product build): the hand-off wait counters of the fused
+// inference kernel, [32 warps][total, wait0, wait1, tiles]
+int srcnn_debug_hp_prof(unsigned* out) {
+  return cudaMemcpyFromSymbol(out, srcnn::fused_hp::hp_prof, 32 * 4 * sizeof(unsigned)) == cudaSuccess
+             ? SRCNN_OK : SRCNN_ECUDA;
+}
+#endif
+
 int srcnn_invalidate_params(srcnn_ctx* ctx) {
   SRCNN_ENTER(ctx);
   ctx->write_gen++;

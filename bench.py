@@ -735,13 +735,20 @@ def run_ours(args, rank, world, local_rank, wl):
                 tiles_per_sm = strips * (rows + 4 * bands) / sms
                 mhz = (wclocks.get("c3") or {}).get("sm_mhz") or 1965.0
                 cyc = c["ms"] * 1e-3 * mhz * 1e6 / tiles_per_sm
-                roofline["mma_operand_model"] = {
-                    "cycles_per_tile_model": 6 * (67 + 51) + 12 * 60, "cycles_per_tile": cyc,
-                    "frac": (6 * (67 + 51) + 12 * 60) / cyc, "tiles_per_sm": tiles_per_sm,
-                    "source": "profiles/r2zb_cta2_probe.txt, profiles/r2w_fused_kernel_sensitivity.txt",
-                    "note": "the kernel's tile period against the measured cost of its 24 MMA "
-                            "instructions per tile (operand fetch: shared memory 128 B/clk, TMEM "
-                            "64 B/clk); launch and prologue time is inside cycles_per_tile"}
+                # tensor-pipe time of a tile's 24 MMA instructions, each timed alone on the B200
+                # (tools/probe/ts_probe.cu): A and B in shared memory 67.7 / 51.5 cycles at
+                # N = 128 / 64 (operand fetch at 128 B/clk), A in tensor memory 35.9 / 20.5 at
+                # N = 64 / 32 (math-bound)
+                pipe = 6 * (67.7 + 51.5) + 6 * (35.9 + 20.5)
+                roofline["mma_pipe_model"] = {
+                    "cycles_per_tile_model": pipe, "cycles_per_tile": cyc,
+                    "frac": pipe / cyc, "tiles_per_sm": tiles_per_sm,
+                    "source": "profiles/r3d_ts_probe.txt, profiles/r3e_hp_prof_blocks.txt",
+                    "note": "the kernel's tile period against the tensor-pipe time of its 24 MMA "
+                            "instructions per tile measured in isolation (ncu's sm__pipe_tc_cycles_active "
+                            "of the kernel agrees: 61.5 %); the rest of the period is the hand-off "
+                            "chain between the roles, not the pipe; launch and prologue time is "
+                            "inside cycles_per_tile"}
         line.update({"value": mpix, "ms_per_step": c["ms"], "gpu_launches": int(c["launches"]),
                      "roofline": roofline,
                      "e2e": {"value": e2e_mpix, "unit": "MPix/s", "ms_per_step": c["e2e_ms"],

@@ -217,6 +217,17 @@ using fused_pl::tmem_ld_wait;
 using tc::mbar_arrive;
 using tc::named_bar_sync;
 
+// HP_SPIN (experiment): bit 0 -- the three MMA issuers poll their barriers (test_wait, never
+// parked) instead of try_wait with a suspend hint; bit 1 -- E1 polls bar1 likewise
+#ifndef HP_SPIN
+#define HP_SPIN 0
+#endif
+__device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity) {
+  while (!tc::mbar_test(bar, parity)) {}
+}
+#define HP_IWAIT(bar, par) { if (HP_SPIN & 1) mbar_poll(bar, par); else tc::mbar_wait(bar, par); }
+#define HP_EWAIT(bar, par) { if (HP_SPIN & 2) mbar_poll(bar, par); else tc::mbar_wait(bar, par); }
+
 #ifdef HP_PROF
 // kernel-development aid: per-warp cycles spent blocked at each hand-off of CTA (1,1,0), read
 // back with srcnn_debug_hp_prof (tools/hp_prof.py); no printf, no per-tile stores
@@ -553,9 +564,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
              ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     };
     for (int t = 0; t < n_tiles; t++) {
-      HPW(0, mbar_wait(&p_full[t & 3], (uint32_t)((t >> 2) & 1)))
+      HPW(0, HP_IWAIT(&p_full[t & 3], (uint32_t)((t >> 2) & 1)))
       // D1[t&1] still holds A2(t-2) until MMA-2(t-2) has read it
-      if (t >= 2) HPW(1, mbar_wait(C::A2SEP ? &d1_free[t & 1] : &bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
+      if (t >= 2) HPW(1, HP_IWAIT(C::A2SEP ? &d1_free[t & 1] : &bar2[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
       const uint32_t d1 = tmem + C::cD1 + 128u * (uint32_t)(t & 1);
       const uint32_t so = (uint32_t)(t & (C::RO - 1)) * C::PB;
@@ -594,9 +605,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::N2);
     const uint64_t wdesc = make_desc_kmajor(sW2, 0, 128, 128 * (C::K2 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      HPW(0, mbar_wait(&a2_full[t & 1], (uint32_t)((t >> 1) & 1)))
+      HPW(0, HP_IWAIT(&a2_full[t & 1], (uint32_t)((t >> 1) & 1)))
       // D2[t&1] still holds A3(t-2) until MMA-3(t-2) has read it
-      if (t >= 2) HPW(1, mbar_wait(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
+      if (t >= 2) HPW(1, HP_IWAIT(&bar3[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
       const uint32_t a2 = tmem + C::cA2 + C::sA2 * (uint32_t)(t & 1);
       const uint32_t d2 = tmem + C::cD2x + C::sD2 * (uint32_t)(t & 1);
@@ -633,8 +644,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     const uint32_t idesc_lo = make_idesc_f16(C::M, C::NT3);
     const uint64_t wdesc = make_desc_kmajor(sW3, 0, 128, 128 * (C::K3 / 8));
     for (int t = 0; t < n_tiles; t++) {
-      HPW(0, mbar_wait(&a3_full[t & 1], (uint32_t)((t >> 1) & 1)))
-      if (t >= 2) HPW(1, mbar_wait(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
+      HPW(0, HP_IWAIT(&a3_full[t & 1], (uint32_t)((t >> 1) & 1)))
+      if (t >= 2) HPW(1, HP_IWAIT(&d3_free[t & 1], (uint32_t)(((t - 2) >> 1) & 1)))
       tcgen05_fence_after();
       const uint32_t a3 = tmem + C::cD2x + C::sD2 * (uint32_t)(t & 1);
       const uint32_t d3 = tmem + C::cD3x + C::sD3 * (uint32_t)(t & 1);
@@ -682,7 +693,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + (warp - C::W_E1) * (32 * C::SP);
     float act_max = 0.f;   // L1ONLY: largest scaled activation this thread stored
     for (int b = 0; b < n_tiles; b++) {
-      HPW(0, mbar_wait(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
+      HPW(0, HP_EWAIT(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
       if (warp == C::W_E1) PL_EV(b, 2)
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);

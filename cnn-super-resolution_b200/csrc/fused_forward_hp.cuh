@@ -699,12 +699,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
       // all loads of this warp's chunks first (one TMEM round trip), then the conversions
       float va[C::E1_CHUNKS][16], vb[C::E1_CHUNKS][16];
+#ifdef HP_PROF
+      const unsigned _tl = (unsigned)clock();
+#endif
 #pragma unroll
       for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
         tmem_ld16_nowait(d1 + (g0 + gl) * 16, va[gl]);
         tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
       }
       tmem_ld_wait();
+#ifdef HP_PROF
+      _hw[1] += (unsigned)clock() - _tl;
+#endif
       if (L1ONLY || C::A2SEP) {     // D1[b&1] may be overwritten by MMA-1(b+2)
         tcgen05_fence_before();
         mbar_arrive(C::A2SEP ? &d1_free[b & 1] : &bar2[b & 1]);
@@ -743,7 +749,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         }
       }
       if (!L1ONLY) {
+#ifdef HP_PROF
+        const unsigned _ts = (unsigned)clock();
+#endif
         tmem_st_wait();
+#ifdef HP_PROF
+        _hw[2] += (unsigned)clock() - _ts;
+#endif
         tcgen05_fence_before();
         mbar_arrive(&a2_full[b & 1]);
       }
@@ -863,6 +875,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tcgen05_fence_after();
       const uint32_t d3 = tmem + lane_base + C::cD3x + C::sD3 * (uint32_t)(b & 1);
       float v[32], w[C::ACC1_23 ? 1 : 32];
+#ifdef HP_PROF
+      const unsigned _tl3 = (unsigned)clock();
+#endif
       tmem_ld16_nowait(d3, v);
       tmem_ld16_nowait(d3 + 16, v + 16);
       if (!C::ACC1_23) {
@@ -870,6 +885,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         tmem_ld16_nowait(d3 + 48, w + (C::ACC1_23 ? 0 : 16));
       }
       tmem_ld_wait();
+#ifdef HP_PROF
+      _hw[2] += (unsigned)clock() - _tl3;
+#endif
       tcgen05_fence_before();
       mbar_arrive(&d3_free[b & 1]);                            // D3[b&1] may be overwritten
       float* qs = sQs + (b & 1) * (C::M * C::QP);

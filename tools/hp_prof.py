@@ -21,7 +21,7 @@ L = C.CDLL(os.environ["SRCNN_B200_LIB"])
 buf = (C.c_uint * 128)()
 assert L.srcnn_debug_hp_prof(buf) == 0
 a = np.array(buf, dtype=np.int64).reshape(32, 4)
-roles = [("E1", 0, 8, "bar1 (MMA-1 done)", "-"), ("E2", 8, 12, "bar2 (MMA-2 done)", "-"),
+roles = [("E1", 0, 8, "bar1 (MMA-1 done)", "(busy) tcgen05.ld"), ("E2", 8, 12, "bar2 (MMA-2 done)", "-"),
          ("E3", 12, 16, "bar3 (MMA-3 done)", "named barrier"), ("IM", 16, 21, "p_free (planes read)", "-"),
          ("I1", 21, 22, "p_full (planes)", "bar2 (D1 free)"), ("I2", 22, 23, "a2_full (E1 done)", "bar3 (D2 free)"),
          ("I3", 23, 24, "a3_full (E2 done)", "d3_free (E3 read D3)")]
@@ -31,4 +31,4 @@ for name, w0, w1, n0, n1 in roles:
         if tot == 0:
             continue
         print("%s warp %2d: %7d cycles, %4d tiles = %6.1f per tile | busy %6.1f | wait %-22s %6.1f | wait %-22s %6.1f" %
-              (name, w, tot, nt, tot / nt, (tot - x0 - x1) / nt, n0, x0 / nt, n1, x1 / nt) + ("  | MMA issue block %6.1f" % (blk / nt) if blk else ""))
+              (name, w, tot, nt, tot / nt, (tot - x0 - x1) / nt, n0, x0 / nt, n1, x1 / nt) + (("  | %s %6.1f" % ("MMA issue block" if name[0] == "I" else "tcgen05.wait::st" if name == "E1" else "tcgen05.ld", blk / nt)) if blk else ""))

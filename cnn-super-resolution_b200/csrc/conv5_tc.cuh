@@ -92,12 +92,32 @@ struct Cfg {
   static constexpr int PW = 136;                      // plane entries (>= M + F - 1)
   static constexpr int PB = PW * 16;                  // bytes per plane
   static constexpr int SLOT_BYTES = 4 * PB;           // hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1
-  static constexpr int NSLOT = 3, NACC = 7;
+  // DYS ("dy-stacked", MODE 0): the five filter rows dy of an input row slice use the SAME A tile
+  // (same input row, same dx shift) and only differ in the output row they feed.  With the
+  // accumulators of consecutive output rows side by side in tensor memory, ONE instruction
+  // A x [W(dy=4); W(dy=3); ... ; W(dy=0)] (N = 5 * COUT = 160) serves all five: 3 instructions per
+  // (slice, dx) -- hi.hi and lo.hi into region H, hi.lo into region L -- instead of 10, and each
+  // is math-bound (80 cycles of tensor math against 72 of operand fetch) where the per-dy
+  // instructions were fetch-bound (94 cycles per 48 of math: the kernel's tensor pipe was 74 %
+  // busy at 39 % math, profiles/r3j_ncu_summary.txt).  Output row rho lives in slot rho % 8 of
+  // both regions; a range of rows that wraps around the ring is issued as two instructions.
+#ifndef C5_DYS
+#define C5_DYS 1
+#endif
+  static constexpr bool DYS = C5_DYS != 0;
+  // two regions (hi.w_lo apart from the rest, one issuer each) where 2 * 8 rows fit tensor memory
+  // (MODE 0); else all three products of a row share one accumulator and one issuer (MODE 1,
+  // where an instruction carries at most 256 / COUT = 4 rows)
+  static constexpr bool TWO = DYS && 2 * 8 * COUT_ <= 512;
+  static constexpr int NSLOT = 3, NACC = DYS ? 8 : 7;
+  static constexpr int REGION = 256;                  // DYS: columns of region H; L follows
+  static constexpr int BLK_BYTES = F * COUT * 32;     // DYS: image block of one (dx, slice)
+  static constexpr int IMG_L = F * NSLICE * BLK_BYTES;   // DYS: byte offset of the W_lo blocks
   // STACK: A_hi x [W_hi ; W_lo] as ONE N = 2*COUT instruction (its two halves land in separate
   // accumulator columns, the epilogue adds them) + A_lo x W_hi: two A-tile fetches per K-step
   // instead of three.  The A tile (128 rows at a 16-byte shifted base: every 128-byte core matrix
   // straddles two shared-memory lines) is the expensive operand.  Needs 2*COUT columns per row.
-  static constexpr bool STACK = 2 * NACC * COUT <= 512;
+  static constexpr bool STACK = !DYS && 2 * NACC * COUT <= 512;
   static constexpr int ACCW = STACK ? 2 * COUT : COUT;
   static constexpr int W_BYTES = 2 * COUT * KT * 2;   // [W_hi rows ; W_lo rows][KT] halves
   static constexpr int W_SBO = 128 * (KT / 8);        // bytes between 8-row groups of the image
@@ -105,10 +125,13 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)oBias + COUT * 4;
   // MMA issuer warps: output rows split modulo N_I (3 instead of 2: forward of a 3 028-patch
   // chunk 0.99 -> 0.94 ms; 4: no further gain)
-  static constexpr int N_I = 3;
+  // (DYS: issuer 0 owns region H, issuer 1 region L -- no accumulator has two writers)
+  static constexpr int N_I = DYS ? (TWO ? 2 : 1) : 3;
   static constexpr int W_E = 0, W_P = 4, N_P = 5, W_I = W_P + N_P, NT = (W_I + N_I) * 32;
-  static constexpr uint32_t TMEM_COLS = NACC * ACCW <= 256 ? 256 : 512;
-  static_assert(NACC * ACCW <= 512, "accumulators must fit tensor memory");
+  static constexpr uint32_t TMEM_COLS = DYS ? 512 : (NACC * ACCW <= 256 ? 256 : 512);
+  static_assert(DYS ? (TWO ? NACC * COUT <= REGION : NACC * COUT <= 512) : NACC * ACCW <= 512,
+                "accumulators must fit tensor memory");
+  static constexpr int MAXROWS = 256 / COUT;          // DYS: output rows per instruction (N <= 256)
   static_assert(CIN % 16 == 0 && COUT % 16 == 0, "channel counts");
   static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory");
 };
@@ -118,7 +141,9 @@ struct Cfg {
 struct Images {
   float sw, inv_sw;        // weights were multiplied by sw
   float pad_[2];
-  unsigned char fwd[Cfg<64, 32, 0>::W_BYTES];   // rows = n2 (hi 0..31, lo 32..63), k = tap*64 + ci
+  // DYS layout: [hi | lo][dx][slice][row = (4 - dy) * 32 + n2][16 ci], every block canonical K-major
+  // (8-row groups 256 bytes apart); otherwise rows = n2 (hi 0..31, lo 32..63), k = tap*64 + ci
+  unsigned char fwd[Cfg<64, 32, 0>::W_BYTES];
   unsigned char d1[Cfg<32, 64, 1>::W_BYTES];    // rows = n1 (hi 0..63, lo 64..127), k = tap*32 + ci
 };
 static_assert(offsetof(Images, fwd) % 16 == 0 && offsetof(Images, d1) % 16 == 0, "uint4 copies");
@@ -155,8 +180,18 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
       const int n = i / KT, k = i % KT;            // k = t*64 + ci
       unsigned short hi, lo;
       fused_hp::split_h(__ldg(w2 + (size_t)k * N2 + n) * sw, hi, lo);
-      f[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
-      f[fused_hp::kmajor16(N2 + n, k, KT)] = __ushort_as_half(lo);
+      using FC = Cfg<64, 32, 0>;
+      if (FC::DYS) {
+        const int t = k / N1, ci = k % N1, dy = t / F, dx = t % F, c = ci / 16, kk = ci % 16;
+        const int row = (F - 1 - dy) * N2 + n;
+        const int off = ((dx * FC::NSLICE + c) * FC::BLK_BYTES) / 2 + (row >> 3) * 128 + (kk >> 3) * 64 +
+                        (row & 7) * 8 + (kk & 7);
+        f[off] = __ushort_as_half(hi);
+        f[FC::IMG_L / 2 + off] = __ushort_as_half(lo);
+      } else {
+        f[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
+        f[fused_hp::kmajor16(N2 + n, k, KT)] = __ushort_as_half(lo);
+      }
     }
   }
   {   // deltas image: Wg[t][ci = k2][co = n1] = W2[24 - t][n1][k2]
@@ -166,8 +201,18 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
       const int t = k / N2, ci = k % N2;
       unsigned short hi, lo;
       fused_hp::split_h(__ldg(w2 + ((size_t)(T - 1 - t) * N1 + n) * N2 + ci) * sw, hi, lo);
-      d[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
-      d[fused_hp::kmajor16(N1 + n, k, KT)] = __ushort_as_half(lo);
+      using DC = Cfg<32, 64, 1>;
+      if (DC::DYS) {
+        const int dy = t / F, dx = t % F, c = ci / 16, kk = ci % 16;
+        const int row = (F - 1 - dy) * N1 + n;
+        const int off = ((dx * DC::NSLICE + c) * DC::BLK_BYTES) / 2 + (row >> 3) * 128 + (kk >> 3) * 64 +
+                        (row & 7) * 8 + (kk & 7);
+        d[off] = __ushort_as_half(hi);
+        d[DC::IMG_L / 2 + off] = __ushort_as_half(lo);
+      } else {
+        d[fused_hp::kmajor16(n, k, KT)] = __ushort_as_half(hi);
+        d[fused_hp::kmajor16(N1 + n, k, KT)] = __ushort_as_half(lo);
+      }
     }
   }
 }
@@ -228,7 +273,7 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       mbar_init(&empty[i], C::N_I);
     }
     for (int i = 0; i < C::NACC; i++) {
-      mbar_init(&done[i], 1);
+      mbar_init(&done[i], C::DYS ? C::N_I : 1);
       mbar_init(&acc_free[i], 128);
     }
   }
@@ -329,6 +374,73 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     };
     constexpr uint32_t W_LO = (uint32_t)(C::COUT / 8) * C::W_SBO;   // first W_lo row group
     int it = 0;
+    if (C::DYS) {
+      // ---- dy-stacked issue.  Input row r feeds output rows rho = r - dy + P; a row is first
+      // touched at input row max(rho - P, 0) (slice 0, dx = 0) and complete after input row
+      // min(rho - P + 4, ih - 1).  TWO: me = 0 issues region H (hi.w_hi + lo.w_hi), me = 1 region L
+      // (hi.w_lo); else the one issuer puts all three products into the row's accumulator.
+      auto bdesc = [](uint32_t addr) -> uint64_t {      // image block: LBO = 128, SBO = 256
+        return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+               ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+      };
+      const uint32_t region = tmem + (uint32_t)(C::TWO ? me * C::REGION : 0);
+      const uint32_t imgH = sW + (uint32_t)((C::TWO && me == 1) ? C::IMG_L : 0);
+      for (int r = 0; r < ih; r++) {
+        const int dy_lo = max(0, r + P - (oh - 1)), dy_hi = min(F - 1, r + P);
+        for (int c = 0; c < C::NSLICE; c++, it++) {
+          const int slot = it % C::NSLOT;
+          mbar_wait(&full[slot], (uint32_t)((it / C::NSLOT) & 1));
+          if (c == 0 && dy_lo == 0 && r + P >= C::NACC)   // row r + P starts: its slot's last row has left
+            mbar_wait(&acc_free[(r + P) % C::NACC], (uint32_t)((((r + P) / C::NACC) - 1) & 1));
+          tcgen05_fence_after();
+          const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
+          if (elect_one()) {
+            // rows of dy = b0 .. a0 (rho ascending) -> slots (r - b + P) % NACC ..., split where the
+            // ring wraps and at MAXROWS rows per instruction
+            auto emit = [&](uint64_t da, uint32_t blk, int a0, int b0, uint32_t acc_flag) {
+              int b = b0;
+              while (b >= a0) {
+                const int s0 = (r - b + P) % C::NACC;
+                const int n = min(min(b - a0 + 1, C::NACC - s0), C::MAXROWS);
+                mma_f16_ss(region + (uint32_t)(s0 * C::COUT), da,
+                           bdesc(blk + (uint32_t)((F - 1 - b) * C::COUT * 32)),
+                           make_idesc_f16(C::M, n * C::COUT), acc_flag);
+                b -= n;
+              }
+            };
+            // the products of a range of rows, in a fixed order
+            auto products = [&](uint64_t dah, uint64_t dal, uint32_t blk, int a0, int b0, uint32_t acc_flag) {
+              emit(dah, blk, a0, b0, acc_flag);                       // hi.w_hi  (TWO, me = 1: hi.w_lo)
+              if (!C::TWO) emit(dah, blk + C::IMG_L, a0, b0, 1u);     // hi.w_lo
+              if (!C::TWO || me == 0) emit(dal, blk, a0, b0, 1u);     // lo.w_hi
+            };
+#pragma unroll 1
+            for (int dx = 0; dx < F; dx++) {
+              const uint32_t blk = imgH + (uint32_t)((dx * C::NSLICE + c) * C::BLK_BYTES);
+              const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
+              int a0 = dy_lo;
+              if (c == 0 && dx == 0) {                   // rows that start here: first product overwrites
+                if (r == 0) {
+                  products(dah, dal, blk, dy_lo, dy_hi, 0u);
+                  a0 = dy_hi + 1;
+                } else if (dy_lo == 0) {
+                  products(dah, dal, blk, 0, 0, 0u);
+                  a0 = 1;
+                }
+              }
+              if (a0 <= dy_hi) products(dah, dal, blk, a0, dy_hi, 1u);
+            }
+            if (c == C::NSLICE - 1)
+              for (int dy = dy_lo; dy <= dy_hi; dy++) {
+                const int rho = r - dy + P;
+                if (r == min(rho - P + (F - 1), ih - 1)) mma_commit(&done[rho % C::NACC]);
+              }
+            mma_commit(&empty[slot]);
+          }
+          __syncwarp();
+        }
+      }
+    } else
     for (int r = 0; r < ih; r++) {
       for (int c = 0; c < C::NSLICE; c++, it++) {
         const int slot = it % C::NSLOT;
@@ -397,14 +509,16 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       mbar_wait(&done[acc], (uint32_t)((rho / C::NACC) & 1));
       tcgen05_fence_after();
       float v[C::COUT];
+      const uint32_t c0 = C::DYS ? (uint32_t)(acc * C::COUT) : (uint32_t)(acc * C::ACCW);
+      const uint32_t c1 = C::DYS ? (uint32_t)(C::REGION + acc * C::COUT) : (uint32_t)(acc * C::ACCW + C::COUT);
 #pragma unroll
       for (int g = 0; g < C::COUT / 16; g++)
-        tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::ACCW + g * 16), v + g * 16);
-      if (C::STACK) {
+        tmem_ld16_nowait(tmem + lane_base + c0 + g * 16, v + g * 16);
+      if (C::STACK || C::TWO) {
         float v2[C::COUT];
 #pragma unroll
         for (int g = 0; g < C::COUT / 16; g++)
-          tmem_ld16_nowait(tmem + lane_base + (uint32_t)(acc * C::ACCW + C::COUT + g * 16), v2 + g * 16);
+          tmem_ld16_nowait(tmem + lane_base + c1 + g * 16, v2 + g * 16);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < C::COUT; j++) v[j] += v2[j];

@@ -127,7 +127,11 @@ struct Cfg {
   // chunk 0.99 -> 0.94 ms; 4: no further gain)
   // (DYS: issuer 0 owns region H, issuer 1 region L -- no accumulator has two writers)
   static constexpr int N_I = DYS ? (TWO ? 2 : 1) : 3;
-  static constexpr int W_E = 0, W_P = 4, N_P = 5, W_I = W_P + N_P, NT = (W_I + N_I) * 32;
+#ifndef C5_NP
+#define C5_NP 5
+#endif
+  static constexpr int W_E = 0, W_P = 4, N_P = C5_NP, W_I = W_P + N_P, NT = (W_I + N_I) * 32;
+  static constexpr int ITEMS = (2 * PW + N_P * 32 - 1) / (N_P * 32);   // plane items per producer thread
   static constexpr uint32_t TMEM_COLS = DYS ? 512 : (NACC * ACCW <= 256 ? 256 : 512);
   static_assert(DYS ? (TWO ? NACC * COUT <= REGION : NACC * COUT <= 512) : NACC * ACCW <= 512,
                 "accumulators must fit tensor memory");
@@ -297,11 +301,11 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     // fall into 4 lines (one lane per pixel with the whole 64-byte slice: 8 lines per quarter
     // and 32 per instruction -- the L1 pipe these kernels are bound by counts lines)
     const int t = tid - C::W_P * 32;
-    long long base[2];       // float offset of (sample, row 0, x, channel 8 ch), -1 = zero column
-    uint8_t* my[2];
-    bool live[2];
+    long long base[C::ITEMS];       // float offset of (sample, row 0, x, channel 8 ch), -1 = zero column
+    uint8_t* my[C::ITEMS];
+    bool live[C::ITEMS];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < C::ITEMS; k++) {
       const int item = t + k * (C::N_P * 32), q = item >> 1, ch = item & 1;
       const long long vin = X0 - P + q;
       base[k] = -1;
@@ -313,41 +317,45 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       my[k] = smem_raw + C::oSlots + ch * C::PB + q * 16;
     }
     const long long row_stride = (long long)iw * C::CIN;
-    float4 v[2][2];
-    auto load = [&](int r, int c) {
+    // Loads run TWO slices ahead of their use (v = this slice, v1 = the next, v2 = the one after):
+    // with the dy-stacked MMAs a slice is consumed every ~1 300 cycles, less than one HBM round
+    // trip, so a single slice in flight per thread made the producers the bound.
+    float4 v[C::ITEMS][2], v1[C::ITEMS][2], v2[C::ITEMS][2];
+    auto load = [&](float4 (&dst)[C::ITEMS][2], int i) {   // slice index i = r * NSLICE + c
+      const int r = i / C::NSLICE, c = i % C::NSLICE;
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
-        if (base[k] >= 0) {
+      for (int k = 0; k < C::ITEMS; k++) {
+        if (base[k] >= 0 && r < ih) {
           const float4* p = reinterpret_cast<const float4*>(a.in + base[k] + r * row_stride + c * 16);
-          v[k][0] = __ldg(p);
-          v[k][1] = __ldg(p + 1);
+          dst[k][0] = __ldg(p);
+          dst[k][1] = __ldg(p + 1);
         } else {
-          v[k][0] = v[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[k][0] = dst[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
-    load(0, 0);
+    load(v, 0);
+    load(v1, 1);
     int it = 0;
     for (int r = 0; r < ih; r++) {
       for (int c = 0; c < C::NSLICE; c++, it++) {
         const int slot = it % C::NSLOT;
-        uint32_t hi[2][4], lo[2][4];
+        load(v2, it + 2);
+        uint32_t hi[C::ITEMS][4], lo[C::ITEMS][4];
 #pragma unroll
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < C::ITEMS; k++)
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             split_h2(v[k][j].x * s_in, v[k][j].y * s_in, hi[k][2 * j], lo[k][2 * j]);
             split_h2(v[k][j].z * s_in, v[k][j].w * s_in, hi[k][2 * j + 1], lo[k][2 * j + 1]);
           }
-        // the loads of the next slice fly while this thread waits for its slot
-        {
-          int nr = r, nc = c + 1;
-          if (nc == C::NSLICE) { nc = 0; nr++; }
-          if (nr < ih) load(nr, nc);
-        }
+#pragma unroll
+        for (int k = 0; k < C::ITEMS; k++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) { v[k][j] = v1[k][j]; v1[k][j] = v2[k][j]; }
         if (it >= C::NSLOT) mbar_wait(&empty[slot], (uint32_t)(((it / C::NSLOT) - 1) & 1));
 #pragma unroll
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < C::ITEMS; k++)
           if (live[k]) {
             uint8_t* sdst = my[k] + slot * C::SLOT_BYTES;
             *reinterpret_cast<uint4*>(sdst) = make_uint4(hi[k][0], hi[k][1], hi[k][2], hi[k][3]);
@@ -385,8 +393,32 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
       };
       const uint32_t region = tmem + (uint32_t)(C::TWO ? me * C::REGION : 0);
       const uint32_t imgH = sW + (uint32_t)((C::TWO && me == 1) ? C::IMG_L : 0);
+      constexpr uint64_t kImgL = (uint64_t)(C::IMG_L >> 4);             // descriptor address units
+      constexpr uint64_t kDx = (uint64_t)((C::NSLICE * C::BLK_BYTES) >> 4);
       for (int r = 0; r < ih; r++) {
         const int dy_lo = max(0, r + P - (oh - 1)), dy_hi = min(F - 1, r + P);
+        // the instructions of one (slice, dx) step of this input row: rows of dy = dy_hi .. dy_lo
+        // (rho ascending) -> slots (r - dy + P) % NACC, cut where the ring wraps and at MAXROWS
+        // rows.  At most 3 pieces; computed once per input row, the issue loop only adds offsets.
+        uint32_t seg_d[3], seg_i[3];
+        uint64_t seg_b[3];
+        int nseg = 0;
+        auto cut = [&](int a0, int b0, uint32_t (&sd)[3], uint64_t (&sb)[3], uint32_t (&si)[3]) {
+          int n_out = 0, b = b0;
+#pragma unroll
+          for (int q = 0; q < 3; q++)      // static indices: the tables stay in registers
+            if (b >= a0) {
+              const int s0 = (r - b + P) % C::NACC;
+              const int n = min(min(b - a0 + 1, C::NACC - s0), C::MAXROWS);
+              sd[q] = (uint32_t)(s0 * C::COUT);
+              sb[q] = (uint64_t)(((F - 1 - b) * C::COUT * 32) >> 4);
+              si[q] = make_idesc_f16(C::M, n * C::COUT);
+              n_out = q + 1;
+              b -= n;
+            }
+          return n_out;
+        };
+        nseg = cut(dy_lo, dy_hi, seg_d, seg_b, seg_i);
         for (int c = 0; c < C::NSLICE; c++, it++) {
           const int slot = it % C::NSLOT;
           mbar_wait(&full[slot], (uint32_t)((it / C::NSLOT) & 1));
@@ -395,41 +427,36 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
           tcgen05_fence_after();
           const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
           if (elect_one()) {
-            // rows of dy = b0 .. a0 (rho ascending) -> slots (r - b + P) % NACC ..., split where the
-            // ring wraps and at MAXROWS rows per instruction
-            auto emit = [&](uint64_t da, uint32_t blk, int a0, int b0, uint32_t acc_flag) {
-              int b = b0;
-              while (b >= a0) {
-                const int s0 = (r - b + P) % C::NACC;
-                const int n = min(min(b - a0 + 1, C::NACC - s0), C::MAXROWS);
-                mma_f16_ss(region + (uint32_t)(s0 * C::COUT), da,
-                           bdesc(blk + (uint32_t)((F - 1 - b) * C::COUT * 32)),
-                           make_idesc_f16(C::M, n * C::COUT), acc_flag);
-                b -= n;
-              }
-            };
-            // the products of a range of rows, in a fixed order
-            auto products = [&](uint64_t dah, uint64_t dal, uint32_t blk, int a0, int b0, uint32_t acc_flag) {
-              emit(dah, blk, a0, b0, acc_flag);                       // hi.w_hi  (TWO, me = 1: hi.w_lo)
-              if (!C::TWO) emit(dah, blk + C::IMG_L, a0, b0, 1u);     // hi.w_lo
-              if (!C::TWO || me == 0) emit(dal, blk, a0, b0, 1u);     // lo.w_hi
-            };
-#pragma unroll 1
-            for (int dx = 0; dx < F; dx++) {
-              const uint32_t blk = imgH + (uint32_t)((dx * C::NSLICE + c) * C::BLK_BYTES);
-              const uint64_t dah = adesc(ah + dx * 16), dal = adesc(al + dx * 16);
-              int a0 = dy_lo;
-              if (c == 0 && dx == 0) {                   // rows that start here: first product overwrites
-                if (r == 0) {
-                  products(dah, dal, blk, dy_lo, dy_hi, 0u);
-                  a0 = dy_hi + 1;
-                } else if (dy_lo == 0) {
-                  products(dah, dal, blk, 0, 0, 0u);
-                  a0 = 1;
+            const uint64_t dah0 = adesc(ah), dal0 = adesc(al);
+            const uint64_t blk0 = bdesc(imgH + (uint32_t)(c * C::BLK_BYTES));
+            // all products of the pieces, in a fixed order
+            auto step = [&](uint64_t dah, uint64_t dal, uint64_t blk, int ns, const uint32_t (&sd)[3],
+                            const uint64_t (&sb)[3], const uint32_t (&si)[3], uint32_t acc_flag) {
+#pragma unroll
+              for (int q = 0; q < 3; q++)
+                if (q < ns) {
+                  mma_f16_ss(region + sd[q], dah, blk + sb[q], si[q], acc_flag);          // hi.w_hi (me = 1: hi.w_lo)
+                  if (!C::TWO) mma_f16_ss(region + sd[q], dah, blk + kImgL + sb[q], si[q], 1u);   // hi.w_lo
+                  if (!C::TWO || me == 0) mma_f16_ss(region + sd[q], dal, blk + sb[q], si[q], 1u);   // lo.w_hi
                 }
+            };
+            int dx0 = 0;
+            if (c == 0 && (r == 0 || dy_lo == 0)) {      // rows start here: their first product overwrites
+              uint32_t fd[3], fi[3];
+              uint64_t fb[3];
+              const int f_hi = r == 0 ? dy_hi : 0;       // at r = 0 every row is new, later only dy = 0
+              int nf = cut(dy_lo, f_hi, fd, fb, fi);
+              step(dah0, dal0, blk0, nf, fd, fb, fi, 0u);
+              if (f_hi < dy_hi) {
+                nf = cut(f_hi + 1, dy_hi, fd, fb, fi);
+                step(dah0, dal0, blk0, nf, fd, fb, fi, 1u);
               }
-              if (a0 <= dy_hi) products(dah, dal, blk, a0, dy_hi, 1u);
+              dx0 = 1;
             }
+            if (dx0 == 0) step(dah0, dal0, blk0, nseg, seg_d, seg_b, seg_i, 1u);
+#pragma unroll
+            for (int dx = 1; dx < F; dx++)
+              step(dah0 + dx, dal0 + dx, blk0 + dx * kDx, nseg, seg_d, seg_b, seg_i, 1u);
             if (c == C::NSLICE - 1)
               for (int dy = dy_lo; dy <= dy_hi; dy++) {
                 const int rho = r - dy + P;

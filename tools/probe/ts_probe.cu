@@ -204,7 +204,7 @@ int main() {
   cudaMalloc(&dc, 4 * sizeof(long long));
   cudaMalloc(&dv, 4 * sizeof(float));
   const int R = 96;
-  for (int N : {32, 64, 128}) run(SS, N, 0, R, 0, dc, dv);
+  for (int N : {32, 64, 96, 128, 160, 192, 256}) run(SS, N, 0, R, 0, dc, dv);
   for (int N : {32, 64, 128}) run(TS, 0, N, R, 0, dc, dv);
   for (int mode : {MIX, TWO, BLK}) {
     run(mode, 128, 64, R, 0, dc, dv);

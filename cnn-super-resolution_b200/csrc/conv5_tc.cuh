@@ -135,6 +135,10 @@ struct Cfg {
   static constexpr uint32_t TMEM_COLS = DYS ? 512 : (NACC * ACCW <= 256 ? 256 : 512);
   static_assert(DYS ? (TWO ? NACC * COUT <= REGION : NACC * COUT <= 512) : NACC * ACCW <= 512,
                 "accumulators must fit tensor memory");
+#ifndef C5_FRAG_EPI
+#define C5_FRAG_EPI 1
+#endif
+  static constexpr bool FRAG_EPI = C5_FRAG_EPI != 0 && DYS && !TWO && MODE_ == 1;   // fragment-layout epilogue
   static constexpr int MAXROWS = 256 / COUT;          // DYS: output rows per instruction (N <= 256)
   static_assert(CIN % 16 == 0 && COUT % 16 == 0, "channel counts");
   static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory");
@@ -519,6 +523,76 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
     }
   } else {
     // ============================ E: epilogue =================================================
+    if (C::FRAG_EPI) {
+      // MODE 1 with the accumulator read as 16x256b fragments (the layout of an mma accumulator:
+      // a thread holds 2 adjacent channels of rows lane/4 and lane/4 + 8 of a 16-lane half, for
+      // every group of 8 channels), so that 4 lanes cover 32 contiguous bytes of a pixel and an
+      // 8-byte access per lane touches 8 lines per instruction.  With one pixel per lane (64
+      // channels = 256 bytes apart) every 16-byte access of a warp touched 32 lines, and the L1
+      // pipe -- mask loads and d1 stores of the epilogue -- was what bound the kernel (81 % busy
+      // at 53 % tensor-pipe activity, profiles/r3l_ncu_summary.txt).
+      const int q4 = lane >> 2, l4 = lane & 3;
+      long long ob[4];   // pixels (warp & 3) * 32 + j * 8 + lane / 4
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const long long vo = X0 + (warp & 3) * 32 + j * 8 + q4;
+        ob[j] = -1;
+        if (vo < vw) {
+          const int smp = (int)(vo / slot_w), x = (int)(vo - (long long)smp * slot_w);
+          if (x < ow) ob[j] = (((long long)smp * oh) * ow + x) * C::COUT + 2 * l4;
+        }
+      }
+      const long long orow_f = (long long)ow * C::COUT;
+      const float csf = 1.f / (s_in * sw);
+      for (int rho = 0; rho < oh; rho++) {
+        const int acc = rho % C::NACC;
+        // the relu' mask of this row does not depend on the accumulator: all its loads are in
+        // flight while the row's MMAs finish (issued after the wait, their HBM round trips --
+        // several dependent batches per row -- were the row period)
+        float2 gm[4][C::COUT / 8];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int g = 0; g < C::COUT / 8; g++)
+            gm[j][g] = ob[j] >= 0 ? __ldg(reinterpret_cast<const float2*>(a.aux + ob[j] + rho * orow_f + 8 * g))
+                                  : make_float2(0.f, 0.f);
+        mbar_wait(&done[acc], (uint32_t)((rho / C::NACC) & 1));
+        tcgen05_fence_after();
+        uint32_t f[2][32];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32 + h * 16) << 16) + (uint32_t)(acc * C::COUT);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+              "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+              "[%32];"
+              : "=r"(f[h][0]), "=r"(f[h][1]), "=r"(f[h][2]), "=r"(f[h][3]), "=r"(f[h][4]), "=r"(f[h][5]),
+                "=r"(f[h][6]), "=r"(f[h][7]), "=r"(f[h][8]), "=r"(f[h][9]), "=r"(f[h][10]), "=r"(f[h][11]),
+                "=r"(f[h][12]), "=r"(f[h][13]), "=r"(f[h][14]), "=r"(f[h][15]), "=r"(f[h][16]),
+                "=r"(f[h][17]), "=r"(f[h][18]), "=r"(f[h][19]), "=r"(f[h][20]), "=r"(f[h][21]),
+                "=r"(f[h][22]), "=r"(f[h][23]), "=r"(f[h][24]), "=r"(f[h][25]), "=r"(f[h][26]),
+                "=r"(f[h][27]), "=r"(f[h][28]), "=r"(f[h][29]), "=r"(f[h][30]), "=r"(f[h][31])
+              : "r"(ta));
+        }
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&acc_free[acc]);
+        // f[h][4 g + 2 s + e] = D[row h*16 + s*8 + lane/4][channel 8 g + 2 (lane%4) + e]
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (ob[j] < 0) continue;
+          const int h = j >> 1, sidx = j & 1;
+          float* o = a.out + ob[j] + rho * orow_f;
+#pragma unroll
+          for (int g = 0; g < C::COUT / 8; g++) {
+            const float x0 = __uint_as_float(f[h][4 * g + 2 * sidx]) * csf;
+            const float x1 = __uint_as_float(f[h][4 * g + 2 * sidx + 1]) * csf;
+            *reinterpret_cast<float2*>(o + 8 * g) =
+                make_float2(gm[j][g].x > 0.f ? x0 : 0.f, gm[j][g].y > 0.f ? x1 : 0.f);
+          }
+        }
+      }
+    } else {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int m = (warp & 3) * 32 + lane;
     const long long vout = X0 + m;
@@ -579,6 +653,7 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
       if (lane == 0 && omax > 0.f) atomicMax(a.out_max, __float_as_uint(omax));
+    }
     }
   }
 

@@ -194,7 +194,9 @@ def test_deltas_vs_oracle(ctx, port, shape):
 
 
 @default_paths_only
-@pytest.mark.parametrize("w1,h1,S", [(25, 25, 170), (30, 19, 150), (25, 25, 333)])
+@pytest.mark.parametrize("w1,h1,S", [(25, 25, 170), (30, 19, 150), (25, 25, 333),
+                                     # maps lower than the 8-row accumulator ring / the 5 filter rows
+                                     (9, 5, 460), (8, 7, 520), (12, 9, 350), (40, 13, 110)])
 def test_conv5_tensor_core_kernels_vs_oracle(ctx, port, w1, h1, S):
     """The 9-5-5 network's layer 2 on the tensor cores (conv5_tc.cuh): forward 64 -> 32 and the
     layer-1 deltas, as virtual-image implicit GEMMs with FP16-split operands, at sample counts

@@ -110,9 +110,20 @@ struct Cfg {
   // where an instruction carries at most 256 / COUT = 4 rows)
   static constexpr bool TWO = DYS && 2 * 8 * COUT_ <= 512;
   static constexpr int NSLOT = 3, NACC = DYS ? 8 : 7;
-  static constexpr int REGION = 256;                  // DYS: columns of region H; L follows
-  static constexpr int BLK_BYTES = F * COUT * 32;     // DYS: image block of one (dx, slice)
-  static constexpr int IMG_L = F * NSLICE * BLK_BYTES;   // DYS: byte offset of the W_lo blocks
+  // HALVES (MODE 1, C_out = 64; experiment, default off): two issuers that each own 32 output
+  // channels -- all three products into their own region, N = 5 * 32 = 160 per instruction like
+  // the forward -- instead of one issuer carrying every instruction.  Same results, same speed
+  // (2.302 ms per chunk of 3 028 either way: the deltas kernel is not issue-bound), twice the A
+  // fetches: not used.
+#ifndef C5_HALVES
+#define C5_HALVES 0
+#endif
+  static constexpr bool HALVES = C5_HALVES != 0 && DYS && !TWO && COUT_ == 64;
+  static constexpr int CI = HALVES ? 32 : COUT_;      // DYS: output channels per issuer and region
+  static constexpr int NH = HALVES ? 2 : 1;
+  static constexpr int REGION = 256;                  // DYS: columns of a region (TWO: H, L; HALVES)
+  static constexpr int BLK_BYTES = F * CI * 32;       // DYS: image block of one (dx, slice[, half])
+  static constexpr int IMG_L = F * NSLICE * NH * BLK_BYTES;   // DYS: byte offset of the W_lo blocks
   // STACK: A_hi x [W_hi ; W_lo] as ONE N = 2*COUT instruction (its two halves land in separate
   // accumulator columns, the epilogue adds them) + A_lo x W_hi: two A-tile fetches per K-step
   // instead of three.  The A tile (128 rows at a 16-byte shifted base: every 128-byte core matrix
@@ -126,20 +137,21 @@ struct Cfg {
   // MMA issuer warps: output rows split modulo N_I (3 instead of 2: forward of a 3 028-patch
   // chunk 0.99 -> 0.94 ms; 4: no further gain)
   // (DYS: issuer 0 owns region H, issuer 1 region L -- no accumulator has two writers)
-  static constexpr int N_I = DYS ? (TWO ? 2 : 1) : 3;
+  static constexpr int N_I = DYS ? ((TWO || HALVES) ? 2 : 1) : 3;
 #ifndef C5_NP
 #define C5_NP 5
 #endif
   static constexpr int W_E = 0, W_P = 4, N_P = C5_NP, W_I = W_P + N_P, NT = (W_I + N_I) * 32;
   static constexpr int ITEMS = (2 * PW + N_P * 32 - 1) / (N_P * 32);   // plane items per producer thread
   static constexpr uint32_t TMEM_COLS = DYS ? 512 : (NACC * ACCW <= 256 ? 256 : 512);
-  static_assert(DYS ? (TWO ? NACC * COUT <= REGION : NACC * COUT <= 512) : NACC * ACCW <= 512,
+  static_assert(DYS ? ((TWO || HALVES) ? NACC * CI <= REGION : NACC * COUT <= 512) : NACC * ACCW <= 512,
                 "accumulators must fit tensor memory");
 #ifndef C5_FRAG_EPI
 #define C5_FRAG_EPI 1
 #endif
   static constexpr bool FRAG_EPI = C5_FRAG_EPI != 0 && DYS && !TWO && MODE_ == 1;   // fragment-layout epilogue
-  static constexpr int MAXROWS = 256 / COUT;          // DYS: output rows per instruction (N <= 256)
+  static_assert(!HALVES || FRAG_EPI, "the per-pixel epilogue reads one region only");
+  static constexpr int MAXROWS = 256 / CI;            // DYS: output rows per instruction (N <= 256)
   static_assert(CIN % 16 == 0 && COUT % 16 == 0, "channel counts");
   static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory");
 };
@@ -212,9 +224,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
       using DC = Cfg<32, 64, 1>;
       if (DC::DYS) {
         const int dy = t / F, dx = t % F, c = ci / 16, kk = ci % 16;
-        const int row = (F - 1 - dy) * N1 + n;
-        const int off = ((dx * DC::NSLICE + c) * DC::BLK_BYTES) / 2 + (row >> 3) * 128 + (kk >> 3) * 64 +
-                        (row & 7) * 8 + (kk & 7);
+        const int row = (F - 1 - dy) * DC::CI + n % DC::CI, half = n / DC::CI;
+        const int off = (((dx * DC::NSLICE + c) * DC::NH + half) * DC::BLK_BYTES) / 2 + (row >> 3) * 128 +
+                        (kk >> 3) * 64 + (row & 7) * 8 + (kk & 7);
         d[off] = __ushort_as_half(hi);
         d[DC::IMG_L / 2 + off] = __ushort_as_half(lo);
       } else {
@@ -395,10 +407,11 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
         return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
                ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
       };
-      const uint32_t region = tmem + (uint32_t)(C::TWO ? me * C::REGION : 0);
-      const uint32_t imgH = sW + (uint32_t)((C::TWO && me == 1) ? C::IMG_L : 0);
+      const uint32_t region = tmem + (uint32_t)((C::TWO || C::HALVES) ? me * C::REGION : 0);
+      const uint32_t imgH = sW + (uint32_t)((C::TWO && me == 1) ? C::IMG_L : 0) +
+                            (uint32_t)(C::HALVES ? me * C::BLK_BYTES : 0);
       constexpr uint64_t kImgL = (uint64_t)(C::IMG_L >> 4);             // descriptor address units
-      constexpr uint64_t kDx = (uint64_t)((C::NSLICE * C::BLK_BYTES) >> 4);
+      constexpr uint64_t kDx = (uint64_t)((C::NSLICE * C::NH * C::BLK_BYTES) >> 4);
       for (int r = 0; r < ih; r++) {
         const int dy_lo = max(0, r + P - (oh - 1)), dy_hi = min(F - 1, r + P);
         // the instructions of one (slice, dx) step of this input row: rows of dy = dy_hi .. dy_lo
@@ -414,9 +427,9 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
             if (b >= a0) {
               const int s0 = (r - b + P) % C::NACC;
               const int n = min(min(b - a0 + 1, C::NACC - s0), C::MAXROWS);
-              sd[q] = (uint32_t)(s0 * C::COUT);
-              sb[q] = (uint64_t)(((F - 1 - b) * C::COUT * 32) >> 4);
-              si[q] = make_idesc_f16(C::M, n * C::COUT);
+              sd[q] = (uint32_t)(s0 * C::CI);
+              sb[q] = (uint64_t)(((F - 1 - b) * C::CI * 32) >> 4);
+              si[q] = make_idesc_f16(C::M, n * C::CI);
               n_out = q + 1;
               b -= n;
             }
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
           const uint32_t ah = sS + slot * C::SLOT_BYTES, al = ah + 2 * C::PB;
           if (elect_one()) {
             const uint64_t dah0 = adesc(ah), dal0 = adesc(al);
-            const uint64_t blk0 = bdesc(imgH + (uint32_t)(c * C::BLK_BYTES));
+            const uint64_t blk0 = bdesc(imgH + (uint32_t)(c * C::NH * C::BLK_BYTES));
             // all products of the pieces, in a fixed order
             auto step = [&](uint64_t dah, uint64_t dal, uint64_t blk, int ns, const uint32_t (&sd)[3],
                             const uint64_t (&sb)[3], const uint32_t (&si)[3], uint32_t acc_flag) {
@@ -561,7 +574,23 @@ __global__ void __launch_bounds__(C::NT, 1) conv5_tc_kernel(Args a) {
         uint32_t f[2][32];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32 + h * 16) << 16) + (uint32_t)(acc * C::COUT);
+          const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32 + h * 16) << 16);
+          if (C::HALVES) {
+            // channels 0..31 in region 0, 32..63 in region 1 (slot = 32 columns in each)
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+              uint32_t* ff = f[h] + 16 * hf;
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                  "%13, %14, %15}, [%16];"
+                  : "=r"(ff[0]), "=r"(ff[1]), "=r"(ff[2]), "=r"(ff[3]), "=r"(ff[4]), "=r"(ff[5]), "=r"(ff[6]),
+                    "=r"(ff[7]), "=r"(ff[8]), "=r"(ff[9]), "=r"(ff[10]), "=r"(ff[11]), "=r"(ff[12]),
+                    "=r"(ff[13]), "=r"(ff[14]), "=r"(ff[15])
+                  : "r"(tl + (uint32_t)(hf * C::REGION + acc * C::CI)));
+            }
+            continue;
+          }
+          const uint32_t ta = tl + (uint32_t)(acc * C::COUT);
           asm volatile(
               "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
               "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "

@@ -21,18 +21,28 @@
 // 128 rows of a K-major A operand are consecutive 16-byte units, so the tile of tap (dy, dx) is
 // the same plane read at base + dx*16 bytes -- the 25 taps of an input row reuse one conversion
 // and one shared-memory copy.  The 5 output rows an input row contributes to (dy = 0..4) each
-// have their own accumulator in tensor memory; a row leaves through the epilogue when its last
-// input row has been issued.  W (hi | lo, 204 800 bytes) stays resident in shared memory.
+// have their own accumulator in tensor memory, side by side in an 8-slot ring (row rho in slot
+// rho % 8), so that ONE instruction A x [W(dy=4); ...; W(dy=0)] feeds all five (N = 5 * C_out
+// = 160 forward; deltas 4 + 1 rows of 64): "dy-stacked" MMAs, see Cfg::DYS.  A row leaves
+// through the epilogue when its last input row has been issued.  W (hi | lo, 204 800 bytes)
+// stays resident in shared memory, stored [hi | lo][dx][slice][(4 - dy) * C_out + n][16] so that
+// a range of filter rows is one B operand.
 //
-// Precision: operands are split x*s = hi + lo into two halves (lo unscaled), the three products
-// hi.hi + hi.lo + lo.hi accumulate in ONE FP32 accumulator (same scheme as the wide inference
-// kernel, fused_forward_hpw.cuh): 22 operand bits.  s is a power of two that maps the largest
-// |x| of the tensor (found on the device by absmax_kernel) to 2^14; the weights likewise.
+// Precision: operands are split x*s = hi + lo into two halves (lo unscaled), products
+// hi.hi + hi.lo + lo.hi: 22 operand bits.  Forward: hi.hi + lo.hi accumulate in region H, hi.lo in
+// region L (one issuer each; the epilogue adds them); deltas: all three in ONE FP32 accumulator
+// (same scheme as the wide inference kernel, fused_forward_hpw.cuh).  s is a power of two that
+// maps the largest |x| of the tensor (found on the device by absmax_kernel) to 2^14; the
+// weights likewise.
 //
-//   P  (5 warps)  input row slice -> split -> planes                          -> full[slot]
-//   I0 .. I2      MMA issuers (output row rho belongs to issuer rho % 3): 5 dx x 3 products per dy
+//   P  (5 warps)  input row slice -> split -> planes (loads two slices ahead)  -> full[slot]
+//   I0 [, I1]     MMA issuers: per (slice, dx) one instruction per product and piece of the
+//                 row range (pieces: where the ring wraps, and <= 256 / C_out rows)
 //                                                                            -> empty[slot], done[acc]
 //   E  (4 warps)  accumulator -> bias + relu / relu' mask -> global          -> acc_free[acc]
+//                 (deltas: 16x256b fragments, mask loaded before the accumulator wait)
+// C5_DYS=0 builds the earlier scheme: one accumulator per row, instructions per (dy, dx), three
+// issuers by output row, A_hi x [W_hi; W_lo] stacked where tensor memory allows.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
     // ============================ PA: im2col tiles ========================================
     for (int i = 0; i < my_tiles; i++) {
       const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
-      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
-      // input offset of the window origin of each pixel of the tile (-1: past the end)
+      // input offset of the window origin of each pixel of the tile (-1: past the end).  base[]
+      // of this parity was last read for tile i-2, before the barrier of tile i-1.
       int* base = sBase + (i & 1) * C::PX;
       if (tid < C::PX) {
         const long long p = p0 + tid;
@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
           v[u][j] = b >= 0 ? __ldg(in + b + toff) : 0.f;
         }
       }
+      // the gather lands in registers: only the stores need the stage MMA(i-2) is reading, so
+      // the loads of tile i fly while that MMA runs (issued behind the wait, their latency was
+      // part of every tile)
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
 #pragma unroll
       for (int u = 0; u < C::PA_ITEMS; u++) {
         const int it = tid + C::N_PA * 32 * u;
@@ -147,7 +151,6 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
     float gb = 0.f;
     for (int i = 0; i < my_tiles; i++) {
       const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
-      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
       float* sB = wg_smem + (i & 1) * C::STAGE + 2 * C::A_FLOATS;
       float v[C::PX / 8][4];   // this thread's 8 pixel quads, all loads in flight together
 #pragma unroll
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
           const long long p = p0 + 4 * ((pw >> 1) + 2 * u) + j;
           v[u][j] = p < P ? __ldg(d + p * C::N + c) : 0.f;
         }
+      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));   // (loads first, as in PA)
 #pragma unroll
       for (int u = 0; u < C::PX / 8; u++) {
         const int q = (pw >> 1) + 2 * u;

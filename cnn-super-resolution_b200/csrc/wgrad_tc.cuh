@@ -39,13 +39,22 @@ struct Cfg {
   static constexpr int A_FLOATS = TP * PX, B_FLOATS = 2 * N * PX;
   static constexpr int STAGE = 2 * A_FLOATS + B_FLOATS;
   static constexpr int oBase = 2 * STAGE;                   // per-pixel input offsets [2][PX]
-  static constexpr int TOTAL = oBase + 2 * PX;
+  // staged input rows for the im2col gather (STAGED, as in wgrad1_fused_tc.cuh): 2 x [NSLOT][SPITCH]
+  static constexpr int NSLOT = 20, SPITCH = 40, MIN_OW = 22;
+  static constexpr int oStage = oBase + 2 * PX;
+  static constexpr int TOTAL = oStage + 2 * NSLOT * SPITCH;
   // the M = 128 MMA also reads rows TP..127 of an A tile: they must lie inside the allocation
   // (their products land in accumulator rows nobody reads)
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(TOTAL + (128 - TP) * PX);
   static constexpr uint32_t cDhi = 0, cDlo = 128, TMEM_COLS = 256;
 };
 
+// STAGED: the input rows a tile's windows touch are copied to shared memory with coalesced
+// cp.async loads, one tile ahead, and the im2col gather reads them from there (gathering from
+// global memory costs one L1 tag lookup per 128-byte line a warp's 32 taps touch, ~8 per load
+// instruction).  Needs MIN_OW <= ow, ow + 8 <= SPITCH and oh >= 3: a tile then spans at most 4
+// output rows of at most 2 samples = NSLOT input rows.  The scheme of wgrad1_fused_tc_kernel.
+template <bool STAGED>
 __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __restrict__ d,
                                                                const float* __restrict__ in,
                                                                float* __restrict__ partial, int ow,
@@ -80,6 +89,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
     const int t = C::T + r / C::PX, k = r % C::PX;
     wg_smem[(tile >> 1) * C::STAGE + (tile & 1) * C::A_FLOATS + kmajor_offset(t, k, C::PX)] = 0.f;
   }
+  for (int i = tid; i < 2 * C::NSLOT * C::SPITCH; i += C::NT) wg_smem[C::oStage + i] = 0.f;
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
@@ -90,59 +100,142 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad1_tc_kernel(const float* __re
 
   if (warp < C::W_PB) {
     // ============================ PA: im2col tiles ========================================
+    float* sStage = wg_smem + C::oStage;
+    // STAGED: pixel offsets and input rows of tile i -> buffers i&1, asynchronously (cp.async):
+    // issued one tile ahead, so the L2 latency hides behind the gather / stores of the tile
+    // before.  slot k of the stage = one input row: rows row0 .. ih-1 of sample s0 (count0 of
+    // them), then rows 0 .. of sample s0+1.  A pixel (sample s, output row `row`, column col)
+    // reads slots first .. first+8 at columns col .. col+8
+    // Tile geometry without integer divisions in the loop (a dependent chain of ten of them was
+    // 1 500 cycles per tile): (sample, output row, column) of the tile's first pixel advance by
+    // a fixed step from tile to tile.
+    int g_p0 = 0, g_s = 0, g_row = 0, g_col = 0, d_s = 0, d_row = 0, d_col = 0;
+    const float inv_iw = 1.f / (float)iw;
+    if (STAGED) {
+      g_p0 = (int)blockIdx.x * C::PX;
+      const int g = g_p0 / ow;
+      g_col = g_p0 - g * ow;
+      g_s = g / oh;
+      g_row = g - g_s * oh;
+      const int step = (int)gridDim.x * C::PX, sg = step / ow;
+      d_col = step - sg * ow;
+      d_s = sg / oh;
+      d_row = sg - d_s * oh;
+    }
+    auto stage_issue = [&](int i) {
+      if (i >= my_tiles) return;
+      const int ip0 = g_p0, s0 = g_s, row0 = g_row, col0 = g_col, count0 = ih - row0;
+      // advance to the next tile of this CTA
+      g_p0 += (int)gridDim.x * C::PX;
+      g_col += d_col;
+      if (g_col >= ow) { g_col -= ow; g_row++; }
+      g_row += d_row;
+      if (g_row >= oh) { g_row -= oh; g_s++; }
+      g_s += d_s;
+      float* st = sStage + (i & 1) * (C::NSLOT * C::SPITCH);
+      // pixel j of the tile: column col0 + j wraps at most three times (ow >= MIN_OW)
+      auto first_slot = [&](int j, int& col) {
+        const int c = col0 + j;
+        const int w = (c >= ow) + (c >= 2 * ow) + (c >= 3 * ow);
+        col = c - w * ow;
+        const int row = row0 + w;
+        return row < oh ? w : count0 + row - oh;
+      };
+      if (tid < C::PX) {
+        int col;
+        const int f = first_slot(tid, col);
+        sBase[(i & 1) * C::PX + tid] = ip0 + tid < P ? f * C::SPITCH + col : 0;
+      }
+      const long long left = P - ip0;
+      int col_l;
+      const int n_elems = (first_slot((left < C::PX ? (int)left : C::PX) - 1, col_l) + C::F) * iw;
+#pragma unroll
+      for (int u = 0; u < (C::NSLOT * C::SPITCH + C::N_PA * 32 - 1) / (C::N_PA * 32); u++) {
+        const int e = tid + C::N_PA * 32 * u;
+        if (e < n_elems) {
+          const int k = __float2int_rz(((float)e + 0.5f) * inv_iw), x = e - k * iw;
+          const int src = k < count0 ? (s0 * ih + row0 + k) : ((s0 + 1) * ih + (k - count0));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                           smem_u32(st + k * C::SPITCH + x)),
+                       "l"(in + src * iw + x)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // loop-invariant per item: stage offset of the tap, first pixel of the quad, tile offset
+    int item_toff[C::PA_ITEMS], item_q4[C::PA_ITEMS], item_off[C::PA_ITEMS];
+#pragma unroll
+    for (int u = 0; u < C::PA_ITEMS; u++) {
+      const int it = tid + C::N_PA * 32 * u;
+      const bool ok = it < C::T * (C::PX / 4);
+      const int t = ok ? it % C::T : 0, q = ok ? it / C::T : 0;
+      item_toff[u] = (t / C::F) * C::SPITCH + (t % C::F);
+      item_q4[u] = 4 * q;
+      item_off[u] = ok ? kmajor_offset(t, 4 * q, C::PX) : -1;
+    }
+    if (STAGED) stage_issue(0);
     for (int i = 0; i < my_tiles; i++) {
       const long long p0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * C::PX;
-      // input offset of the window origin of each pixel of the tile (-1: past the end).  base[]
-      // of this parity was last read for tile i-2, before the barrier of tile i-1.
       int* base = sBase + (i & 1) * C::PX;
-      if (tid < C::PX) {
-        const long long p = p0 + tid;
-        int b = -1;
-        if (p < P) {
-          const long long s = p / per;
-          const int rem = (int)(p - s * per), row = rem / ow, col = rem - row * ow;
-          b = (int)((s * ih + row) * iw + col);
+      float v[C::PA_ITEMS][4];
+      if (STAGED) {
+        const float* st = sStage + (i & 1) * (C::NSLOT * C::SPITCH);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        named_bar_sync(1, C::N_PA * 32);   // tile i staged; everybody is done with tile i-1
+        stage_issue(i + 1);
+#pragma unroll
+        for (int u = 0; u < C::PA_ITEMS; u++) {
+          const int4 b4 = *reinterpret_cast<const int4*>(base + item_q4[u]);
+          v[u][0] = st[b4.x + item_toff[u]];
+          v[u][1] = st[b4.y + item_toff[u]];
+          v[u][2] = st[b4.z + item_toff[u]];
+          v[u][3] = st[b4.w + item_toff[u]];
         }
-        base[tid] = b;
+        // the stage is separate from the operand tiles: only the stores wait for MMA(i-2)
+        if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+      } else {
+        if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
+        // input offset of the window origin of each pixel of the tile (-1: past the end)
+        if (tid < C::PX) {
+          const long long p = p0 + tid;
+          int b = -1;
+          if (p < P) {
+            const long long sm = p / per;
+            const int rem = (int)(p - sm * per), row = rem / ow, col = rem - row * ow;
+            b = (int)((sm * ih + row) * iw + col);
+          }
+          base[tid] = b;
+        }
+        named_bar_sync(1, C::N_PA * 32);
+        // item = (tap t, pixel quad q); consecutive lanes take consecutive taps.  All loads of
+        // a thread are issued before the first is used
+#pragma unroll
+        for (int u = 0; u < C::PA_ITEMS; u++) {
+          const int it = tid + C::N_PA * 32 * u;
+          const int t = it % C::T, q = it / C::T;
+          const int toff = (t / C::F) * iw + (t % C::F);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int b = it < C::T * (C::PX / 4) ? base[4 * q + j] : -1;
+            v[u][j] = b >= 0 ? __ldg(in + b + toff) : 0.f;
+          }
+        }
       }
-      named_bar_sync(1, C::N_PA * 32);
       float* sAh = wg_smem + (i & 1) * C::STAGE;
       float* sAl = sAh + C::A_FLOATS;
-      // item = (tap t, pixel quad q); consecutive lanes take consecutive taps.  All loads of a
-      // thread are issued before the first is used: the gather is latency-bound otherwise
-      // (one item at a time: 6 000 cycles per tile against 900 of MMA work)
-      float v[C::PA_ITEMS][4];
 #pragma unroll
       for (int u = 0; u < C::PA_ITEMS; u++) {
-        const int it = tid + C::N_PA * 32 * u;
-        const int t = it % C::T, q = it / C::T;
-        const int toff = (t / C::F) * iw + (t % C::F);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int b = it < C::T * (C::PX / 4) ? base[4 * q + j] : -1;
-          v[u][j] = b >= 0 ? __ldg(in + b + toff) : 0.f;
-        }
-      }
-      // the gather lands in registers: only the stores need the stage MMA(i-2) is reading, so
-      // the loads of tile i fly while that MMA runs (issued behind the wait, their latency was
-      // part of every tile)
-      if (i >= 2) mbar_wait(&empty[i & 1], (uint32_t)(((i - 2) >> 1) & 1));
-#pragma unroll
-      for (int u = 0; u < C::PA_ITEMS; u++) {
-        const int it = tid + C::N_PA * 32 * u;
-        if (it < C::T * (C::PX / 4)) {
-          const int t = it % C::T, q = it / C::T;
+        if (item_off[u] >= 0) {
           float hi[4], lo[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) split_tf32(v[u][j], hi[j], lo[j]);
-          const int off = kmajor_offset(t, 4 * q, C::PX);
-          *reinterpret_cast<float4*>(sAh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(sAl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<float4*>(sAh + item_off[u]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(sAl + item_off[u]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       fence_proxy_async();
-      mbar_arrive(&full[i & 1]);   // (base[] of this stage is rewritten two tiles later, behind
-                                   // the next tile's barrier)
+      mbar_arrive(&full[i & 1]);
     }
   } else if (warp < C::W_I) {
     // ============================ PB: delta tiles + bias sums ==============================
@@ -455,14 +548,20 @@ inline int wgrad1_tc(srcnn_ctx* ctx, const float* d, const float* in, int n, int
   if (in_elems > 0x7fffffffLL) return 0;   // 32-bit input offsets
   const long long tiles = (P + Cfg::PX - 1) / Cfg::PX;
   if (tiles > 0x7fffffffLL) return 0;
-  SRCNN_TRY(ensure_func_setup(ctx, wgrad1_tc_kernel, Cfg::SMEM_BYTES));
+  const bool staged = ow >= Cfg::MIN_OW && ow + Cfg::F - 1 <= Cfg::SPITCH && oh >= 3;
+  if (staged) SRCNN_TRY(ensure_func_setup(ctx, wgrad1_tc_kernel<true>, Cfg::SMEM_BYTES));
+  else SRCNN_TRY(ensure_func_setup(ctx, wgrad1_tc_kernel<false>, Cfg::SMEM_BYTES));
   const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
   *count = grid;
   SRCNN_TRY(ensure_scratch(ctx, &ctx->splitk_scratch, &ctx->splitk_bytes,
                            sizeof(float) * (size_t)grid * (Cfg::T * Cfg::N + Cfg::N)));
-  wgrad1_tc_kernel<<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
-      d, in, (float*)ctx->splitk_scratch, ow, oh, P, (int)tiles);
+  if (staged)
+    wgrad1_tc_kernel<true><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
+        d, in, (float*)ctx->splitk_scratch, ow, oh, P, (int)tiles);
+  else
+    wgrad1_tc_kernel<false><<<grid, Cfg::NT, Cfg::SMEM_BYTES, ctx->stream>>>(
+        d, in, (float*)ctx->splitk_scratch, ow, oh, P, (int)tiles);
   return 1;
 }
 

@@ -148,17 +148,18 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad5_tc_kernel(Args a) {
 #pragma unroll
     for (int c = 0; c < 16; c++) gb[c] = 0.f;
     const bool bias_thread = set == 0 && j == 0;
-    float4 v[4];
-    auto load = [&](int i) {
-      const bool ok = i >= i0 && q < Q1 && sy < oh2 && sx < ow2;
+    // loads run two K-steps ahead of their use (v: this K-step, vn: the next)
+    float4 v[4], vn[4];
+    auto load = [&](float4 (&dstv)[4], int i) {
+      const bool ok = i >= i0 && i < n_ks && q < Q1 && sy < oh2 && sx < ow2;
       if (ok) {
         const float4* p = reinterpret_cast<const float4*>(
             a.d2 + (((size_t)ss * oh2 + sy) * ow2 + sx) * C::N + half * 16);
 #pragma unroll
-        for (int c = 0; c < 4; c++) v[c] = __ldg(p + c);
+        for (int c = 0; c < 4; c++) dstv[c] = __ldg(p + c);
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; c++) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 4; c++) dstv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (i >= i0) {   // advance to the pixel of the next K-step
         q += C::KS;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad5_tc_kernel(Args a) {
         while (sy >= h1) { sy -= h1; ss++; }
       }
     };
-    if (n_ks > 0) load(0);
+    if (n_ks > 0) { load(v, 0); load(vn, 1); }
     for (int i = 0; i < n_ks; i++) {
       const int stage = i % C::NSTAGE;
       uint32_t hi[8], lo[8];
@@ -179,7 +180,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) wgrad5_tc_kernel(Args a) {
           gb[4 * c] += v[c].x; gb[4 * c + 1] += v[c].y; gb[4 * c + 2] += v[c].z; gb[4 * c + 3] += v[c].w;
         }
       }
-      if (i + 1 < n_ks) load(i + 1);   // in flight while waiting for the stage
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] = vn[c];
+      load(vn, i + 2);                 // in flight while waiting for the stage
       if (i >= C::NSTAGE) mbar_wait(&empty_a[stage], (uint32_t)(((i / C::NSTAGE) - 1) & 1));
       uint8_t* s = dst + stage * C::STAGE;
       *reinterpret_cast<uint4*>(s) = make_uint4(hi[0], hi[1], hi[2], hi[3]);                        // hi, group c=0

@@ -21,17 +21,17 @@
 // 128 rows of a K-major A operand are consecutive 16-byte units, so the tile of tap (dy, dx) is
 // the same plane read at base + dx*16 bytes -- the 25 taps of an input row reuse one conversion
 // and one shared-memory copy.  The 5 output rows an input row contributes to (dy = 0..4) each
-// have their own accumulator in tensor memory, side by side in an 8-slot ring (row rho in slot
-// rho % 8), so that ONE instruction A x [W(dy=4); ...; W(dy=0)] feeds all five (N = 5 * C_out
+// have their own accumulator in tensor memory, side by side in a ring of 16 (forward) / 8
+// (deltas) slots (row rho in slot rho % NACC), so that ONE instruction A x [W(dy=4); ...; W(dy=0)] feeds all five (N = 5 * C_out
 // = 160 forward; deltas 4 + 1 rows of 64): "dy-stacked" MMAs, see Cfg::DYS.  A row leaves
 // through the epilogue when its last input row has been issued.  W (hi | lo, 204 800 bytes)
 // stays resident in shared memory, stored [hi | lo][dx][slice][(4 - dy) * C_out + n][16] so that
 // a range of filter rows is one B operand.
 //
 // Precision: operands are split x*s = hi + lo into two halves (lo unscaled), products
-// hi.hi + hi.lo + lo.hi: 22 operand bits.  Forward: hi.hi + lo.hi accumulate in region H, hi.lo in
-// region L (one issuer each; the epilogue adds them); deltas: all three in ONE FP32 accumulator
-// (same scheme as the wide inference kernel, fused_forward_hpw.cuh).  s is a power of two that
+// hi.hi + hi.lo + lo.hi: 22 operand bits, all three in ONE FP32 accumulator per output row
+// (same scheme as the wide inference kernel, fused_forward_hpw.cuh; one issuer, so the
+// summation order is fixed).  s is a power of two that
 // maps the largest |x| of the tensor (found on the device by absmax_kernel) to 2^14; the
 // weights likewise.
 //
@@ -114,12 +114,19 @@ struct Cfg {
 #ifndef C5_DYS
 #define C5_DYS 1
 #endif
+#ifndef C5_TWO
+#define C5_TWO 0
+#endif
   static constexpr bool DYS = C5_DYS != 0;
   // two regions (hi.w_lo apart from the rest, one issuer each) where 2 * 8 rows fit tensor memory
   // (MODE 0); else all three products of a row share one accumulator and one issuer (MODE 1,
   // where an instruction carries at most 256 / COUT = 4 rows)
-  static constexpr bool TWO = DYS && 2 * 8 * COUT_ <= 512;
-  static constexpr int NSLOT = 3, NACC = DYS ? 8 : 7;
+  static constexpr bool TWO = C5_TWO != 0 && DYS && 2 * 8 * COUT_ <= 512;
+  // Forward (C_out = 32): ONE region of 16 slots and one issuer with all three products in a
+  // row's accumulator, like the deltas: a range of 5 rows wraps in 4 of 16 input rows instead
+  // of 4 of 8 (chunk of 3 028 patches 2.229 -> 2.207 ms).  C5_TWO=1: two regions of 8 slots, H
+  // (hi.w_hi + lo.w_hi) and L (hi.w_lo), one issuer each, added by the epilogue.
+  static constexpr int NSLOT = 3, NACC = DYS ? ((C5_TWO == 0 && COUT_ * 16 <= 512) ? 16 : 8) : 7;
   // HALVES (MODE 1, C_out = 64; experiment, default off): two issuers that each own 32 output
   // channels -- all three products into their own region, N = 5 * 32 = 160 per instruction like
   // the forward -- instead of one issuer carrying every instruction.  Same results, same speed

@@ -119,8 +119,16 @@ __global__ void __launch_bounds__(NT) n1_forward_smem_kernel(const float* __rest
   const float bias = __ldg(B);
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
     __syncthreads();
+    // cp.async: every 16-byte piece of the sample is in flight at once (a load -> store loop
+    // runs its ~14 iterations per thread as ~14 dependent HBM round trips: that WAS the kernel,
+    // 107 us per 3 028 samples of 21x21x32)
     const float4* src = reinterpret_cast<const float4*>(in + (long long)s * ih * iw * k);
-    for (int i = threadIdx.x; i < n4; i += NT) reinterpret_cast<float4*>(smp)[i] = __ldg(src + i);
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(smp);
+    for (int i = threadIdx.x; i < n4; i += NT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16u * (uint32_t)i), "l"(src + i)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int run = warp; run < oh * runs_per_row; run += NT / 32) {
       const int y = run / runs_per_row, x0 = (run - y * runs_per_row) * P;

@@ -6,7 +6,6 @@ Prints wall-clock ms per image (srcnn_block after each) for
   staged    srcnn_infer_rows_host (the product path: pipelined sub-band copies)
   zc-both   one launch, input and output in host memory
   zc-out    whole-image H2D copy, one launch writing host memory
-  zc-in     one launch reading host memory into a device buffer, whole-image D2H copy
 Kernel-development aid, not part of the bench contract."""
 import os
 import sys
@@ -36,7 +35,6 @@ for i, b in enumerate(imgs):
 h_in = [ctx.wrap(b.ptr, b.nbytes) for b in imgs]
 h_out = [ctx.wrap(b.ptr, b.nbytes) for b in outs]
 d_in = ctx.alloc(4 * IMG * IMG)
-d_out = ctx.alloc(4 * O * O)
 
 
 def staged(i):
@@ -54,13 +52,6 @@ def zc_out(i):
     ctx.block()
 
 
-def zc_in(i):
-    net.forward_fused(h_in[i], d_out, IMG, IMG, 1)
-    outs[i].array[:] = 0  # not timed as part of the path below; see loop
-    ctx.block()
-
-
-ref = None
 for name, fn in (("staged", staged), ("zc-both", zc_both), ("zc-out", zc_out)):
     for i in range(3):
         fn(i % R)

@@ -217,6 +217,13 @@ using fused_pl::tmem_ld_wait;
 using tc::mbar_arrive;
 using tc::named_bar_sync;
 
+// HP_L1WIDE (experiment, default off): in the layer-1-only launch the warps of the idle E2 / E3
+// roles take channel chunks too -- 16 warps of one 16-channel chunk each instead of 8 of two.
+// Same results; a C4 chunk of 3 028 patches takes 2.226 ms instead of 2.200 (64-byte runs per
+// pixel in the out1 stores instead of 128): E1's arithmetic is not that launch's bound.
+#ifndef HP_L1WIDE
+#define HP_L1WIDE 0
+#endif
 // HP_SPIN (experiment): bit 0 -- the three MMA issuers poll their barriers (test_wait, never
 // parked) instead of try_wait with a suspend hint; bit 1 -- E1 polls bar1 likewise
 #ifndef HP_SPIN
@@ -433,8 +440,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
     for (int i = 0; i < 2; i++) {
       mbar_init(&bar1[i], 1);
       mbar_init(&a2_full[i], C::N_E1 * 32);
-      mbar_init(&bar2[i], (L1ONLY && !C::A2SEP) ? C::N_E1 * 32 : 1);
-      mbar_init(&d1_free[i], C::N_E1 * 32);
+      mbar_init(&bar2[i], (L1ONLY && !C::A2SEP) ? (HP_L1WIDE ? 16 : C::N_E1) * 32 : 1);
+      mbar_init(&d1_free[i], ((L1ONLY && HP_L1WIDE) ? 16 : C::N_E1) * 32);
       mbar_init(&a3_full[i], 128);
       mbar_init(&bar3[i], 1);
       mbar_init(&d3_free[i], 128);
@@ -597,7 +604,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
 #endif
       PL_EV(t, 1)
     }
-  } else if (L1ONLY && !is_e1) {
+  } else if (L1ONLY && !is_e1 && !(HP_L1WIDE && (is_e2 || is_e3))) {
     // layer-1-only launch: the layer-2 / layer-3 roles have nothing to do
   } else if (warp == C::W_I2) {
     // ============================ I2: layer-2 MMA issuer (A2 in TMEM) ======================
@@ -674,13 +681,19 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
 #endif
       PL_EV(t, 9)
     }
-  } else if (is_e1) {
+  } else if (is_e1 || (L1ONLY && HP_L1WIDE && (is_e2 || is_e3))) {
     // ============================ E1: A2 = split(relu(out1) * s1), in place ================
     // warp w: TMEM lane quarter w&3, chunks g0 .. g0+E1_CHUNKS-1 of 16 channels.  Chunk g reads
     // D1 columns [16g,16g+16) and [64+16g, ..), then writes its hi pairs to a2col(g) and its lo
     // pairs to 64 + a2col(g): columns this warp has consumed
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int g0 = ((warp - C::W_E1) >> 2) * C::E1_CHUNKS;
+    // (wide layer-1-only launch: warp group wg = E1 first half, E1 second half, E2, E3 owns chunk wg)
+    constexpr bool WIDE = L1ONLY && HP_L1WIDE != 0;
+    constexpr int NCH = WIDE ? 1 : C::E1_CHUNKS;       // chunks per warp
+    constexpr int SPX = WIDE ? 20 : C::SP;             // floats per staged pixel
+    constexpr int LPP = WIDE ? 4 : 8;                  // lanes per pixel in the store loop
+    const int wg = is_e1 ? (warp - C::W_E1) >> 2 : (is_e2 ? 2 : 3);
+    const int g0 = WIDE ? wg : wg * C::E1_CHUNKS;
     // out1 (training): pixel index of this lane's pixel in tile 0, -1 = not an out1 pixel
     int pix1 = -1;
     const bool keep1 = BATCH && bx.out1 != nullptr;
@@ -690,7 +703,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       if (m < C::OW3 && vx < a.w && px < w1) pix1 = (smp * h1 + R0) * w1 + px;
     }
     const int w1_row = bx.pw - (C::F1 - 1);
-    float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) + (warp - C::W_E1) * (32 * C::SP);
+    float* st1 = reinterpret_cast<float*>(smem_raw + C::oS1) +
+                 (WIDE ? (wg * 4 + (warp & 3)) * (32 * SPX) : (warp - C::W_E1) * (32 * C::SP));
     float act_max = 0.f;   // L1ONLY: largest scaled activation this thread stored
     for (int b = 0; b < n_tiles; b++) {
       HPW(0, HP_EWAIT(&bar1[b & 1], (uint32_t)((b >> 1) & 1)))       // MMA-1(b) done
@@ -698,12 +712,12 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       tcgen05_fence_after();
       const uint32_t d1 = tmem + lane_base + C::cD1 + 128u * (uint32_t)(b & 1);
       // all loads of this warp's chunks first (one TMEM round trip), then the conversions
-      float va[C::E1_CHUNKS][16], vb[C::E1_CHUNKS][16];
+      float va[NCH][16], vb[NCH][16];
 #ifdef HP_PROF
       const unsigned _tl = (unsigned)clock();
 #endif
 #pragma unroll
-      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
+      for (int gl = 0; gl < NCH; gl++) {
         tmem_ld16_nowait(d1 + (g0 + gl) * 16, va[gl]);
         tmem_ld16_nowait(d1 + C::N1 + (g0 + gl) * 16, vb[gl]);
       }
@@ -721,7 +735,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
       }
       const uint32_t a2w = tmem + lane_base + C::cA2 + C::sA2 * (uint32_t)(b & 1);
 #pragma unroll
-      for (int gl = 0; gl < C::E1_CHUNKS; gl++) {
+      for (int gl = 0; gl < NCH; gl++) {
         const int g = g0 + gl;
         uint32_t hi[8], lo[8];
         float act[16];
@@ -741,7 +755,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
           tmem_st8u(a2w + C::A2LO + col, lo);
         }
         if (keep1) {
-          float4* q = reinterpret_cast<float4*>(st1 + lane * C::SP + gl * 16);
+          float4* q = reinterpret_cast<float4*>(st1 + lane * SPX + gl * 16);
 #pragma unroll
           for (int j = 0; j < 4; j++)
             q[j] = make_float4(act[4 * j] * sc.inv_s1, act[4 * j + 1] * sc.inv_s1,
@@ -764,10 +778,10 @@ __global__ void __launch_bounds__(Cfg::NT, 1) forward_fused_hp_kernel(fused::Arg
         // 64-byte run per thread touched 32 lines per instruction and bound the whole kernel)
         __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
-          const int pp = it * 4 + (lane >> 3), ck = lane & 7;
+        for (int it = 0; it < LPP; it++) {
+          const int pp = it * (32 / LPP) + lane / LPP, ck = lane % LPP;
           const int pidx = __shfl_sync(0xffffffffu, pix1, pp);
-          const float4 v = *reinterpret_cast<const float4*>(st1 + pp * C::SP + ck * 4);
+          const float4 v = *reinterpret_cast<const float4*>(st1 + pp * SPX + ck * 4);
           if (pidx >= 0)
             *reinterpret_cast<float4*>(bx.out1 + ((size_t)pidx + (size_t)b * w1_row) * C::N1 +
                                        g0 * 16 + ck * 4) = v;
